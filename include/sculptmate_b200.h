@@ -1,0 +1,178 @@
+/* sculptmate_b200 -- C ABI of the B200-native extract_mesh hot path.
+ *
+ * Drop-in boundary for ONE path of shravan-d/SculptMate: TripoSR's
+ * TSR.extract_mesh = dense triplane query (grid_sample x3 -> NeRFMLP) over an
+ * R^3 lattice followed by marching cubes.  The reference is pure Python with no
+ * FFI of its own, so each entry point cites the Python interface it replaces
+ * (paths relative to the reference root); the binding a maintainer would add is
+ * a ctypes stub, shown in INTEGRATION.md and shipped as sculptmate_b200/_capi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*;
+ *   - every `*_dev` / unqualified pointer is DEVICE memory on the current device,
+ *     every `*_host` pointer is host memory;
+ *   - functions return SMB_OK (0) or a negative smb_status; they never throw and
+ *     never synchronise the device unless the name ends in `_host`;
+ *   - all kernels are sm_100a only; there is no CPU fallback.
+ */
+#ifndef SCULPTMATE_B200_H
+#define SCULPTMATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMB_PLANE_CHANNELS 40     /* TripoSR/checkpoints/config.yaml:22-23 (out_channels: 40) */
+#define SMB_HIDDEN 64             /* config.yaml:27 n_neurons */
+#define SMB_MAX_HIDDEN_LAYERS 16  /* config.yaml:28 uses 9 */
+
+typedef enum smb_status {
+  SMB_OK = 0,
+  SMB_ERR_CUDA = -1,        /* a CUDA runtime call or launch failed */
+  SMB_ERR_BAD_ARG = -2,     /* null pointer / non-positive size / unsupported shape */
+  SMB_ERR_WORKSPACE = -3,   /* workspace too small */
+  SMB_ERR_ARCH = -4,        /* device is not sm_100 */
+  SMB_ERR_LEVEL_RANGE = -5, /* iso level outside the data range (skimage: ValueError) */
+  SMB_ERR_NO_SURFACE = -6   /* no triangle produced (skimage: RuntimeError) */
+} smb_status;
+
+const char* smb_status_string(int status);
+/* 0 when the current device is compute capability 10.x, else SMB_ERR_ARCH / SMB_ERR_CUDA. */
+int smb_device_check(void);
+int smb_version(void);
+
+/* ------------------------------------------------------------------ decoder
+ * NeRFMLP weights (tsr/models/network_utils.py:48-79; state-dict keys
+ * layers.{0,2,..,2L}.{weight,bias}) packed once into a device blob that holds
+ * every form the kernels need.  n_hidden = config n_hidden_layers (9):
+ * Linear(120,64)+SiLU, (n_hidden-1) x [Linear(64,64)+SiLU], Linear(64,4).
+ *
+ * weights_host[l] is (out,in) row-major fp32 exactly as nn.Linear stores it,
+ * biases_host[l] is (out) fp32, l = 0..n_hidden (n_hidden+1 layers).
+ */
+typedef struct smb_decoder_layout {
+  uint32_t total_bytes;
+  uint32_t n_hidden;
+  uint32_t off_tc_hidden;  /* (n_hidden-1) x 8192 B: W_l/2, l=1.., fp16, K-major 128B-swizzle UMMA image */
+  uint32_t off_tc_final;   /* 2048 B: last layer padded to 16 rows, fp16, same image format */
+  uint32_t off_tc_l0;      /* 16384 B: W_0/2 padded to K=128 as two [64 x 64] K-blocks (points kernel) */
+  uint32_t off_bias_half;  /* n_hidden x 64 fp32: b_l/2, l = 0..n_hidden-1 */
+  uint32_t off_bias_final; /* 4 fp32 (padded to 16 B) */
+  uint32_t off_w0_half;    /* 64 x 120 fp32: W_0/2 (plane projection for the lattice kernel) */
+  uint32_t off_f32;        /* plain fp32 copy: for each layer W (out,in) then b (out) */
+  uint32_t reserved[7];
+} smb_decoder_layout;
+
+int smb_decoder_layout_for(int n_hidden, smb_decoder_layout* out);
+/* Fills blob_host (layout->total_bytes bytes, host memory); the caller uploads it. */
+int smb_decoder_pack_host(const float* const* weights_host, const float* const* biases_host, int n_hidden,
+                          const smb_decoder_layout* layout, void* blob_host);
+
+/* ------------------------------------------------------------- scene planes
+ * Per scene code (triplane (3,Cp,Hp,Wp) fp32 NCHW, nerf_renderer.py:61-66):
+ *   planes_cl : channels-last copy (3,Hp,Wp,Cp) fp32   -- arbitrary-position query
+ *   planes_q  : layer-0 projection (3,Hp,Wp,64) fp32 = (W_0/2) . plane -- lattice query
+ * (bilinear interpolation is linear, so projecting before interpolating equals
+ * the reference's interpolate-then-Linear in exact arithmetic; it is done in fp32.)
+ */
+int smb_scene_prepare(const float* triplane, int Hp, int Wp, const void* decoder_blob,
+                      const smb_decoder_layout* layout, float* planes_cl, float* planes_q, void* stream);
+
+/* ------------------------------------------------------------- field query
+ * Replaces TriplaneNeRFRenderer.query_triplane (nerf_renderer.py:41-91) for
+ * arbitrary positions.  positions (n,3) fp32 in (-radius, radius); the
+ * (-radius,radius)->(-1,1) rescale (nerf_renderer.py:52-54) happens in-kernel
+ * with the reference's fp32 operation order.  Any output pointer may be NULL.
+ *   density (n), features (n,3), density_act (n) = exp(density+density_bias),
+ *   color (n,3) = sigmoid(features).
+ * fp32 CUDA-core kernel: bit-comparable to the reference within fp32 noise.
+ */
+typedef struct smb_query_cfg {
+  float radius;        /* renderer.cfg.radius (0.87) */
+  float density_bias;  /* renderer.cfg.density_bias (-1.0) */
+  int align_corners;   /* 0 TripoSR (nerf_renderer.py:64), 1 SF3D (sf3d/system.py:193) */
+  int Hp, Wp;          /* plane size */
+} smb_query_cfg;
+
+int smb_query_points_f32(const float* planes_cl, const void* decoder_blob, const smb_decoder_layout* layout,
+                         const smb_query_cfg* cfg, const float* positions, int64_t n, float* density,
+                         float* features, float* density_act, float* color, void* stream);
+
+/* Lattice query = the density half of TSR.extract_mesh (tsr/system.py:171-184):
+ * evaluates density_act on x-planes [x_begin, x_begin+nx) of the R^3 lattice
+ * (row (i*R+j)*R+k = (x_i,y_j,z_k), isosurface.py:25-39) without materialising
+ * positions.  axis_u (R) holds the per-axis sample coordinate already mapped to
+ * (-1,1) by the caller with the reference's own torch ops (linspace ->
+ * scale_tensor -> scale_tensor), so coordinates are bit-identical.
+ * out_density_act: (nx,R,R) fp32.  out_density (optional, may be NULL): raw logit.
+ *   smb_query_lattice_tc  : fused tcgen05 kernel (fp16 operands, fp32 accumulate)
+ *   smb_query_lattice_f32 : fp32 CUDA-core kernel (same result as query_points_f32)
+ */
+/* Scalar fp32 restatement of linspace(0,1,R) -> (-radius,radius) -> (-1,1) for hosts
+ * without torch (within 2 ulp of aten's vectorised linspace; see capi.cu). */
+int smb_lattice_axis_host(int R, float radius, float* axis_u_host);
+
+int smb_query_lattice_tc(const float* planes_q, const void* decoder_blob, const smb_decoder_layout* layout,
+                         const smb_query_cfg* cfg, const float* axis_u, int R, int x_begin, int nx,
+                         float* out_density_act, float* out_density, void* stream);
+int smb_query_lattice_f32(const float* planes_cl, const void* decoder_blob, const smb_decoder_layout* layout,
+                          const smb_query_cfg* cfg, const float* axis_u, int R, int x_begin, int nx,
+                          float* out_density_act, float* out_density, void* stream);
+
+/* ---------------------------------------------------------- marching cubes
+ * Replaces MarchingCubeHelper.forward (tsr/models/isosurface.py:41-54), i.e.
+ * skimage.measure.marching_cubes(level, 0.0) + the wrapper's post-processing,
+ * on a slab of x-planes.  val(p) = (grid[p] - sub) * sign, surface at val = 0,
+ * case bit = val > 0.  Output order is canonical and deterministic:
+ * vertices by (x-plane; in-plane edges by (j,k,axis); then x-edges by (j,k)),
+ * triangles by (cell, table order).  Two calls: count, then emit.
+ */
+#define SMB_MC_FLIP 1    /* faces[:, [1,0,2]]            isosurface.py:52 */
+#define SMB_MC_DIV 2     /* verts / vdiv (IEEE fp32)     isosurface.py:53 */
+#define SMB_MC_AFFINE 4  /* verts * vmul + vadd          system.py:185-189 */
+
+typedef struct smb_mc_counts {
+  int64_t nverts;          /* vertices this slab stores */
+  int64_t ntris;           /* triangles this slab stores */
+  int64_t nverts_numbered; /* nverts + in-plane crossings of the last plane when not emitted */
+  int64_t reserved;
+} smb_mc_counts;
+
+size_t smb_mc_workspace_bytes(int nx, int ny, int nz);
+/* counts_dev: device smb_mc_counts written by the stream; copy it back to size the outputs. */
+int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub, float sign, int emit_last_plane,
+                 void* workspace, size_t workspace_bytes, smb_mc_counts* counts_dev, void* stream);
+/* Must follow smb_mc_count on the same grid/workspace.  vertex_id_offset is added to
+ * every face index (running vertex count of the lower slabs); x_origin is the global
+ * index of the slab's first plane.  verts (nverts,3) fp32, faces (ntris,3) int64. */
+int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                int emit_last_plane, int flags, float vdiv, float vmul, float vadd, int64_t vertex_id_offset,
+                const void* workspace, float* verts, int64_t* faces, void* stream);
+/* cube-case index of every cell, (nx-1,ny-1,nz-1) uint8 (parity/debug). */
+int smb_mc_cases(const float* grid, int nx, int ny, int nz, float sub, float sign, unsigned char* cases,
+                 void* stream);
+/* min/max of val over the grid -> minmax_dev[2]; used to tell SMB_ERR_LEVEL_RANGE from SMB_ERR_NO_SURFACE. */
+int smb_grid_minmax(const float* grid, int64_t n, float sub, float sign, float* minmax_dev, void* stream);
+
+/* ------------------------------------------------- whole path, host buffers
+ * TSR.extract_mesh for one scene code with HOST inputs and outputs
+ * (tsr/system.py:171-200 minus the Blender import): uploads the triplane,
+ * runs prepare -> lattice query (tensor cores) -> marching cubes, downloads
+ * the mesh.  Synchronises the stream.  The mesh is returned in buffers owned by
+ * the handle and valid until the next call / smb_extractor_destroy.
+ */
+typedef struct smb_extractor smb_extractor;
+int smb_extractor_create(const float* const* weights_host, const float* const* biases_host, int n_hidden,
+                         float radius, float density_bias, int Hp, int Wp, smb_extractor** out);
+void smb_extractor_destroy(smb_extractor* ex);
+int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int resolution, float threshold,
+                          const float** verts_host, const int64_t** faces_host, int64_t* nverts,
+                          int64_t* ntris);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCULPTMATE_B200_H */

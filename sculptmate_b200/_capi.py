@@ -1,0 +1,129 @@
+"""ctypes binding of ``include/sculptmate_b200.h`` (the C ABI of the CUDA library).
+
+This is the stub a maintainer of the reference would add.
+There is no CPU fallback: if the shared library is missing, ``load()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_ubyte, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsculptmate_b200.so")
+
+OK = 0
+ERR_CUDA, ERR_BAD_ARG, ERR_WORKSPACE, ERR_ARCH, ERR_LEVEL_RANGE, ERR_NO_SURFACE = -1, -2, -3, -4, -5, -6
+MC_FLIP, MC_DIV, MC_AFFINE = 1, 2, 4
+
+
+class DecoderLayout(ctypes.Structure):
+    _fields_ = [
+        ("total_bytes", c_uint32),
+        ("n_hidden", c_uint32),
+        ("off_tc_hidden", c_uint32),
+        ("off_tc_final", c_uint32),
+        ("off_tc_l0", c_uint32),
+        ("off_bias_half", c_uint32),
+        ("off_bias_final", c_uint32),
+        ("off_w0_half", c_uint32),
+        ("off_f32", c_uint32),
+        ("reserved", c_uint32 * 7),
+    ]
+
+
+class QueryCfg(ctypes.Structure):
+    _fields_ = [
+        ("radius", c_float),
+        ("density_bias", c_float),
+        ("align_corners", c_int),
+        ("Hp", c_int),
+        ("Wp", c_int),
+    ]
+
+
+class McCounts(ctypes.Structure):
+    _fields_ = [
+        ("nverts", c_int64),
+        ("ntris", c_int64),
+        ("nverts_numbered", c_int64),
+        ("reserved", c_int64),
+    ]
+
+
+# every symbol include/sculptmate_b200.h declares: name -> (restype, argtypes)
+_FLOATPP = POINTER(POINTER(c_float))
+SIGNATURES = {
+    "smb_status_string": (c_char_p, [c_int]),
+    "smb_device_check": (c_int, []),
+    "smb_version": (c_int, []),
+    "smb_decoder_layout_for": (c_int, [c_int, POINTER(DecoderLayout)]),
+    "smb_decoder_pack_host": (c_int, [_FLOATPP, _FLOATPP, c_int, POINTER(DecoderLayout), c_void_p]),
+    "smb_scene_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(DecoderLayout), c_void_p, c_void_p, c_void_p]),
+    "smb_query_points_f32": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "smb_lattice_axis_host": (c_int, [c_int, c_float, POINTER(c_float)]),
+    "smb_query_lattice_tc": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    ),
+    "smb_query_lattice_f32": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    ),
+    "smb_mc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "smb_mc_count": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "smb_mc_emit": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "smb_mc_cases": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "smb_grid_minmax": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "smb_extractor_create": (c_int, [_FLOATPP, _FLOATPP, c_int, c_float, c_float, c_int, c_int, POINTER(c_void_p)]),
+    "smb_extractor_destroy": (None, [c_void_p]),
+    "smb_extract_mesh_host": (
+        c_int,
+        [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],
+    ),
+}
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library.  Raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is missing: build it with `python -m sculptmate_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def status_string(rc: int) -> str:
+    return load().smb_status_string(rc).decode()
+
+
+class SmbError(RuntimeError):
+    def __init__(self, rc: int, where: str):
+        self.rc = rc
+        super().__init__(f"{where}: {status_string(rc)} (status {rc})")
+
+
+def check(rc: int, where: str) -> None:
+    if rc != OK:
+        raise SmbError(rc, where)

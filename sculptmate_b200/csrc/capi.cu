@@ -1,0 +1,343 @@
+// Host side of the C ABI: status strings, decoder packing, lattice coordinates and
+// the host-buffer extractor (the whole TSR.extract_mesh path for one scene code,
+// /root/reference/TripoSR/tsr/system.py:171-200 minus the Blender import).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "field_common.cuh"
+#include "ptx_sm100.cuh"
+
+using namespace smb;
+
+extern "C" const char* smb_status_string(int status) {
+  switch (status) {
+    case SMB_OK: return "ok";
+    case SMB_ERR_CUDA: return "CUDA runtime error";
+    case SMB_ERR_BAD_ARG: return "bad argument";
+    case SMB_ERR_WORKSPACE: return "workspace too small";
+    case SMB_ERR_ARCH: return "device is not sm_100 (B200)";
+    case SMB_ERR_LEVEL_RANGE: return "Surface level must be within volume data range.";
+    case SMB_ERR_NO_SURFACE: return "No surface found at the given iso value.";
+  }
+  return "unknown status";
+}
+
+extern "C" int smb_version(void) { return 100; }
+
+extern "C" int smb_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SMB_ERR_CUDA;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return SMB_ERR_CUDA;
+  return major == 10 ? SMB_OK : SMB_ERR_ARCH;
+}
+
+// ------------------------------------------------------------------ decoder
+static uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+extern "C" int smb_decoder_layout_for(int n_hidden, smb_decoder_layout* out) {
+  if (!out || n_hidden < 2 || n_hidden > kMaxHidden) return SMB_ERR_BAD_ARG;
+  memset(out, 0, sizeof(*out));
+  uint32_t off = 0;
+  out->n_hidden = (uint32_t)n_hidden;
+  // [hidden | head | bias_half | bias_final] must stay contiguous (field_tc.cu stages them with one bulk-copy run)
+  out->off_tc_hidden = off;
+  off += (uint32_t)(n_hidden - 1) * 8192u;
+  out->off_tc_final = off;
+  off += 2048u;
+  out->off_bias_half = off;
+  off += (uint32_t)n_hidden * kHid * 4u;
+  out->off_bias_final = off;
+  off += 16u;
+  off = (off + 1023u) & ~1023u;
+  out->off_tc_l0 = off;
+  off += 16384u;
+  out->off_w0_half = off;
+  off += kHid * kFeat * 4u;
+  out->off_f32 = align16(off);
+  off = out->off_f32;
+  off += (kHid * kFeat + kHid) * 4u;
+  off += (uint32_t)(n_hidden - 1) * (kHid * kHid + kHid) * 4u;
+  off += (kOut * kHid + kOut) * 4u;
+  out->total_bytes = align16(off);
+  return SMB_OK;
+}
+
+static void put_half(unsigned char* img, uint32_t byte_off, float v) {
+  __half h = __float2half_rn(v);
+  memcpy(img + byte_off, &h, 2);
+}
+
+extern "C" int smb_decoder_pack_host(const float* const* W, const float* const* B, int n_hidden,
+                                     const smb_decoder_layout* L, void* blob_host) {
+  if (!W || !B || !L || !blob_host || n_hidden != (int)L->n_hidden) return SMB_ERR_BAD_ARG;
+  for (int l = 0; l <= n_hidden; ++l)
+    if (!W[l] || !B[l]) return SMB_ERR_BAD_ARG;
+  unsigned char* blob = static_cast<unsigned char*>(blob_host);
+  memset(blob, 0, L->total_bytes);
+  // hidden layers 1..n_hidden-1: B operand [n][k] = W_l[n][k] / 2, K-major SW128 image
+  for (int l = 1; l < n_hidden; ++l) {
+    unsigned char* img = blob + L->off_tc_hidden + (size_t)(l - 1) * 8192;
+    for (int n = 0; n < kHid; ++n)
+      for (int k = 0; k < kHid; ++k) put_half(img, sw128_offset(n, k), 0.5f * W[l][n * kHid + k]);
+  }
+  {  // head: rows 0..3 = W_L (not halved: no SiLU after it), rows 4..15 zero
+    unsigned char* img = blob + L->off_tc_final;
+    for (int n = 0; n < kOut; ++n)
+      for (int k = 0; k < kHid; ++k) put_half(img, sw128_offset(n, k), W[n_hidden][n * kHid + k]);
+  }
+  {  // layer 0 padded to K = 128 as two 64-wide K blocks
+    unsigned char* img = blob + L->off_tc_l0;
+    for (int n = 0; n < kHid; ++n)
+      for (int k = 0; k < kFeat; ++k)
+        put_half(img + (size_t)(k / 64) * 8192, sw128_offset(n, k % 64), 0.5f * W[0][n * kFeat + k]);
+  }
+  float* bh = reinterpret_cast<float*>(blob + L->off_bias_half);
+  for (int l = 0; l < n_hidden; ++l)
+    for (int n = 0; n < kHid; ++n) bh[l * kHid + n] = 0.5f * B[l][n];
+  float* bf = reinterpret_cast<float*>(blob + L->off_bias_final);
+  for (int n = 0; n < kOut; ++n) bf[n] = B[n_hidden][n];
+  float* w0h = reinterpret_cast<float*>(blob + L->off_w0_half);
+  for (int t = 0; t < kHid * kFeat; ++t) w0h[t] = 0.5f * W[0][t];
+  float* f = reinterpret_cast<float*>(blob + L->off_f32);
+  for (int l = 0; l <= n_hidden; ++l) {
+    const int out = (l == n_hidden) ? kOut : kHid;
+    const int in = (l == 0) ? kFeat : kHid;
+    memcpy(f, W[l], sizeof(float) * out * in);
+    f += out * in;
+    memcpy(f, B[l], sizeof(float) * out);
+    f += out;
+  }
+  return SMB_OK;
+}
+
+// ------------------------------------------------------- lattice coordinates
+// Per-axis sample coordinate of the R-lattice mapped to (-1,1): a scalar IEEE fp32
+// restatement of what the reference computes with torch ops:
+//   torch.linspace(0, 1, R)                              isosurface.py:30-32
+//   scale_tensor(., (0,1), (-radius, radius))            system.py:177-181
+//   scale_tensor(., (-radius, radius), (-1, 1))          nerf_renderer.py:52-54
+// aten's CPU linspace is vectorised (base + step*lane per SIMD vector), so its values
+// differ from this scalar form by <= 2 ulp at a few indices, depending on the host's
+// SIMD width; the Python host therefore builds axis_u with torch itself, and this
+// function serves non-Python hosts (tests/test_capi_host.py bounds the difference).
+extern "C" int smb_lattice_axis_host(int R, float radius, float* axis_u_host) {
+  if (R < 1 || !axis_u_host) return SMB_ERR_BAD_ARG;
+  const double r = (double)radius;
+  const float a_sub = 0.0f, a_div = (float)(1.0 - 0.0), a_mul = (float)(r - (-r)), a_add = (float)(-r);
+  const float b_sub = (float)(-r), b_div = (float)(r - (-r)), b_mul = (float)(1.0 - (-1.0)), b_add = -1.0f;
+  const float step = R > 1 ? (1.0f - 0.0f) / (float)(R - 1) : 0.0f;
+  for (int i = 0; i < R; ++i) {
+    volatile float t;
+    if (R == 1) {
+      t = 0.0f;
+    } else if (i < R / 2) {
+      volatile float m = step * (float)i;
+      t = 0.0f + m;
+    } else {
+      volatile float m = step * (float)(R - 1 - i);
+      t = 1.0f - m;
+    }
+    volatile float v = t - a_sub;
+    v = v / a_div;
+    v = v * a_mul;
+    v = v + a_add;
+    v = v - b_sub;
+    v = v / b_div;
+    v = v * b_mul;
+    v = v + b_add;
+    axis_u_host[i] = v;
+  }
+  return SMB_OK;
+}
+
+// --------------------------------------------------------------- extractor
+struct smb_extractor {
+  smb_decoder_layout layout;
+  smb_query_cfg cfg;
+  void* blob_dev = nullptr;
+  float* triplane_dev = nullptr;
+  float* planes_q = nullptr;
+  float* axis_dev = nullptr;
+  float* density = nullptr;
+  void* mc_ws = nullptr;
+  smb_mc_counts* counts_dev = nullptr;
+  float* verts_dev = nullptr;
+  int64_t* faces_dev = nullptr;
+  float* minmax_dev = nullptr;
+  // pinned host staging
+  float* triplane_pin = nullptr;
+  smb_mc_counts* counts_pin = nullptr;
+  float* verts_pin = nullptr;
+  int64_t* faces_pin = nullptr;
+  float* minmax_pin = nullptr;
+  size_t verts_cap = 0, faces_cap = 0, verts_pin_cap = 0, faces_pin_cap = 0;
+  size_t mc_ws_bytes = 0;
+  int res = 0;
+  cudaStream_t stream = nullptr;
+};
+
+#define EX_CUDA(call)                        \
+  do {                                       \
+    if ((call) != cudaSuccess) return SMB_ERR_CUDA; \
+  } while (0)
+
+extern "C" int smb_extractor_create(const float* const* W, const float* const* B, int n_hidden, float radius,
+                                    float density_bias, int Hp, int Wp, smb_extractor** out) {
+  if (!out || Hp <= 0 || Wp <= 0) return SMB_ERR_BAD_ARG;
+  int rc = smb_device_check();
+  if (rc != SMB_OK) return rc;
+  smb_extractor* ex = new smb_extractor();
+  rc = smb_decoder_layout_for(n_hidden, &ex->layout);
+  if (rc != SMB_OK) {
+    delete ex;
+    return rc;
+  }
+  std::vector<unsigned char> blob(ex->layout.total_bytes);
+  rc = smb_decoder_pack_host(W, B, n_hidden, &ex->layout, blob.data());
+  if (rc != SMB_OK) {
+    delete ex;
+    return rc;
+  }
+  ex->cfg.radius = radius;
+  ex->cfg.density_bias = density_bias;
+  ex->cfg.align_corners = 0;
+  ex->cfg.Hp = Hp;
+  ex->cfg.Wp = Wp;
+  const size_t tp_bytes = (size_t)3 * kCp * Hp * Wp * sizeof(float);
+  bool ok = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc(&ex->blob_dev, blob.size()) == cudaSuccess &&
+            cudaMalloc(&ex->triplane_dev, tp_bytes) == cudaSuccess &&
+            cudaMalloc(&ex->planes_q, (size_t)3 * Hp * Wp * kHid * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&ex->counts_dev, sizeof(smb_mc_counts)) == cudaSuccess &&
+            cudaMalloc(&ex->minmax_dev, 2 * sizeof(float)) == cudaSuccess &&
+            cudaMallocHost(&ex->triplane_pin, tp_bytes) == cudaSuccess &&
+            cudaMallocHost(&ex->counts_pin, sizeof(smb_mc_counts)) == cudaSuccess &&
+            cudaMallocHost(&ex->minmax_pin, 2 * sizeof(float)) == cudaSuccess &&
+            cudaMemcpy(ex->blob_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) {
+    smb_extractor_destroy(ex);
+    return SMB_ERR_CUDA;
+  }
+  *out = ex;
+  return SMB_OK;
+}
+
+extern "C" void smb_extractor_destroy(smb_extractor* ex) {
+  if (!ex) return;
+  cudaFree(ex->blob_dev);
+  cudaFree(ex->triplane_dev);
+  cudaFree(ex->planes_q);
+  cudaFree(ex->axis_dev);
+  cudaFree(ex->density);
+  cudaFree(ex->mc_ws);
+  cudaFree(ex->counts_dev);
+  cudaFree(ex->verts_dev);
+  cudaFree(ex->faces_dev);
+  cudaFree(ex->minmax_dev);
+  cudaFreeHost(ex->triplane_pin);
+  cudaFreeHost(ex->counts_pin);
+  cudaFreeHost(ex->verts_pin);
+  cudaFreeHost(ex->faces_pin);
+  cudaFreeHost(ex->minmax_pin);
+  if (ex->stream) cudaStreamDestroy(ex->stream);
+  delete ex;
+}
+
+static int ensure_resolution(smb_extractor* ex, int R) {
+  // per-resolution workspaces are cached like the reference caches its helper
+  // (system.py:118-124 set_marching_cubes_resolution)
+  if (ex->res == R) return SMB_OK;
+  cudaFree(ex->axis_dev);
+  cudaFree(ex->density);
+  cudaFree(ex->mc_ws);
+  ex->axis_dev = nullptr;
+  ex->density = nullptr;
+  ex->mc_ws = nullptr;
+  ex->res = 0;
+  std::vector<float> axis(R);
+  int rc = smb_lattice_axis_host(R, ex->cfg.radius, axis.data());
+  if (rc != SMB_OK) return rc;
+  ex->mc_ws_bytes = smb_mc_workspace_bytes(R, R, R);
+  EX_CUDA(cudaMalloc(&ex->axis_dev, sizeof(float) * R));
+  EX_CUDA(cudaMalloc(&ex->density, sizeof(float) * (size_t)R * R * R));
+  EX_CUDA(cudaMalloc(&ex->mc_ws, ex->mc_ws_bytes));
+  EX_CUDA(cudaMemcpy(ex->axis_dev, axis.data(), sizeof(float) * R, cudaMemcpyHostToDevice));
+  ex->res = R;
+  return SMB_OK;
+}
+
+extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int R, float threshold,
+                                     const float** verts_host, const int64_t** faces_host, int64_t* nverts,
+                                     int64_t* ntris) {
+  if (!ex || !triplane_host || R < 2 || !verts_host || !faces_host || !nverts || !ntris) return SMB_ERR_BAD_ARG;
+  int rc = ensure_resolution(ex, R);
+  if (rc != SMB_OK) return rc;
+  cudaStream_t st = ex->stream;
+  const size_t tp_bytes = (size_t)3 * kCp * ex->cfg.Hp * ex->cfg.Wp * sizeof(float);
+  memcpy(ex->triplane_pin, triplane_host, tp_bytes);
+  EX_CUDA(cudaMemcpyAsync(ex->triplane_dev, ex->triplane_pin, tp_bytes, cudaMemcpyHostToDevice, st));
+  rc = smb_scene_prepare(ex->triplane_dev, ex->cfg.Hp, ex->cfg.Wp, ex->blob_dev, &ex->layout, nullptr, ex->planes_q, st);
+  if (rc != SMB_OK) return rc;
+  rc = smb_query_lattice_tc(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, 0, R, ex->density,
+                            nullptr, st);
+  if (rc != SMB_OK) return rc;
+  // system.py:184  helper(-(density - threshold))  ->  level = density - threshold, iso 0
+  rc = smb_mc_count(ex->density, R, R, R, threshold, 1.0f, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
+  if (rc != SMB_OK) return rc;
+  EX_CUDA(cudaMemcpyAsync(ex->counts_pin, ex->counts_dev, sizeof(smb_mc_counts), cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaStreamSynchronize(st));
+  const int64_t V = ex->counts_pin->nverts, F = ex->counts_pin->ntris;
+  if (V == 0 || F == 0) {
+    rc = smb_grid_minmax(ex->density, (int64_t)R * R * R, threshold, 1.0f, ex->minmax_dev, st);
+    if (rc != SMB_OK) return rc;
+    EX_CUDA(cudaMemcpyAsync(ex->minmax_pin, ex->minmax_dev, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    EX_CUDA(cudaStreamSynchronize(st));
+    *nverts = 0;
+    *ntris = 0;
+    if (ex->minmax_pin[0] > 0.0f || ex->minmax_pin[1] < 0.0f) return SMB_ERR_LEVEL_RANGE;
+    return SMB_ERR_NO_SURFACE;
+  }
+  if ((size_t)V > ex->verts_cap) {
+    cudaFree(ex->verts_dev);
+    ex->verts_cap = 0;
+    EX_CUDA(cudaMalloc(&ex->verts_dev, sizeof(float) * 3 * (size_t)V * 5 / 4));
+    ex->verts_cap = (size_t)V * 5 / 4;
+  }
+  if ((size_t)F > ex->faces_cap) {
+    cudaFree(ex->faces_dev);
+    ex->faces_cap = 0;
+    EX_CUDA(cudaMalloc(&ex->faces_dev, sizeof(int64_t) * 3 * (size_t)F * 5 / 4));
+    ex->faces_cap = (size_t)F * 5 / 4;
+  }
+  if ((size_t)V > ex->verts_pin_cap) {
+    cudaFreeHost(ex->verts_pin);
+    ex->verts_pin_cap = 0;
+    EX_CUDA(cudaMallocHost(&ex->verts_pin, sizeof(float) * 3 * (size_t)V * 5 / 4));
+    ex->verts_pin_cap = (size_t)V * 5 / 4;
+  }
+  if ((size_t)F > ex->faces_pin_cap) {
+    cudaFreeHost(ex->faces_pin);
+    ex->faces_pin_cap = 0;
+    EX_CUDA(cudaMallocHost(&ex->faces_pin, sizeof(int64_t) * 3 * (size_t)F * 5 / 4));
+    ex->faces_pin_cap = (size_t)F * 5 / 4;
+  }
+  // isosurface.py:52-53 (flip, /(R-1)) and system.py:185-189 (scale to +-radius)
+  const double r = (double)ex->cfg.radius;
+  rc = smb_mc_emit(ex->density, R, R, R, threshold, 1.0f, 0, 1, SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE,
+                   (float)(R - 1.0), (float)(r - (-r)), (float)(-r), 0, ex->mc_ws, ex->verts_dev, ex->faces_dev, st);
+  if (rc != SMB_OK) return rc;
+  EX_CUDA(cudaMemcpyAsync(ex->verts_pin, ex->verts_dev, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaMemcpyAsync(ex->faces_pin, ex->faces_dev, sizeof(int64_t) * 3 * F, cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaStreamSynchronize(st));
+  *verts_host = ex->verts_pin;
+  *faces_host = ex->faces_pin;
+  *nverts = V;
+  *ntris = F;
+  return SMB_OK;
+}

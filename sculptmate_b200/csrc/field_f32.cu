@@ -1,0 +1,313 @@
+// fp32 CUDA-core field kernels:
+//   * scene preparation (channels-last planes, layer-0 projected planes),
+//   * query_points_f32 / query_lattice_f32: one thread per sample, bilinear gather
+//     from channels-last planes + the NeRFMLP chain in fp32 with weights staged in
+//     shared memory.  This is the reference-precision path (arbitrary positions,
+//     colour query, parity anchor for the tensor-core kernel), not the fast path.
+//
+// Reference semantics (relative to /root/reference):
+//   TripoSR/tsr/models/nerf_renderer.py:41-91  (plane pairing, grid_sample, exp/sigmoid)
+//   TripoSR/tsr/models/network_utils.py:116-124 (Linear/SiLU chain; out[0]=density, out[1:4]=features)
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "field_common.cuh"
+
+namespace smb {
+
+// ---------------------------------------------------------------- prepare
+// NCHW (3,Cp,H,W) -> channels-last (3,H,W,Cp)
+__global__ void planes_to_channels_last(const float* __restrict__ src, float* __restrict__ dst, int H, int W) {
+  const int HW = H * W;
+  const long long total = 3LL * HW * kCp;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(t % kCp);
+    long long r = t / kCp;
+    int hw = (int)(r % HW);
+    int p = (int)(r / HW);
+    dst[t] = src[((long long)p * kCp + c) * HW + hw];
+  }
+}
+
+// planes_q[p][h][w][n] = sum_c (W0/2)[n][p*Cp + c] * plane[p][c][h][w]   (fp32)
+__global__ void project_planes(const float* __restrict__ src, const float* __restrict__ w0_half,
+                               float* __restrict__ dst, int H, int W) {
+  __shared__ float sW[kHid * kCp];  // this plane's (64 x 40) slice of W0/2
+  const int p = blockIdx.y;
+  for (int t = threadIdx.x; t < kHid * kCp; t += blockDim.x) {
+    int n = t / kCp, c = t % kCp;
+    sW[t] = w0_half[n * kFeat + p * kCp + c];
+  }
+  __syncthreads();
+  const int HW = H * W;
+  const int n = threadIdx.x & (kHid - 1);
+  const int sub = threadIdx.x >> 6;  // texels per block iteration = blockDim/64
+  const int per = blockDim.x >> 6;
+  for (int hw = blockIdx.x * per + sub; hw < HW; hw += gridDim.x * per) {
+    const float* s = src + (long long)p * kCp * HW + hw;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int c = 0; c < kCp; ++c) acc = fmaf(sW[n * kCp + c], s[(long long)c * HW], acc);
+    dst[((long long)p * HW + hw) * kHid + n] = acc;
+  }
+}
+
+// ------------------------------------------------------------- fp32 query
+struct F32Params {
+  const float* planes_cl;  // (3,H,W,Cp)
+  const float* wts;        // fp32 section of the decoder blob
+  int n_hidden;
+  int H, W, align_corners;
+  float density_bias;
+  PosScale ps;
+  // arbitrary positions
+  const float* positions;  // (n,3) or nullptr for lattice mode
+  long long n;
+  // lattice mode
+  const float* axis_u;
+  int R, x_begin;
+  float *density, *features, *density_act, *color;
+};
+
+__device__ __forceinline__ void gather_plane(const float* __restrict__ plane, int H, int W, int align, float u,
+                                             float v, float* __restrict__ f /*[kCp]*/) {
+  // u -> W axis, v -> H axis (grid_sample's grid[...,0] is x/width)
+  Tap2 tx = make_tap(u, W, align);
+  Tap2 ty = make_tap(v, H, align);
+  const float4* p00 = reinterpret_cast<const float4*>(plane + ((long long)ty.i0 * W + tx.i0) * kCp);
+  const float4* p01 = reinterpret_cast<const float4*>(plane + ((long long)ty.i0 * W + tx.i1) * kCp);
+  const float4* p10 = reinterpret_cast<const float4*>(plane + ((long long)ty.i1 * W + tx.i0) * kCp);
+  const float4* p11 = reinterpret_cast<const float4*>(plane + ((long long)ty.i1 * W + tx.i1) * kCp);
+  const float w00 = ty.w0 * tx.w0, w01 = ty.w0 * tx.w1, w10 = ty.w1 * tx.w0, w11 = ty.w1 * tx.w1;
+#pragma unroll
+  for (int c4 = 0; c4 < kCp / 4; ++c4) {
+    float4 a = __ldg(p00 + c4), b = __ldg(p01 + c4), c = __ldg(p10 + c4), d = __ldg(p11 + c4);
+    f[4 * c4 + 0] = a.x * w00 + b.x * w01 + c.x * w10 + d.x * w11;
+    f[4 * c4 + 1] = a.y * w00 + b.y * w01 + c.y * w10 + d.y * w11;
+    f[4 * c4 + 2] = a.z * w00 + b.z * w01 + c.z * w10 + d.z * w11;
+    f[4 * c4 + 3] = a.w * w00 + b.w * w01 + c.w * w10 + d.w * w11;
+  }
+}
+
+__device__ __forceinline__ float silu_f32(float x) { return x / (1.0f + expf(-x)); }
+
+// One thread per sample.  Weights live in shared memory (<= 163 KB for 9 hidden
+// layers); all lanes read the same weight -> broadcast LDS.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) query_f32_kernel(F32Params p) {
+  extern __shared__ __align__(16) float sw[];
+  // fp32 section layout: for l in 0..n_hidden: W_l (out,in) then b_l (out)
+  int total = kHid * kFeat + kHid;
+  total += (p.n_hidden - 1) * (kHid * kHid + kHid);
+  total += kOut * kHid + kOut;
+  for (int t = threadIdx.x; t < total; t += kThreads) sw[t] = p.wts[t];
+  __syncthreads();
+
+  const long long RR = (long long)p.R * p.R;
+  for (long long s = blockIdx.x * (long long)kThreads + threadIdx.x; s < p.n;
+       s += (long long)gridDim.x * kThreads) {
+    float ux, uy, uz;
+    if (p.positions) {
+      ux = scale_pos(p.positions[3 * s + 0], p.ps);
+      uy = scale_pos(p.positions[3 * s + 1], p.ps);
+      uz = scale_pos(p.positions[3 * s + 2], p.ps);
+    } else {
+      int i = (int)(s / RR);
+      int rem = (int)(s - (long long)i * RR);
+      int j = rem / p.R, k = rem - j * p.R;
+      ux = p.axis_u[p.x_begin + i];
+      uy = p.axis_u[j];
+      uz = p.axis_u[k];
+    }
+    float act[kHid];
+    float nxt[kHid];
+    {
+      float f[kFeat];
+      const long long psz = (long long)p.H * p.W * kCp;
+      gather_plane(p.planes_cl + 0 * psz, p.H, p.W, p.align_corners, ux, uy, f + 0 * kCp);
+      gather_plane(p.planes_cl + 1 * psz, p.H, p.W, p.align_corners, ux, uz, f + 1 * kCp);
+      gather_plane(p.planes_cl + 2 * psz, p.H, p.W, p.align_corners, uy, uz, f + 2 * kCp);
+      const float* W = sw;
+      const float* b = sw + kHid * kFeat;
+      for (int n = 0; n < kHid; ++n) {
+        float acc = b[n];
+        const float4* wr = reinterpret_cast<const float4*>(W + n * kFeat);
+#pragma unroll
+        for (int k4 = 0; k4 < kFeat / 4; ++k4) {
+          float4 w = wr[k4];
+          acc = fmaf(w.x, f[4 * k4 + 0], acc);
+          acc = fmaf(w.y, f[4 * k4 + 1], acc);
+          acc = fmaf(w.z, f[4 * k4 + 2], acc);
+          acc = fmaf(w.w, f[4 * k4 + 3], acc);
+        }
+        nxt[n] = silu_f32(acc);
+      }
+#pragma unroll
+      for (int n = 0; n < kHid; ++n) act[n] = nxt[n];
+    }
+    const float* base = sw + kHid * kFeat + kHid;
+    for (int l = 1; l < p.n_hidden; ++l) {
+      const float* W = base;
+      const float* b = base + kHid * kHid;
+      for (int n = 0; n < kHid; ++n) {
+        float acc = b[n];
+        const float4* wr = reinterpret_cast<const float4*>(W + n * kHid);
+#pragma unroll
+        for (int k4 = 0; k4 < kHid / 4; ++k4) {
+          float4 w = wr[k4];
+          acc = fmaf(w.x, act[4 * k4 + 0], acc);
+          acc = fmaf(w.y, act[4 * k4 + 1], acc);
+          acc = fmaf(w.z, act[4 * k4 + 2], acc);
+          acc = fmaf(w.w, act[4 * k4 + 3], acc);
+        }
+        nxt[n] = silu_f32(acc);
+      }
+#pragma unroll
+      for (int n = 0; n < kHid; ++n) act[n] = nxt[n];
+      base += kHid * kHid + kHid;
+    }
+    float o[kOut];
+    {
+      const float* W = base;
+      const float* b = base + kOut * kHid;
+#pragma unroll
+      for (int n = 0; n < kOut; ++n) {
+        float acc = b[n];
+        const float4* wr = reinterpret_cast<const float4*>(W + n * kHid);
+#pragma unroll
+        for (int k4 = 0; k4 < kHid / 4; ++k4) {
+          float4 w = wr[k4];
+          acc = fmaf(w.x, act[4 * k4 + 0], acc);
+          acc = fmaf(w.y, act[4 * k4 + 1], acc);
+          acc = fmaf(w.z, act[4 * k4 + 2], acc);
+          acc = fmaf(w.w, act[4 * k4 + 3], acc);
+        }
+        o[n] = acc;
+      }
+    }
+    if (p.density) p.density[s] = o[0];
+    if (p.density_act) p.density_act[s] = expf(__fadd_rn(o[0], p.density_bias));
+    if (p.features) {
+      p.features[3 * s + 0] = o[1];
+      p.features[3 * s + 1] = o[2];
+      p.features[3 * s + 2] = o[3];
+    }
+    if (p.color) {
+      p.color[3 * s + 0] = 1.0f / (1.0f + expf(-o[1]));
+      p.color[3 * s + 1] = 1.0f / (1.0f + expf(-o[2]));
+      p.color[3 * s + 2] = 1.0f / (1.0f + expf(-o[3]));
+    }
+  }
+}
+
+static int f32_smem_bytes(int n_hidden) {
+  int total = kHid * kFeat + kHid + (n_hidden - 1) * (kHid * kHid + kHid) + kOut * kHid + kOut;
+  return total * (int)sizeof(float);
+}
+
+static int launch_f32(const F32Params& p, cudaStream_t st) {
+  constexpr int kThreads = 128;
+  int smem = f32_smem_bytes(p.n_hidden);
+  if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
+  cudaError_t e =
+      cudaFuncSetAttribute(query_f32_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return SMB_ERR_CUDA;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (p.n + kThreads - 1) / kThreads;
+  if (blocks > sms) blocks = sms;  // persistent: weights are staged once per CTA
+  if (blocks < 1) return SMB_OK;
+  query_f32_kernel<kThreads><<<(unsigned)blocks, kThreads, smem, st>>>(p);
+  return smb_check(cudaGetLastError());
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" int smb_scene_prepare(const float* triplane, int Hp, int Wp, const void* decoder_blob,
+                                 const smb_decoder_layout* layout, float* planes_cl, float* planes_q,
+                                 void* stream) {
+  if (!triplane || Hp <= 0 || Wp <= 0 || (!planes_cl && !planes_q)) return SMB_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (planes_cl) {
+    planes_to_channels_last<<<296, 256, 0, st>>>(triplane, planes_cl, Hp, Wp);
+    if (cudaGetLastError() != cudaSuccess) return SMB_ERR_CUDA;
+  }
+  if (planes_q) {
+    if (!decoder_blob || !layout) return SMB_ERR_BAD_ARG;
+    const float* w0h = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_w0_half);
+    int per = 256 / kHid;
+    int gx = (Hp * Wp + per - 1) / per;
+    if (gx > 1024) gx = 1024;
+    project_planes<<<dim3(gx, 3), 256, 0, st>>>(triplane, w0h, planes_q, Hp, Wp);
+    if (cudaGetLastError() != cudaSuccess) return SMB_ERR_CUDA;
+  }
+  return SMB_OK;
+}
+
+static PosScale make_pos_scale(float radius) {
+  // scale_tensor(positions, (-r, r), (-1, 1)) with python-float scales (utils.py:228-230)
+  PosScale ps;
+  double r = (double)radius;
+  ps.sub = (float)(-r);
+  ps.div = (float)(r - (-r));
+  ps.mul = (float)(1.0 - (-1.0));
+  ps.add = -1.0f;
+  return ps;
+}
+
+extern "C" int smb_query_points_f32(const float* planes_cl, const void* decoder_blob,
+                                    const smb_decoder_layout* layout, const smb_query_cfg* cfg,
+                                    const float* positions, int64_t n, float* density, float* features,
+                                    float* density_act, float* color, void* stream) {
+  if (!planes_cl || !decoder_blob || !layout || !cfg || n < 0) return SMB_ERR_BAD_ARG;
+  if (n == 0) return SMB_OK;
+  if (!positions) return SMB_ERR_BAD_ARG;
+  F32Params p{};
+  p.planes_cl = planes_cl;
+  p.wts = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_f32);
+  p.n_hidden = (int)layout->n_hidden;
+  p.H = cfg->Hp;
+  p.W = cfg->Wp;
+  p.align_corners = cfg->align_corners;
+  p.density_bias = cfg->density_bias;
+  p.ps = make_pos_scale(cfg->radius);
+  p.positions = positions;
+  p.n = n;
+  p.R = 1;
+  p.density = density;
+  p.features = features;
+  p.density_act = density_act;
+  p.color = color;
+  return launch_f32(p, (cudaStream_t)stream);
+}
+
+extern "C" int smb_query_lattice_f32(const float* planes_cl, const void* decoder_blob,
+                                     const smb_decoder_layout* layout, const smb_query_cfg* cfg,
+                                     const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
+                                     float* out_density, void* stream) {
+  if (!planes_cl || !decoder_blob || !layout || !cfg || !axis_u || R <= 0 || nx < 0 || x_begin < 0 ||
+      x_begin + nx > R)
+    return SMB_ERR_BAD_ARG;
+  if (nx == 0) return SMB_OK;
+  F32Params p{};
+  p.planes_cl = planes_cl;
+  p.wts = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_f32);
+  p.n_hidden = (int)layout->n_hidden;
+  p.H = cfg->Hp;
+  p.W = cfg->Wp;
+  p.align_corners = cfg->align_corners;
+  p.density_bias = cfg->density_bias;
+  p.ps = make_pos_scale(cfg->radius);
+  p.positions = nullptr;
+  p.n = (long long)nx * R * R;
+  p.axis_u = axis_u;
+  p.R = R;
+  p.x_begin = x_begin;
+  p.density = out_density;
+  p.density_act = out_density_act;
+  return launch_f32(p, (cudaStream_t)stream);
+}

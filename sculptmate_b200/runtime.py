@@ -1,0 +1,340 @@
+"""Tensor-level host wrappers over the C ABI.
+
+PyTorch is plumbing here: it owns device memory and streams; all arithmetic on
+the hot path happens in the CUDA library.  Every function requires CUDA tensors
+and raises otherwise -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import DecoderLayout, McCounts, QueryCfg, check
+
+PLANE_CHANNELS = 40
+HIDDEN = 64
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"sculptmate_b200: `{name}` must be a CUDA tensor (got {t.device}); the B200 path has no CPU fallback"
+        )
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else int(t.data_ptr())
+
+
+# ------------------------------------------------------------------ decoder
+def decoder_layout(n_hidden: int) -> DecoderLayout:
+    lay = DecoderLayout()
+    check(_capi.load().smb_decoder_layout_for(int(n_hidden), ctypes.byref(lay)), "smb_decoder_layout_for")
+    return lay
+
+
+def pack_decoder_host(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, DecoderLayout]:
+    """Pack NeRFMLP parameters (network_utils.py:48-79) into the kernel blob (host, uint8)."""
+    n_hidden = len(weights) - 1
+    if len(biases) != len(weights) or n_hidden < 2:
+        raise ValueError("expected n_hidden+1 weight and bias tensors (n_hidden >= 2)")
+    exp_shapes = [(HIDDEN, 3 * PLANE_CHANNELS)] + [(HIDDEN, HIDDEN)] * (n_hidden - 1) + [(4, HIDDEN)]
+    ws, bs = [], []
+    for l, (w, b) in enumerate(zip(weights, biases)):
+        if tuple(w.shape) != exp_shapes[l] or tuple(b.shape) != (exp_shapes[l][0],):
+            raise NotImplementedError(
+                f"decoder layer {l} has shape {tuple(w.shape)}; the CUDA path is built for the TripoSR decoder "
+                f"(in 120, width 64, out 4; config.yaml:25-30), expected {exp_shapes[l]}"
+            )
+        ws.append(w.detach().to(device="cpu", dtype=torch.float32).contiguous())
+        bs.append(b.detach().to(device="cpu", dtype=torch.float32).contiguous())
+    lay = decoder_layout(n_hidden)
+    blob = torch.zeros(lay.total_bytes, dtype=torch.uint8)
+    fpp = ctypes.POINTER(ctypes.c_float)
+    W = (fpp * len(ws))(*[ctypes.cast(w.data_ptr(), fpp) for w in ws])
+    B = (fpp * len(bs))(*[ctypes.cast(b.data_ptr(), fpp) for b in bs])
+    check(
+        _capi.load().smb_decoder_pack_host(W, B, n_hidden, ctypes.byref(lay), ctypes.c_void_p(blob.data_ptr())),
+        "smb_decoder_pack_host",
+    )
+    return blob, lay
+
+
+@dataclass
+class DecoderPack:
+    blob: torch.Tensor  # uint8 on the device
+    layout: DecoderLayout
+    key: Tuple
+
+    @property
+    def device(self) -> torch.device:
+        return self.blob.device
+
+
+def decoder_params(decoder: torch.nn.Module) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+    """Linear layers of a NeRFMLP in order (state-dict keys layers.{0,2,..}.{weight,bias})."""
+    lin = [m for m in decoder.layers if isinstance(m, torch.nn.Linear)]
+    if any(m.bias is None for m in lin):
+        raise NotImplementedError("the CUDA path expects NeRFMLP with bias=True (config default)")
+    acts = [m for m in decoder.layers if not isinstance(m, torch.nn.Linear)]
+    if not all(isinstance(a, torch.nn.SiLU) for a in acts):
+        raise NotImplementedError("the CUDA path implements activation='silu' (TripoSR config.yaml:29)")
+    return [m.weight for m in lin], [m.bias for m in lin]
+
+
+_pack_cache: Dict[int, DecoderPack] = {}
+
+
+def get_decoder_pack(decoder: torch.nn.Module, device: torch.device) -> DecoderPack:
+    """Device blob for `decoder`, rebuilt when any parameter changes (ptr/version) or moves."""
+    ws, bs = decoder_params(decoder)
+    key = tuple((p.data_ptr(), p._version, str(p.device)) for p in (*ws, *bs)) + (str(device),)
+    cached = _pack_cache.get(id(decoder))
+    if cached is not None and cached.key == key:
+        return cached
+    blob, lay = pack_decoder_host(ws, bs)
+    pack = DecoderPack(blob=blob.to(device), layout=lay, key=key)
+    _pack_cache[id(decoder)] = pack
+    return pack
+
+
+# ------------------------------------------------------------- scene planes
+@dataclass
+class ScenePlanes:
+    planes_cl: Optional[torch.Tensor]  # (3,H,W,40) fp32
+    planes_q: Optional[torch.Tensor]  # (3,H,W,64) fp32
+    Hp: int
+    Wp: int
+
+
+def prepare_scene(triplane: torch.Tensor, pack: DecoderPack, want_cl: bool = True, want_q: bool = True) -> ScenePlanes:
+    _require_cuda(triplane, "triplane")
+    if triplane.dim() != 4 or triplane.shape[0] != 3 or triplane.shape[1] != PLANE_CHANNELS:
+        raise NotImplementedError(f"triplane must be (3,{PLANE_CHANNELS},Hp,Wp); got {tuple(triplane.shape)}")
+    tp = triplane.detach().to(torch.float32).contiguous()
+    _, _, Hp, Wp = tp.shape
+    dev = tp.device
+    cl = torch.empty((3, Hp, Wp, PLANE_CHANNELS), dtype=torch.float32, device=dev) if want_cl else None
+    q = torch.empty((3, Hp, Wp, HIDDEN), dtype=torch.float32, device=dev) if want_q else None
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_scene_prepare(
+                tp.data_ptr(), Hp, Wp, pack.blob.data_ptr(), ctypes.byref(pack.layout), _ptr(cl), _ptr(q), _stream_ptr(dev)
+            ),
+            "smb_scene_prepare",
+        )
+    return ScenePlanes(cl, q, Hp, Wp)
+
+
+def _cfg(radius: float, density_bias: float, Hp: int, Wp: int, align_corners: bool = False) -> QueryCfg:
+    return QueryCfg(float(radius), float(density_bias), int(bool(align_corners)), int(Hp), int(Wp))
+
+
+# -------------------------------------------------------------- field query
+def query_points(
+    planes: ScenePlanes,
+    pack: DecoderPack,
+    positions: torch.Tensor,
+    radius: float,
+    density_bias: float,
+    want: Sequence[str] = ("density", "features", "density_act", "color"),
+    align_corners: bool = False,
+) -> Dict[str, torch.Tensor]:
+    """query_triplane for arbitrary positions (n,3) in (-radius, radius); fp32 CUDA-core kernel."""
+    _require_cuda(positions, "positions")
+    pos = positions.detach().to(torch.float32).contiguous().view(-1, 3)
+    n = pos.shape[0]
+    dev = pos.device
+    widths = {"density": 1, "features": 3, "density_act": 1, "color": 3}
+    outs = {k: torch.empty((n, widths[k]), dtype=torch.float32, device=dev) for k in want}
+    cfg = _cfg(radius, density_bias, planes.Hp, planes.Wp, align_corners)
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_query_points_f32(
+                planes.planes_cl.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
+                pos.data_ptr(), n, _ptr(outs.get("density")), _ptr(outs.get("features")),
+                _ptr(outs.get("density_act")), _ptr(outs.get("color")), _stream_ptr(dev),
+            ),
+            "smb_query_points_f32",
+        )
+    return outs
+
+
+def lattice_axis(resolution: int, radius: float, points_range=(0, 1), device=None) -> torch.Tensor:
+    """Per-axis lattice coordinate mapped to (-1,1) with the reference's own torch ops:
+    linspace (isosurface.py:30-32) -> scale_tensor (system.py:177-181) -> scale_tensor
+    (nerf_renderer.py:52-54).  The lattice is separable, so R values describe all R^3 rows."""
+    from .tsr.utils import scale_tensor
+
+    a = torch.linspace(*points_range, resolution)
+    a = scale_tensor(a, points_range, (-radius, radius))
+    a = scale_tensor(a, (-radius, radius), (-1, 1))
+    return a.to(device) if device is not None else a
+
+
+def query_lattice(
+    planes: ScenePlanes,
+    pack: DecoderPack,
+    axis_u: torch.Tensor,
+    resolution: int,
+    radius: float,
+    density_bias: float,
+    x_begin: int = 0,
+    nx: Optional[int] = None,
+    precision: str = "tc",
+    want_raw: bool = False,
+    out: Optional[torch.Tensor] = None,
+):
+    """density_act on x-planes [x_begin, x_begin+nx) of the R^3 lattice -> (nx,R,R) fp32."""
+    R = int(resolution)
+    nx = R - x_begin if nx is None else int(nx)
+    _require_cuda(axis_u, "axis_u")
+    dev = axis_u.device
+    if out is None:
+        out = torch.empty((nx, R, R), dtype=torch.float32, device=dev)
+    raw = torch.empty((nx, R, R), dtype=torch.float32, device=dev) if want_raw else None
+    cfg = _cfg(radius, density_bias, planes.Hp, planes.Wp, False)
+    lib = _capi.load()
+    with torch.cuda.device(dev):
+        if precision == "tc":
+            rc = lib.smb_query_lattice_tc(
+                planes.planes_q.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
+                axis_u.data_ptr(), R, int(x_begin), nx, out.data_ptr(), _ptr(raw), _stream_ptr(dev),
+            )
+            check(rc, "smb_query_lattice_tc")
+        elif precision == "fp32":
+            rc = lib.smb_query_lattice_f32(
+                planes.planes_cl.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
+                axis_u.data_ptr(), R, int(x_begin), nx, out.data_ptr(), _ptr(raw), _stream_ptr(dev),
+            )
+            check(rc, "smb_query_lattice_f32")
+        else:
+            raise ValueError(f"precision must be 'tc' or 'fp32', got {precision!r}")
+    return (out, raw) if want_raw else out
+
+
+# ---------------------------------------------------------- marching cubes
+class McWorkspaceCache:
+    """Per-(device, shape) scratch + pinned counters, cached like the reference caches
+    its helper per resolution (system.py:118-124)."""
+
+    def __init__(self) -> None:
+        self._ws: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+
+    def get(self, device: torch.device, shape: Tuple[int, int, int]):
+        key = (str(device), tuple(shape))
+        if key not in self._ws:
+            nbytes = _capi.load().smb_mc_workspace_bytes(*shape)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            counts_dev = torch.zeros(4, dtype=torch.int64, device=device)
+            counts_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
+            if len(self._ws) > 4:
+                self._ws.clear()
+            self._ws[key] = (ws, counts_dev, counts_pin)
+        return self._ws[key]
+
+
+_mc_cache = McWorkspaceCache()
+
+
+@dataclass
+class McPending:
+    grid: torch.Tensor
+    sub: float
+    sign: float
+    emit_last_plane: bool
+    nverts: int
+    ntris: int
+    nverts_numbered: int
+
+
+def mc_count(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, emit_last_plane: bool = True) -> McPending:
+    """Classify + scan; returns the counts (one host sync to read them)."""
+    _require_cuda(grid, "grid")
+    if grid.dim() != 3 or grid.dtype != torch.float32 or not grid.is_contiguous():
+        raise ValueError("grid must be a contiguous (nx,ny,nz) float32 tensor")
+    nx, ny, nz = grid.shape
+    dev = grid.device
+    ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_mc_count(
+                grid.data_ptr(), nx, ny, nz, float(sub), float(sign), int(emit_last_plane), ws.data_ptr(),
+                ws.numel(), counts_dev.data_ptr(), _stream_ptr(dev),
+            ),
+            "smb_mc_count",
+        )
+        counts_pin.copy_(counts_dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    return McPending(grid, float(sub), float(sign), bool(emit_last_plane), int(counts_pin[0]), int(counts_pin[1]), int(counts_pin[2]))
+
+
+def mc_emit(
+    pending: McPending,
+    x_origin: int = 0,
+    flags: int = 0,
+    vdiv: float = 1.0,
+    vmul: float = 1.0,
+    vadd: float = 0.0,
+    vertex_id_offset: int = 0,
+    verts_out: Optional[torch.Tensor] = None,
+    faces_out: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    grid = pending.grid
+    nx, ny, nz = grid.shape
+    dev = grid.device
+    ws, _, _ = _mc_cache.get(dev, (nx, ny, nz))
+    verts = verts_out if verts_out is not None else torch.empty((pending.nverts, 3), dtype=torch.float32, device=dev)
+    faces = faces_out if faces_out is not None else torch.empty((pending.ntris, 3), dtype=torch.int64, device=dev)
+    if pending.nverts == 0 and pending.ntris == 0:
+        return verts, faces
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_mc_emit(
+                grid.data_ptr(), nx, ny, nz, pending.sub, pending.sign, int(x_origin), int(pending.emit_last_plane),
+                int(flags), float(vdiv), float(vmul), float(vadd), int(vertex_id_offset), ws.data_ptr(),
+                verts.data_ptr(), faces.data_ptr(), _stream_ptr(dev),
+            ),
+            "smb_mc_emit",
+        )
+    return verts, faces
+
+
+def mc_cases(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0) -> torch.Tensor:
+    _require_cuda(grid, "grid")
+    nx, ny, nz = grid.shape
+    out = torch.empty((nx - 1, ny - 1, nz - 1), dtype=torch.uint8, device=grid.device)
+    with torch.cuda.device(grid.device):
+        check(
+            _capi.load().smb_mc_cases(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), out.data_ptr(), _stream_ptr(grid.device)),
+            "smb_mc_cases",
+        )
+    return out
+
+
+def grid_minmax(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0) -> Tuple[float, float]:
+    _require_cuda(grid, "grid")
+    out = torch.empty(2, dtype=torch.float32, device=grid.device)
+    with torch.cuda.device(grid.device):
+        check(
+            _capi.load().smb_grid_minmax(grid.data_ptr(), grid.numel(), float(sub), float(sign), out.data_ptr(), _stream_ptr(grid.device)),
+            "smb_grid_minmax",
+        )
+    lo, hi = out.cpu().tolist()
+    return lo, hi
+
+
+def raise_for_empty_surface(grid: torch.Tensor, sub: float, sign: float) -> None:
+    """Same exception types skimage raises at isosurface.py:46-48."""
+    lo, hi = grid_minmax(grid, sub, sign)
+    if lo > 0.0 or hi < 0.0:
+        raise ValueError("Surface level must be within volume data range.")
+    raise RuntimeError("No surface found at the given iso value.")

@@ -1,0 +1,95 @@
+"""Drop-in for the query path of /root/reference/TripoSR/tsr/models/nerf_renderer.py.
+
+``query_triplane(decoder, positions, triplane)`` keeps the reference signature and
+return dict (nerf_renderer.py:41-91) but runs as one fused CUDA launch: the three
+bilinear plane gathers, the concat, the whole NeRFMLP chain and the exp / sigmoid
+tails, with no (N,120) feature tensor, no per-chunk launches and no torch.cat.
+``query_lattice`` is the lattice specialisation extract_mesh uses (tensor cores).
+The volume renderer (``_forward``/``forward``, :93-172) is out of scope.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from ... import runtime
+from ..utils import BaseModule
+
+
+class TriplaneNeRFRenderer(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        radius: float
+
+        feature_reduction: str = "concat"
+        density_activation: str = "trunc_exp"
+        density_bias: float = -1.0
+        color_activation: str = "sigmoid"
+        num_samples_per_ray: int = 128
+        randomized: bool = False
+
+    cfg: Config
+
+    def configure(self) -> None:
+        assert self.cfg.feature_reduction in ["concat", "mean"]
+        self.chunk_size = 0
+        self._scene_key = None
+        self._scene: Optional[runtime.ScenePlanes] = None
+
+    def set_chunk_size(self, chunk_size: int):
+        # kept for API compatibility (generate.py:25); the fused kernels do not chunk
+        assert chunk_size >= 0, "chunk_size must be a non-negative integer (0 for no chunking)."
+        self.chunk_size = chunk_size
+
+    def _check_supported(self) -> None:
+        c = self.cfg
+        if c.feature_reduction != "concat" or c.density_activation != "exp" or c.color_activation != "sigmoid":
+            raise NotImplementedError(
+                "the CUDA path implements the TripoSR renderer config (config.yaml:32-37): "
+                "feature_reduction=concat, density_activation=exp, color_activation=sigmoid; got "
+                f"{c.feature_reduction}/{c.density_activation}/{c.color_activation}"
+            )
+
+    def _planes(self, decoder: torch.nn.Module, triplane: torch.Tensor):
+        pack = runtime.get_decoder_pack(decoder, triplane.device)
+        key = (triplane.data_ptr(), triplane._version, tuple(triplane.shape), pack.key)
+        if self._scene_key != key:
+            self._scene = runtime.prepare_scene(triplane, pack)
+            self._scene_key = key
+        return pack, self._scene
+
+    def query_triplane(
+        self,
+        decoder: torch.nn.Module,
+        positions: torch.Tensor,
+        triplane: torch.Tensor,
+    ) -> Dict[str, torch.Tensor]:
+        self._check_supported()
+        input_shape = positions.shape[:-1]
+        pack, scene = self._planes(decoder, triplane)
+        out = runtime.query_points(scene, pack, positions.reshape(-1, 3), self.cfg.radius, self.cfg.density_bias)
+        return {k: v.view(*input_shape, -1) for k, v in out.items()}
+
+    def query_lattice(
+        self,
+        decoder: torch.nn.Module,
+        triplane: torch.Tensor,
+        resolution: int,
+        axis_u: Optional[torch.Tensor] = None,
+        x_begin: int = 0,
+        nx: Optional[int] = None,
+        precision: str = "tc",
+        out: Optional[torch.Tensor] = None,
+    ) -> torch.Tensor:
+        """density_act of query_triplane on the MarchingCubeHelper lattice, planes
+        [x_begin, x_begin+nx) -> (nx,R,R); positions are generated in-kernel."""
+        self._check_supported()
+        pack, scene = self._planes(decoder, triplane)
+        if axis_u is None:
+            axis_u = runtime.lattice_axis(resolution, self.cfg.radius, device=triplane.device)
+        return runtime.query_lattice(
+            scene, pack, axis_u, resolution, self.cfg.radius, self.cfg.density_bias,
+            x_begin=x_begin, nx=nx, precision=precision, out=out,
+        )
