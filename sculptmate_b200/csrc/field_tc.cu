@@ -299,8 +299,9 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   // rows of the (.,z) planes one 128-sample segment can touch (+2 for the taps, +1 slack)
   {
     double span = 127.0 * cfg->Hp / (double)(R - 1);
-    if (span > cfg->Hp) span = cfg->Hp;
-    if ((int)span + 3 > kTRows) return SMB_ERR_BAD_ARG;
+    int rows = (int)span + 3;
+    if (rows > cfg->Hp + 2) rows = cfg->Hp + 2;  // rows -1 .. Hp (the two zero borders)
+    if (rows > kTRows) return SMB_ERR_BAD_ARG;
   }
   constexpr int kWG = 4;
   const int wbytes = tc_weight_bytes(nh);

@@ -1,0 +1,146 @@
+"""GPU parity of the whole path behind the reference's extract_mesh signature."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_decoder, mesh_topology
+from test_gpu_field import _model
+
+pytestmark = pytest.mark.gpu
+RADIUS = 0.87
+
+
+def test_extract_mesh_dropin_against_reference_golden(golden):
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    R, thr = int(g["resolution"]), float(g["threshold"])
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    ret = m.extract_mesh(tp[None], enable_texture=True, mesh_name="golden", resolution=R, threshold=thr)
+    assert ret is None  # the reference returns None and delivers through import_obj_blender
+    verts, faces, colors, name = m.meshes[-1]
+    assert name == "golden" and verts.dtype == np.float32 and faces.dtype == np.int64 and colors.dtype == np.float32
+    assert verts.shape[1] == 3 and faces.shape[1] == 3 and colors.shape == verts.shape
+    assert np.abs(verts).max() <= RADIUS + 1e-6
+    # tensor-core density differs from the reference's fp32 density in the 4th digit, so a few
+    # cells may flip: counts within 1 %, geometry close
+    assert abs(len(verts) / len(g["verts"]) - 1) < 0.01 and abs(len(faces) / len(g["faces"]) - 1) < 0.01
+    # with the fp32 kernel the cube cases are identical -> connectivity identical to the golden
+    v32, f32 = m.extract_mesh_tensors(tp, R, thr, precision="fp32")
+    np.testing.assert_array_equal(f32.cpu().numpy(), g["faces"])
+    assert np.abs(v32.cpu().numpy() - g["verts"]).max() < 1e-4
+    # the reference-shaped slow path (grid_vertices -> query_triplane -> helper) agrees too
+    vu, fu = m.extract_mesh_unfused(tp, R, thr)
+    np.testing.assert_array_equal(fu.cpu().numpy(), g["faces"])
+    assert np.abs(vu.cpu().numpy() - g["verts"]).max() < 1e-4
+
+
+def test_colour_query_at_golden_vertices(golden):
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    col = m.renderer.query_triplane(m.decoder, torch.from_numpy(g["verts"]).cuda(), tp)["color"]
+    assert np.abs(col.cpu().numpy() - g["colors"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("R", [32, 64, 128])
+def test_mesh_bit_exact_vs_oracle_on_shared_density(golden, R):
+    """north_star: connectivity bit-exact when both sides are fed the same density grid."""
+    from oracle import mc_oracle
+
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    dens = m.renderer.query_lattice(m.decoder, tp, R)
+    thr = float(dens.median())
+    v, f = m.extract_mesh_tensors(tp, R, thr)
+    v_ref, f_ref, _ = mc_oracle.marching_cubes_slab(
+        dens.cpu().numpy(), sub=np.float32(thr), flags=7, vdiv=float(R - 1.0), vmul=float(RADIUS - (-RADIUS)), vadd=float(-RADIUS)
+    )
+    np.testing.assert_array_equal(v.cpu().numpy(), v_ref)
+    np.testing.assert_array_equal(f.cpu().numpy(), f_ref)
+
+
+def test_threshold_errors_like_reference(golden):
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    with pytest.raises(ValueError, match="within volume data range"):
+        m.extract_mesh(tp[None], resolution=16, threshold=25.0)  # the reference default on random-init density
+
+
+def test_batch_of_scene_codes(golden):
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    codes = torch.stack([tp, tp.flip(-1), tp])
+    m.extract_mesh(codes, resolution=24, threshold=float(g["threshold"]), mesh_name="b")
+    assert len(m.meshes) == 3
+    np.testing.assert_array_equal(m.meshes[0][1], m.meshes[2][1])
+    assert not np.array_equal(m.meshes[0][0].shape, ()) and m.meshes[1][0].shape != ()
+
+
+def test_capi_host_extractor_matches_python_path(golden):
+    from sculptmate_b200 import _capi
+
+    lib = _capi.load()
+    g = golden("extract_mesh.npz")
+    ws, bs = golden_decoder(g)
+    fpp = ctypes.POINTER(ctypes.c_float)
+    ws_c = [np.ascontiguousarray(w) for w in ws]
+    bs_c = [np.ascontiguousarray(b) for b in bs]
+    W = (fpp * 10)(*[w.ctypes.data_as(fpp) for w in ws_c])
+    B = (fpp * 10)(*[b.ctypes.data_as(fpp) for b in bs_c])
+    ex = ctypes.c_void_p()
+    assert lib.smb_extractor_create(W, B, 9, RADIUS, -1.0, 16, 16, ctypes.byref(ex)) == 0
+    try:
+        tp = np.ascontiguousarray(g["triplane"])
+        vp, fp_ = fpp(), ctypes.POINTER(ctypes.c_int64)()
+        nv, nt = ctypes.c_int64(), ctypes.c_int64()
+        R, thr = int(g["resolution"]), float(g["threshold"])
+        rc = lib.smb_extract_mesh_host(ex, tp.ctypes.data_as(fpp), R, thr, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
+        assert rc == 0
+        v = np.ctypeslib.as_array(vp, shape=(nv.value, 3)).copy()
+        f = np.ctypeslib.as_array(fp_, shape=(nt.value, 3)).copy()
+        m = _model(g)
+        v2, f2 = m.extract_mesh_tensors(torch.from_numpy(tp).cuda(), R, thr)
+        # the C host computes lattice coordinates with the scalar linspace formula (<= 2 ulp from
+        # aten's), so density can differ in the last bits: same connectivity here, verts close
+        assert f.shape == tuple(f2.shape) and np.array_equal(f, f2.cpu().numpy())
+        assert np.abs(v - v2.cpu().numpy()).max() < 1e-4
+        rc = lib.smb_extract_mesh_host(ex, tp.ctypes.data_as(fpp), R, 1e9, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
+        assert rc == _capi.ERR_LEVEL_RANGE
+    finally:
+        lib.smb_extractor_destroy(ex)
+
+
+def test_full_size_256_mesh_properties(golden):
+    """256^3 (BASELINE configs[1]): closedness away from the boundary is not guaranteed for a
+    field that crosses the lattice border, so check size-independent properties: determinism,
+    index range, every vertex referenced, vertices on lattice edges, and oracle bit-equality
+    on a 24-plane sub-slab of the same density grid."""
+    from oracle import mc_oracle
+    from sculptmate_b200 import runtime
+
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    R = 256
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    dens = m.renderer.query_lattice(m.decoder, tp, R)
+    thr = float(dens.median())
+    v, f = m.extract_mesh_tensors(tp, R, thr)
+    v2, f2 = m.extract_mesh_tensors(tp, R, thr)
+    assert torch.equal(v, v2) and torch.equal(f, f2)
+    assert int(f.min()) == 0 and int(f.max()) == len(v) - 1
+    assert len(torch.unique(f)) == len(v)
+    idx = (v + RADIUS) / (2 * RADIUS) * (R - 1)
+    offgrid = ((idx - idx.round()).abs() > 1e-3).sum(dim=1)
+    assert int(offgrid.max()) <= 1
+    sl = dens[120:144].contiguous()
+    pend = runtime.mc_count(sl, sub=thr, sign=1.0, emit_last_plane=False)
+    vs, fs = runtime.mc_emit(pend, x_origin=120, flags=7, vdiv=float(R - 1.0), vmul=1.74, vadd=-0.87)
+    vr, fr, _ = mc_oracle.marching_cubes_slab(sl.cpu().numpy(), sub=np.float32(thr), x_origin=120, emit_last_plane=False, flags=7,
+                                              vdiv=float(R - 1.0), vmul=1.74, vadd=-0.87)
+    np.testing.assert_array_equal(vs.cpu().numpy(), vr)
+    np.testing.assert_array_equal(fs.cpu().numpy(), fr)

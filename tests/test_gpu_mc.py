@@ -1,0 +1,125 @@
+"""GPU parity: CUDA marching cubes vs the oracle, bit-exact, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import mesh_topology, volume
+
+pytestmark = pytest.mark.gpu
+
+FLAGS = 7  # FLIP | DIV | AFFINE
+
+
+def _gpu_mc(g, sub, sign, emit_last=True, x_origin=0, off=0, R=None):
+    from sculptmate_b200 import runtime
+
+    R = R or max(g.shape)
+    gd = torch.from_numpy(g).cuda()
+    pend = runtime.mc_count(gd, sub=sub, sign=sign, emit_last_plane=emit_last)
+    v, f = runtime.mc_emit(pend, x_origin=x_origin, flags=FLAGS, vdiv=float(R - 1), vmul=1.74, vadd=-0.87, vertex_id_offset=off)
+    return v.cpu().numpy(), f.cpu().numpy(), pend
+
+
+def _oracle_mc(g, sub, sign, emit_last=True, x_origin=0, R=None):
+    from oracle import mc_oracle
+
+    R = R or max(g.shape)
+    return mc_oracle.marching_cubes_slab(g, sub=sub, sign=sign, x_origin=x_origin, emit_last_plane=emit_last, flags=FLAGS,
+                                         vdiv=float(R - 1), vmul=1.74, vadd=-0.87)
+
+
+CASES = [
+    ("sphere", (16, 16, 16)), ("noise", (20, 20, 20)), ("gyroid", (33, 33, 33)), ("smooth", (40, 17, 70)),
+    ("noise", (9, 33, 65)), ("noise", (2, 2, 2)), ("smooth", (3, 70, 2)), ("torus", (64, 64, 64)), ("gyroid", (96, 96, 96)),
+]
+
+
+@pytest.mark.parametrize("kind,shape", CASES)
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_mesh_bit_exact(kind, shape, sign):
+    R = max(shape)
+    g = volume(kind, R, seed=4)[: shape[0], : shape[1], : shape[2]].copy()
+    v, f, pend = _gpu_mc(g, 0.03, sign)
+    v_ref, f_ref, c = _oracle_mc(g, 0.03, sign)
+    assert (pend.nverts, pend.ntris, pend.nverts_numbered) == (c.nverts, c.ntris, c.nverts_numbered)
+    np.testing.assert_array_equal(v.view(np.uint32), v_ref.view(np.uint32))
+    np.testing.assert_array_equal(f, f_ref)
+
+
+@pytest.mark.parametrize("kind,shape", CASES)
+def test_cube_cases_bit_exact(kind, shape):
+    from oracle import mc_oracle
+    from sculptmate_b200 import runtime
+
+    if min(shape) < 2:
+        pytest.skip("no cells")
+    R = max(shape)
+    g = volume(kind, R, seed=4)[: shape[0], : shape[1], : shape[2]].copy()
+    cs = runtime.mc_cases(torch.from_numpy(g).cuda(), 0.03, 1.0).cpu().numpy()
+    np.testing.assert_array_equal(cs, mc_oracle.cube_cases(g, 0.03, 1.0))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slabs_on_gpu_concatenate_to_single_gpu_mesh(world):
+    from sculptmate_b200.dist import slab_partition
+
+    R = 72
+    g = volume("gyroid", R)
+    v_full, f_full, _ = _gpu_mc(g, 0.0, 1.0)
+    vs, fs, off = [], [], 0
+    for r, (a, b) in enumerate(slab_partition(R, world)):
+        v, f, pend = _gpu_mc(g[a : b + 1].copy(), 0.0, 1.0, emit_last=(r == world - 1), x_origin=a, off=off, R=R)
+        vs.append(v)
+        fs.append(f)
+        off += pend.nverts
+    np.testing.assert_array_equal(np.concatenate(vs), v_full)
+    np.testing.assert_array_equal(np.concatenate(fs), f_full)
+
+
+def test_full_size_256_properties():
+    """BASELINE config size: checked through size-independent properties (closed oriented
+    surface, Euler characteristic, volume) plus bit-exactness of a sub-slab vs the oracle."""
+    R = 256
+    g = volume("torus", R)
+    v, f, pend = _gpu_mc(g, 0.0, 1.0)
+    closed, chi, vol = mesh_topology(v, f)
+    assert closed and chi == 0 and vol > 0
+    exact = 2 * np.pi**2 * 0.55 * 0.22**2 * (0.87 / 1.0) ** 3  # torus volume in (-.87,.87) units
+    assert abs(vol / exact - 1) < 5e-3
+    v2, f2, _ = _gpu_mc(g, 0.0, 1.0)
+    np.testing.assert_array_equal(v, v2)  # deterministic
+    np.testing.assert_array_equal(f, f2)
+    sl = g[100:133].copy()
+    vs, fs, _ = _gpu_mc(sl, 0.0, 1.0, x_origin=100, R=R)
+    vr, fr, _ = _oracle_mc(sl, 0.0, 1.0, x_origin=100, R=R)
+    np.testing.assert_array_equal(vs, vr)
+    np.testing.assert_array_equal(fs, fr)
+
+
+def test_helper_forward_dropin(golden):
+    """MarchingCubeHelper.forward == the reference wrapper run on the oracle MC (golden)."""
+    from sculptmate_b200.tsr import MarchingCubeHelper
+
+    g = golden("helper_sphere.npz")
+    h = MarchingCubeHelper(int(g["resolution"]))
+    v, f = h(torch.from_numpy(g["level_in"]).cuda())
+    assert v.dtype == torch.float32 and f.dtype == torch.int64 and v.is_cuda and f.is_cuda
+    np.testing.assert_array_equal(v.cpu().numpy(), g["v_pos"])
+    np.testing.assert_array_equal(f.cpu().numpy(), g["t_pos_idx"])
+    v1, f1 = h(torch.from_numpy(g["level_in"]).cuda().view(-1))  # (R^3,) accepted like (R^3,1)
+    assert torch.equal(v1, v) and torch.equal(f1, f)
+
+
+def test_error_behaviour_matches_skimage():
+    from sculptmate_b200.tsr import MarchingCubeHelper
+
+    R = 8
+    h = MarchingCubeHelper(R)
+    with pytest.raises(ValueError, match="within volume data range"):
+        h(torch.ones(R**3, 1).cuda())
+    with pytest.raises(ValueError):
+        h(-torch.ones(R**3, 1).cuda())
+    z = torch.ones(R**3, 1)
+    z[77] = 0.0
+    with pytest.raises(RuntimeError, match="No surface"):
+        h(z.cuda())
