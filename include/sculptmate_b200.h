@@ -168,6 +168,11 @@ typedef struct smb_extractor smb_extractor;
 int smb_extractor_create(const float* const* weights_host, const float* const* biases_host, int n_hidden,
                          float radius, float density_bias, int Hp, int Wp, smb_extractor** out);
 void smb_extractor_destroy(smb_extractor* ex);
+/* Optional: supply the per-axis lattice coordinates (R values in (-1,1)) for resolution R instead of
+ * the scalar smb_lattice_axis_host restatement -- a host that has torch passes the values the
+ * reference's own ops produce (isosurface.py:30-32 -> system.py:177-181 -> nerf_renderer.py:52-54),
+ * making the C path bit-identical to the Python drop-in.  Copied; valid until R changes. */
+int smb_extractor_set_axis(smb_extractor* ex, int resolution, const float* axis_u_host);
 int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int resolution, float threshold,
                           const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                           int64_t* ntris);

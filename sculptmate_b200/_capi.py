@@ -83,6 +83,7 @@ SIGNATURES = {
     "smb_grid_minmax": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
     "smb_extractor_create": (c_int, [_FLOATPP, _FLOATPP, c_int, c_float, c_float, c_int, c_int, POINTER(c_void_p)]),
     "smb_extractor_destroy": (None, [c_void_p]),
+    "smb_extractor_set_axis": (c_int, [c_void_p, c_int, POINTER(c_float)]),
     "smb_extract_mesh_host": (
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],

@@ -272,6 +272,14 @@ static int ensure_resolution(smb_extractor* ex, int R) {
   return SMB_OK;
 }
 
+extern "C" int smb_extractor_set_axis(smb_extractor* ex, int R, const float* axis_u_host) {
+  if (!ex || !axis_u_host || R < 2) return SMB_ERR_BAD_ARG;
+  int rc = ensure_resolution(ex, R);
+  if (rc != SMB_OK) return rc;
+  EX_CUDA(cudaMemcpy(ex->axis_dev, axis_u_host, sizeof(float) * R, cudaMemcpyHostToDevice));
+  return SMB_OK;
+}
+
 extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int R, float threshold,
                                      const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                                      int64_t* ntris) {

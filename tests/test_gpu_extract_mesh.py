@@ -106,9 +106,21 @@ def test_capi_host_extractor_matches_python_path(golden):
         m = _model(g)
         v2, f2 = m.extract_mesh_tensors(torch.from_numpy(tp).cuda(), R, thr)
         # the C host computes lattice coordinates with the scalar linspace formula (<= 2 ulp from
-        # aten's), so density can differ in the last bits: same connectivity here, verts close
+        # aten's); through the fp16-operand MLP that moves density by up to the stated fp16 tolerance,
+        # so vertices may slide along their edges: same connectivity here, verts within 0.2 cell
+        cell = 2 * RADIUS / (R - 1)
         assert f.shape == tuple(f2.shape) and np.array_equal(f, f2.cpu().numpy())
-        assert np.abs(v - v2.cpu().numpy()).max() < 1e-4
+        assert np.abs(v - v2.cpu().numpy()).max() < 0.2 * cell
+        # with the host's torch-built coordinates the C path is bit-identical to the Python drop-in
+        from sculptmate_b200 import runtime
+
+        axis = np.ascontiguousarray(runtime.lattice_axis(R, RADIUS).numpy())
+        assert lib.smb_extractor_set_axis(ex, R, axis.ctypes.data_as(fpp)) == 0
+        rc = lib.smb_extract_mesh_host(ex, tp.ctypes.data_as(fpp), R, thr, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
+        assert rc == 0
+        v = np.ctypeslib.as_array(vp, shape=(nv.value, 3)).copy()
+        f = np.ctypeslib.as_array(fp_, shape=(nt.value, 3)).copy()
+        assert np.array_equal(f, f2.cpu().numpy()) and np.array_equal(v, v2.cpu().numpy())
         rc = lib.smb_extract_mesh_host(ex, tp.ctypes.data_as(fpp), R, 1e9, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
         assert rc == _capi.ERR_LEVEL_RANGE
     finally:
