@@ -1,23 +1,26 @@
-// Marching cubes on sm_100a: classify -> scan -> emit, deterministic and
+// Marching cubes on sm_100a: signs -> count+scan -> emit, deterministic and
 // duplicate-free.  Replaces the CPU call skimage.measure.marching_cubes(level, 0.0)
 // and the wrapper post-processing in MarchingCubeHelper.forward
 // (/root/reference/TripoSR/tsr/models/isosurface.py:41-54).
 //
-// HBM-bound integer/bit work: no tensor cores.  One warp owns one "word" = 32
-// consecutive z-samples of an (x,y) row, so every global access is a coalesced
-// 128-byte row segment, sign tests become warp ballots and all per-word prefix
-// arithmetic is popc on ballot masks.
+// HBM-bound integer/bit work: no tensor cores.  The unit of work is a "word" =
+// 32 consecutive z-samples of an (x,y) row.
 //
-//   K1 classify : reads the density slab once; per word writes the sign mask and
-//                 the three crossing masks (x/y/z edges owned by the word's points),
-//                 the number of owned crossings (split: in-plane / x-edge) and the
-//                 number of triangles of the word's 32 cells.
-//   K2 scan     : exclusive prefix sums over the per-word counts, laid out so that
-//                 the flat scan order IS the canonical output order.
-//   K3 emit     : words with work write their vertices (each lattice edge is owned
-//                 by exactly one sample -> no duplicates, no atomics) and their
-//                 triangles; vertex ids of neighbouring words come from
-//                 prefix[word] + popc(mask & lanes_below).
+//   K1 mc_signs  : streams the density slab ONCE (coalesced 128-byte row segments,
+//                  8 independent loads in flight per lane) and reduces it 32:1 to sign
+//                  bit masks with warp ballots.  Everything downstream works on the
+//                  masks (R^3/8 bytes, L2 resident).
+//   K2 mc_count  : one thread per word, one CTA per chunk of 2048 words of a plane:
+//                  crossing masks by XOR of neighbouring sign masks, owned-vertex and
+//                  triangle counts (popc / case table), CTA-wide exclusive scan; writes
+//                  a 16-byte record per word + the chunk totals.
+//   K3 mc_totals : one CTA turns chunk totals into chunk bases in canonical order.
+//   K4 mc_emit   : persistent warps skip inactive words 32 at a time (one ballot),
+//                  and for an active word write its owned vertices (each lattice edge
+//                  is owned by exactly one sample -> no duplicates, no atomics) and the
+//                  triangles of its 32 cells; vertex ids of neighbouring words come
+//                  from prefix[word] + popc(mask & lanes_below).  Density is re-read
+//                  only at the two end points of crossing edges.
 //
 // Canonical order (identical to oracle/mc_oracle.c): vertices by x-plane i, inside a
 // plane first the in-plane crossings by (j,k) with the y-edge before the z-edge of a
@@ -32,14 +35,15 @@
 
 namespace smb {
 
-struct WordRec {  // 16 B per word
-  uint32_t mx, my, mz, pos;
-};
+constexpr int kChunkWords = 2048;  // words per count CTA (256 threads x 8)
+constexpr int kWordsPerThread = 8;
 
 struct McDims {
-  int nx, ny, nz, wz;  // wz = words per z-row
-  long long nrows;     // nx*ny
-  long long nwords;    // nrows*wz
+  int nx, ny, nz, wz;   // wz = words per z-row
+  int pw;               // words per x-plane = ny*wz
+  int cpp;              // chunks per plane
+  long long nwords;     // nx*pw
+  long long nchunks;    // nx*cpp
 };
 
 __host__ __device__ inline McDims make_dims(int nx, int ny, int nz) {
@@ -48,24 +52,30 @@ __host__ __device__ inline McDims make_dims(int nx, int ny, int nz) {
   d.ny = ny;
   d.nz = nz;
   d.wz = (nz + 31) / 32;
-  d.nrows = (long long)nx * ny;
-  d.nwords = d.nrows * d.wz;
+  d.pw = ny * d.wz;
+  d.cpp = (d.pw + kChunkWords - 1) / kChunkWords;
+  d.nwords = (long long)nx * d.pw;
+  d.nchunks = (long long)nx * d.cpp;
   return d;
 }
 
-// workspace carve-up (all offsets 256 B aligned)
-struct McWorkspace {
-  WordRec* rec;        // nwords
-  uint32_t* vcnt;      // 2*nwords, index ((i*2+g)*ny + j)*wz + w
-  uint32_t* tcnt;      // nwords
-  uint32_t* vpre;      // 2*nwords exclusive prefix (within scan chunk) ...
-  uint32_t* tpre;      // nwords
-  uint32_t* vchunk;    // per-chunk bases for vpre
-  uint32_t* tchunk;    // per-chunk bases for tpre
-  size_t bytes;
+// per word: chunk-local exclusive prefixes of (in-plane vertices, x-edge vertices,
+// triangles) and an info word (bit 0: the word owns a vertex or has a triangle).
+struct __align__(16) WordRec {
+  uint32_t a, b, t, info;
+};
+// per chunk: totals (K2) -> global exclusive bases (K3), same field meaning.
+struct __align__(16) ChunkRec {
+  uint32_t a, b, t, pad;
 };
 
-constexpr int kScanChunk = 2048;  // entries per scan CTA (256 threads x 8)
+struct McWorkspace {
+  uint32_t* pos;     // nwords sign masks
+  WordRec* rec;      // nwords
+  ChunkRec* ctot;    // nchunks totals
+  ChunkRec* cbase;   // nchunks bases
+  size_t bytes;
+};
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -79,15 +89,10 @@ __host__ inline McWorkspace carve(void* base, const McDims& d) {
     return p;
   };
   const size_t nw = (size_t)d.nwords;
-  const size_t vch = (2 * nw + kScanChunk - 1) / kScanChunk + 1;
-  const size_t tch = (nw + kScanChunk - 1) / kScanChunk + 1;
+  w.pos = reinterpret_cast<uint32_t*>(take((nw + 1) * 4));
   w.rec = reinterpret_cast<WordRec*>(take(nw * sizeof(WordRec)));
-  w.vcnt = reinterpret_cast<uint32_t*>(take(2 * nw * 4));
-  w.tcnt = reinterpret_cast<uint32_t*>(take(nw * 4));
-  w.vpre = reinterpret_cast<uint32_t*>(take(2 * nw * 4));
-  w.tpre = reinterpret_cast<uint32_t*>(take(nw * 4));
-  w.vchunk = reinterpret_cast<uint32_t*>(take(vch * 4));
-  w.tchunk = reinterpret_cast<uint32_t*>(take(tch * 4));
+  w.ctot = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
+  w.cbase = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
   w.bytes = off;
   return w;
 }
@@ -96,87 +101,48 @@ __device__ __forceinline__ float mc_val(const float* __restrict__ g, long long i
   return __fmul_rn(__fsub_rn(__ldg(g + idx), sub), sign);
 }
 
-// ------------------------------------------------------------ K1 classify
-// One warp per word; a CTA of 8 warps covers 8 consecutive j rows of one (i, w)
-// so the j+1 rows it needs are mostly its own neighbours' rows (L1 hits).
-__global__ void __launch_bounds__(256) mc_classify(const float* __restrict__ grid, McDims d, float sub, float sign,
-                                                   WordRec* __restrict__ rec, uint32_t* __restrict__ vcnt,
-                                                   uint32_t* __restrict__ tcnt) {
+// streaming load: the slab is read exactly once by K1, do not keep it in L1
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------ K1 signs
+// One warp reduces 8 words per iteration: 8 independent coalesced 128-byte loads in
+// flight per warp, then 8 ballots.  Persistent grid-stride over groups of 8 words.
+__global__ void __launch_bounds__(256) mc_signs(const float* __restrict__ grid, McDims d, float sub, float sign,
+                                                uint32_t* __restrict__ pos) {
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int jblocks = (d.ny + 7) / 8;
-  // blockIdx.x enumerates (i, jblock, w) with w fastest
-  long long b = blockIdx.x;
-  const int w = (int)(b % d.wz);
-  b /= d.wz;
-  const int jb = (int)(b % jblocks);
-  const int i = (int)(b / jblocks);
-  const int j = jb * 8 + warp;
-  if (j >= d.ny) return;
-  const int k = w * 32 + lane;
-  const long long sy = d.nz, sx = (long long)d.ny * d.nz;
-  const long long p = (long long)i * sx + (long long)j * sy + k;
-  const bool in = k < d.nz;
-  const bool hx = i + 1 < d.nx, hy = j + 1 < d.ny;
-
-  // sign bits of the four (i..i+1, j..j+1) rows at this lane's k
-  const bool b00 = in && mc_val(grid, p, sub, sign) > 0.0f;
-  const bool b01 = in && hy && mc_val(grid, p + sy, sub, sign) > 0.0f;
-  const bool b10 = in && hx && mc_val(grid, p + sx, sub, sign) > 0.0f;
-  const bool b11 = in && hx && hy && mc_val(grid, p + sx + sy, sub, sign) > 0.0f;
-  const uint32_t m00 = __ballot_sync(0xffffffffu, b00);
-  const uint32_t m01 = __ballot_sync(0xffffffffu, b01);
-  const uint32_t m10 = __ballot_sync(0xffffffffu, b10);
-  const uint32_t m11 = __ballot_sync(0xffffffffu, b11);
-  // bit 0 of the next word of each row (k = w*32+32), fetched by lanes 0..3
-  const int kn = w * 32 + 32;
-  bool nb = false;
-  if (kn < d.nz && lane < 4) {
-    const bool need = (lane == 0) || (lane == 1 && hy) || (lane == 2 && hx) || (lane == 3 && hx && hy);
-    if (need) {
-      const long long q = (long long)i * sx + (long long)j * sy + kn + ((lane & 1) ? sy : 0) + ((lane & 2) ? sx : 0);
-      nb = mc_val(grid, q, sub, sign) > 0.0f;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long ngroups = (d.nwords + 7) / 8;
+  const bool dense = (d.nz & 31) == 0;  // rows are whole words: the slab is one flat run of words
+  for (long long g = warp; g < ngroups; g += nwarps) {
+    const long long w0 = g * 8;
+    float v[8];
+    bool ok[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const long long word = w0 + e;
+      ok[e] = word < d.nwords;
+      long long idx;
+      if (dense) {
+        idx = word * 32 + lane;
+      } else {
+        const long long row = word / d.wz;
+        const int k = (int)(word - row * d.wz) * 32 + lane;
+        ok[e] = ok[e] && k < d.nz;
+        idx = row * d.nz + k;
+      }
+      v[e] = ok[e] ? ld_stream(grid + idx) : 0.0f;
     }
-  }
-  const uint32_t nmask = __ballot_sync(0xffffffffu, nb);
-  // masks shifted to "k+1" alignment
-  const uint32_t s00 = (m00 >> 1) | ((nmask & 1u) << 31);
-  const uint32_t s01 = (m01 >> 1) | (((nmask >> 1) & 1u) << 31);
-  const uint32_t s10 = (m10 >> 1) | (((nmask >> 2) & 1u) << 31);
-  const uint32_t s11 = (m11 >> 1) | (((nmask >> 3) & 1u) << 31);
-
-  // validity masks over this word's lanes
-  const int nin = min(32, d.nz - w * 32);                       // samples present
-  const uint32_t vin = nin >= 32 ? 0xffffffffu : ((1u << nin) - 1u);
-  const int nz1 = min(32, d.nz - 1 - w * 32);                   // lanes with k+1 < nz
-  const uint32_t vz = nz1 >= 32 ? 0xffffffffu : (nz1 <= 0 ? 0u : ((1u << nz1) - 1u));
-
-  const uint32_t mx = hx ? ((m00 ^ m10) & vin) : 0u;
-  const uint32_t my = hy ? ((m00 ^ m01) & vin) : 0u;
-  const uint32_t mz = (m00 ^ s00) & vz;
-
-  // cube case of this lane's cell (corner c = 4*di + 2*dj + dk)
-  uint32_t ntri = 0;
-  if (hx && hy && ((vz >> lane) & 1u)) {
-    const uint32_t cs = ((m00 >> lane) & 1u) | (((s00 >> lane) & 1u) << 1) | (((m01 >> lane) & 1u) << 2) |
-                        (((s01 >> lane) & 1u) << 3) | (((m10 >> lane) & 1u) << 4) | (((s10 >> lane) & 1u) << 5) |
-                        (((m11 >> lane) & 1u) << 6) | (((s11 >> lane) & 1u) << 7);
-    ntri = SMB_MC_NTRI[cs];
-  }
-  const uint32_t tsum = __reduce_add_sync(0xffffffffu, ntri);
-
-  if (lane == 0) {
-    const long long word = ((long long)i * d.ny + j) * d.wz + w;
-    WordRec r;
-    r.mx = mx;
-    r.my = my;
-    r.mz = mz;
-    r.pos = m00;
-    rec[word] = r;
-    const long long rowwords = (long long)d.ny * d.wz;
-    vcnt[((long long)i * 2 + 0) * rowwords + (long long)j * d.wz + w] = __popc(my) + __popc(mz);
-    vcnt[((long long)i * 2 + 1) * rowwords + (long long)j * d.wz + w] = __popc(mx);
-    tcnt[word] = tsum;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const bool bit = ok[e] && __fmul_rn(__fsub_rn(v[e], sub), sign) > 0.0f;
+      const uint32_t m = __ballot_sync(0xffffffffu, bit);
+      if (lane == e && w0 + e < d.nwords) pos[w0 + e] = m;
+    }
   }
 }
 
@@ -202,68 +168,174 @@ __global__ void mc_cases_kernel(const float* __restrict__ grid, int nx, int ny, 
   }
 }
 
-// ---------------------------------------------------------------- K2 scan
-// Phase A: every CTA scans one chunk of 2048 counts (exclusive, chunk-local) and
-// records the chunk total.  blockIdx.y selects the array (0 = vertices, 1 = triangles).
-__global__ void __launch_bounds__(256) mc_scan_chunks(const uint32_t* __restrict__ vcnt, uint32_t* __restrict__ vpre,
-                                                      uint32_t* __restrict__ vchunk, long long nv,
-                                                      const uint32_t* __restrict__ tcnt, uint32_t* __restrict__ tpre,
-                                                      uint32_t* __restrict__ tchunk, long long nt) {
-  const uint32_t* cnt = blockIdx.y ? tcnt : vcnt;
-  uint32_t* pre = blockIdx.y ? tpre : vpre;
-  uint32_t* chunk = blockIdx.y ? tchunk : vchunk;
-  const long long n = blockIdx.y ? nt : nv;
-  const long long base = (long long)blockIdx.x * kScanChunk;
-  if (base >= n) return;
-  __shared__ uint32_t warp_sums[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t v[8];
-  uint32_t local = 0;
-  const long long o = base + (long long)tid * 8;
+// ------------------------------------------------- masks of one word
+// Sign masks around word (i,j,w): rows (di,dj) in {0,1}^2 at "k" alignment (m) and
+// "k+1" alignment (s), plus validity.  All loads hit the L2-resident mask array.
+struct WordMasks {
+  uint32_t m[4], s[4];  // row = di*2 + dj
+  uint32_t vin, vz;     // lanes with a sample / lanes with k+1 < nz
+  bool hx, hy;
+};
+
+__device__ __forceinline__ WordMasks load_masks(const uint32_t* __restrict__ pos, const McDims& d, int i, int j,
+                                                int w) {
+  WordMasks r;
+  r.hx = i + 1 < d.nx;
+  r.hy = j + 1 < d.ny;
+  const bool hw = w + 1 < d.wz;
+  const long long base = ((long long)i * d.ny + j) * d.wz + w;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    v[e] = (o + e < n) ? cnt[o + e] : 0u;
-    local += v[e];
+  for (int row = 0; row < 4; ++row) {
+    const int di = row >> 1, dj = row & 1;
+    uint32_t cur = 0u, nxt = 0u;
+    if ((di == 0 || r.hx) && (dj == 0 || r.hy)) {
+      const long long wd = base + (long long)di * d.pw + (long long)dj * d.wz;
+      cur = __ldg(pos + wd);
+      if (hw) nxt = __ldg(pos + wd + 1);
+    }
+    r.m[row] = cur;
+    r.s[row] = (cur >> 1) | ((nxt & 1u) << 31);
   }
-  uint32_t inc = local;
-#pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
-    if (lane >= s) inc += y;
-  }
-  if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
-  uint32_t wbase = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    if (q < warp) wbase += warp_sums[q];
-  uint32_t run = wbase + inc - local;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    if (o + e < n) pre[o + e] = run;
-    run += v[e];
-  }
-  if (tid == 255) chunk[blockIdx.x] = wbase + inc;  // chunk total (exclusive base filled in phase B)
+  const int nin = min(32, d.nz - w * 32);
+  r.vin = nin >= 32 ? 0xffffffffu : ((1u << nin) - 1u);
+  const int nz1 = min(32, d.nz - 1 - w * 32);
+  r.vz = nz1 >= 32 ? 0xffffffffu : (nz1 <= 0 ? 0u : ((1u << nz1) - 1u));
+  return r;
 }
 
-// Phase B: one CTA turns the chunk totals into exclusive chunk bases (sequential
-// over tiles of 1024 with a running carry) and publishes the grand totals.
-__global__ void __launch_bounds__(1024) mc_scan_totals(uint32_t* __restrict__ vchunk, long long nvch,
-                                                       uint32_t* __restrict__ tchunk, long long ntch,
-                                                       long long v_last_plane_start_entry, const uint32_t* vpre,
-                                                       int emit_last_plane, smb_mc_counts* __restrict__ counts) {
+// crossing masks of the edges OWNED by the samples of word (i,j,w)
+__device__ __forceinline__ void owned_masks(const WordMasks& k, uint32_t& mx, uint32_t& my, uint32_t& mz) {
+  mx = k.hx ? ((k.m[0] ^ k.m[2]) & k.vin) : 0u;
+  my = k.hy ? ((k.m[0] ^ k.m[1]) & k.vin) : 0u;
+  mz = (k.m[0] ^ k.s[0]) & k.vz;
+}
+
+// lanes whose cell (i,j,k) has corners of both signs
+__device__ __forceinline__ uint32_t active_cells(const WordMasks& k) {
+  if (!(k.hx && k.hy)) return 0u;
+  const uint32_t a = k.m[0];
+  return ((a ^ k.s[0]) | (a ^ k.m[1]) | (a ^ k.s[1]) | (a ^ k.m[2]) | (a ^ k.s[2]) | (a ^ k.m[3]) | (a ^ k.s[3])) &
+         k.vz;
+}
+
+__device__ __forceinline__ uint32_t cell_case(const WordMasks& k, int lane) {
+  return ((k.m[0] >> lane) & 1u) | (((k.s[0] >> lane) & 1u) << 1) | (((k.m[1] >> lane) & 1u) << 2) |
+         (((k.s[1] >> lane) & 1u) << 3) | (((k.m[2] >> lane) & 1u) << 4) | (((k.s[2] >> lane) & 1u) << 5) |
+         (((k.m[3] >> lane) & 1u) << 6) | (((k.s[3] >> lane) & 1u) << 7);
+}
+
+// ------------------------------------------------------- K2 count + scan
+// blockIdx.x = i*cpp + c : chunk c of plane i.  Thread t owns the 8 consecutive words
+// c*2048 + 8t .. +7 of the plane (blocked, so the scan order is the canonical order).
+// The three counters are packed into one 64-bit lane (21/21/22 bits: a chunk holds at
+// most 2048*64 in-plane vertices, 2048*32 x-edge vertices, 2048*160 triangles).
+__global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos, McDims d, WordRec* __restrict__ rec,
+                                                ChunkRec* __restrict__ ctot) {
+  __shared__ unsigned char s_ntri[256];
+  __shared__ unsigned long long s_warp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s_ntri[tid] = SMB_MC_NTRI[tid];
+  __syncthreads();
+  const int i = (int)(blockIdx.x / d.cpp);
+  const int c = (int)(blockIdx.x - (long long)i * d.cpp);
+  const int jw0 = c * kChunkWords + tid * kWordsPerThread;
+
+  unsigned long long local[kWordsPerThread + 1];
+  unsigned long long sum = 0;
+#pragma unroll
+  for (int e = 0; e < kWordsPerThread; ++e) {
+    const int jw = jw0 + e;
+    unsigned long long cnt = 0;
+    if (jw < d.pw) {
+      const int j = jw / d.wz, w = jw - j * d.wz;
+      const WordMasks k = load_masks(pos, d, i, j, w);
+      uint32_t mx, my, mz;
+      owned_masks(k, mx, my, mz);
+      uint32_t act = active_cells(k);
+      uint32_t nt = 0;
+      while (act) {
+        const int b = __ffs(act) - 1;
+        act &= act - 1;
+        nt += s_ntri[cell_case(k, b)];
+      }
+      cnt = (unsigned long long)(__popc(my) + __popc(mz)) | ((unsigned long long)__popc(mx) << 21) |
+            ((unsigned long long)nt << 42);
+    }
+    local[e] = sum;  // exclusive within the thread
+    sum += cnt;
+  }
+  local[kWordsPerThread] = sum;
+  // CTA-wide exclusive scan of the per-thread sums
+  unsigned long long inc = sum;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, s);
+    if (lane >= s) inc += y;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long wbase = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const unsigned long long v = s_warp[q];
+    if (q < warp) wbase += v;
+    total += v;
+  }
+  const unsigned long long tbase = wbase + inc - sum;
+#pragma unroll
+  for (int e = 0; e < kWordsPerThread; ++e) {
+    const int jw = jw0 + e;
+    if (jw < d.pw) {
+      const unsigned long long p = tbase + local[e];
+      WordRec r;
+      r.a = (uint32_t)(p & 0x1fffffu);
+      r.b = (uint32_t)((p >> 21) & 0x1fffffu);
+      r.t = (uint32_t)(p >> 42);
+      r.info = (local[e + 1] != local[e]) ? 1u : 0u;
+      rec[(long long)i * d.pw + jw] = r;
+    }
+  }
+  if (tid == 0) {
+    ChunkRec cr;
+    cr.a = (uint32_t)(total & 0x1fffffu);
+    cr.b = (uint32_t)((total >> 21) & 0x1fffffu);
+    cr.t = (uint32_t)(total >> 42);
+    cr.pad = 0;
+    ctot[blockIdx.x] = cr;
+  }
+}
+
+// ------------------------------------------------------------ K3 totals
+// One CTA: exclusive scan of the chunk totals in canonical order.  Vertices: for each
+// plane i, the in-plane counts of its chunks, then the x-edge counts of its chunks.
+// Triangles: chunk order.  Sequential over tiles of 1024 with a running carry.
+__global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ ctot, ChunkRec* __restrict__ cbase,
+                                                  McDims d, int emit_last_plane, smb_mc_counts* __restrict__ counts) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t totals[2];
   for (int a = 0; a < 2; ++a) {
-    uint32_t* chunk = a ? tchunk : vchunk;
-    const long long n = a ? ntch : nvch;
+    const long long n = a ? d.nchunks : 2 * d.nchunks;
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (long long base = 0; base < n; base += 1024) {
       const long long idx = base + tid;
-      const uint32_t v = idx < n ? chunk[idx] : 0u;
+      uint32_t v = 0;
+      long long chunk = 0;
+      int grp = 0;
+      if (idx < n) {
+        if (a) {
+          chunk = idx;
+          v = ctot[chunk].t;
+        } else {
+          const long long i = idx / (2 * d.cpp);
+          const int r = (int)(idx - i * 2 * d.cpp);
+          grp = r / d.cpp;
+          chunk = i * d.cpp + (r - grp * d.cpp);
+          v = grp ? ctot[chunk].b : ctot[chunk].a;
+        }
+      }
       uint32_t inc = v;
 #pragma unroll
       for (int s = 1; s < 32; s <<= 1) {
@@ -283,9 +355,12 @@ __global__ void __launch_bounds__(1024) mc_scan_totals(uint32_t* __restrict__ vc
         warp_sums[lane] = winc - ws;  // exclusive warp base
       }
       __syncthreads();
-      const uint32_t carry = carry_s;
-      const uint32_t excl = carry + warp_sums[warp] + inc - v;
-      if (idx < n) chunk[idx] = excl;
+      const uint32_t excl = carry_s + warp_sums[warp] + inc - v;
+      if (idx < n) {
+        if (a) cbase[chunk].t = excl;
+        else if (grp) cbase[chunk].b = excl;
+        else cbase[chunk].a = excl;
+      }
       __syncthreads();
       if (tid == 1023) carry_s = excl + v;
       __syncthreads();
@@ -294,12 +369,10 @@ __global__ void __launch_bounds__(1024) mc_scan_totals(uint32_t* __restrict__ vc
     __syncthreads();
   }
   if (tid == 0) {
-    // chunk bases are final now, so prefix(entry) = vchunk[entry/chunk] + vpre[entry]
     long long stored = totals[0];
-    if (!emit_last_plane) {
-      const long long e = v_last_plane_start_entry;
-      stored = (long long)vchunk[e / kScanChunk] + vpre[e];
-    }
+    // a slab that is not the last one numbers, but does not store, the in-plane
+    // crossings of its last plane (they are the first vertices of the next slab)
+    if (!emit_last_plane) stored = cbase[(long long)(d.nx - 1) * d.cpp].a;
     counts->nverts = stored;
     counts->ntris = totals[1];
     counts->nverts_numbered = totals[0];
@@ -307,7 +380,7 @@ __global__ void __launch_bounds__(1024) mc_scan_totals(uint32_t* __restrict__ vc
   }
 }
 
-// ---------------------------------------------------------------- K3 emit
+// ---------------------------------------------------------------- K4 emit
 struct EmitParams {
   const float* grid;
   McDims d;
@@ -315,8 +388,9 @@ struct EmitParams {
   int x_origin, emit_last_plane, flags;
   float vdiv, vmul, vadd;
   long long id_offset;
+  const uint32_t* pos;
   const WordRec* rec;
-  const uint32_t *tcnt, *vpre, *tpre, *vchunk, *tchunk;
+  const ChunkRec* cbase;
   float* verts;
   long long* faces;
 };
@@ -332,151 +406,152 @@ struct NbrWord {  // what a triangle needs to number a vertex owned by a neighbo
   uint32_t v0, v1;  // global exclusive vertex prefix of the word: in-plane group / x-edge group
 };
 
-__global__ void __launch_bounds__(256) mc_emit(EmitParams p) {
-  __shared__ NbrWord nbr[8][8];  // [warp][row(di,dj)*2 + word(0: w, 1: w+1)]
+constexpr int kEmitWarps = 8;
+
+__global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
+  __shared__ NbrWord nbr[kEmitWarps][8];  // [warp][row(di,dj)*2 + word(0: w, 1: w+1)]
+  __shared__ signed char s_tri[256][16];
+  __shared__ unsigned char s_ntri[256];
+  for (int t = threadIdx.x; t < 256 * 16; t += blockDim.x) (&s_tri[0][0])[t] = (&SMB_MC_TRI[0][0])[t];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) s_ntri[t] = SMB_MC_NTRI[t];
+  __syncthreads();
+
   const McDims d = p.d;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int jblocks = (d.ny + 7) / 8;
-  long long b = blockIdx.x;
-  const int w = (int)(b % d.wz);
-  b /= d.wz;
-  const int jb = (int)(b % jblocks);
-  const int i = (int)(b / jblocks);
-  const int j = jb * 8 + warp;
-  if (j >= d.ny) return;
-  const long long rowwords = (long long)d.ny * d.wz;
-  const long long word = ((long long)i * d.ny + j) * d.wz + w;
-  const WordRec r = p.rec[word];
-  const uint32_t tc = p.tcnt[word];
-  if ((r.mx | r.my | r.mz) == 0u && tc == 0u) return;  // nothing owned, nothing to triangulate
-
-  const int k = w * 32 + lane;
+  const long long gwarp = (long long)blockIdx.x * kEmitWarps + warp;
+  const long long nwarps = (long long)gridDim.x * kEmitWarps;
+  const long long nbatch = (d.nwords + 31) / 32;
   const long long sy = d.nz, sx = (long long)d.ny * d.nz;
-  const long long pt = (long long)i * sx + (long long)j * sy + k;
   const uint32_t lt = (1u << lane) - 1u;
 
-  // ---- vertices owned by this word's samples ------------------------------
-  if (r.mx | r.my | r.mz) {
-    const long long e0 = ((long long)i * 2 + 0) * rowwords + (long long)j * d.wz + w;
-    const long long e1 = e0 + rowwords;
-    const long long v0 = (long long)p.vchunk[e0 / kScanChunk] + p.vpre[e0];
-    const long long v1 = (long long)p.vchunk[e1 / kScanChunk] + p.vpre[e1];
-    const bool by = (r.my >> lane) & 1u, bz = (r.mz >> lane) & 1u, bx = (r.mx >> lane) & 1u;
-    if (bx | by | bz) {
-      const float a = mc_val(p.grid, pt, p.sub, p.sign);
-      const float fi = (float)(p.x_origin + i), fj = (float)j, fk = (float)k;
-      const bool store_inplane = (i < d.nx - 1) || p.emit_last_plane;
-      const long long n_before = __popc(r.my & lt) + __popc(r.mz & lt);
-      if (by && store_inplane) {
-        const float bb = mc_val(p.grid, pt + sy, p.sub, p.sign);
-        const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-        float* o = p.verts + 3 * (v0 + n_before);
-        o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
-        o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
-        o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
-      }
-      if (bz && store_inplane) {
-        const float bb = mc_val(p.grid, pt + 1, p.sub, p.sign);
-        const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-        float* o = p.verts + 3 * (v0 + n_before + (by ? 1 : 0));
-        o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
-        o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
-        o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
-      }
-      if (bx) {
-        const float bb = mc_val(p.grid, pt + sx, p.sub, p.sign);
-        const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-        float* o = p.verts + 3 * (v1 + __popc(r.mx & lt));
-        o[0] = mc_xform(__fadd_rn(fi, t), p.flags, p.vdiv, p.vmul, p.vadd);
-        o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
-        o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
-      }
-    }
-  }
+  for (long long batch = gwarp; batch < nbatch; batch += nwarps) {
+    const long long myword = batch * 32 + lane;
+    uint32_t info = 0;
+    if (myword < d.nwords) info = __ldg(&p.rec[myword].info);
+    uint32_t todo = __ballot_sync(0xffffffffu, info & 1u);
+    while (todo) {  // warp-uniform
+      const int wb = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long word = batch * 32 + wb;
+      const int i = (int)(word / d.pw);
+      const int jw = (int)(word - (long long)i * d.pw);
+      const int j = jw / d.wz, w = jw - j * d.wz;
+      const int k = w * 32 + lane;
+      const long long pt = (long long)i * sx + (long long)j * sy + k;
 
-  // ---- triangles of this word's cells ---------------------------------------
-  if (tc == 0u) return;  // warp-uniform
-  // stage the 4 rows x 2 words this warp's cells can reference
-  if (lane < 8) {
-    const int row = lane >> 1, ww = lane & 1;
-    const int di = row >> 1, dj = row & 1;
-    NbrWord nw;
-    nw.mx = nw.my = nw.mz = 0u;
-    nw.v0 = nw.v1 = 0u;
-    if (i + di < d.nx && j + dj < d.ny && w + ww < d.wz) {
-      const long long wd = ((long long)(i + di) * d.ny + (j + dj)) * d.wz + (w + ww);
-      const WordRec q = p.rec[wd];
-      nw.mx = q.mx;
-      nw.my = q.my;
-      nw.mz = q.mz;
-      const long long e0 = ((long long)(i + di) * 2 + 0) * rowwords + (long long)(j + dj) * d.wz + (w + ww);
-      const long long e1 = e0 + rowwords;
-      nw.v0 = p.vchunk[e0 / kScanChunk] + p.vpre[e0];
-      nw.v1 = p.vchunk[e1 / kScanChunk] + p.vpre[e1];
-    }
-    nbr[warp][lane] = nw;
-  }
-  // sign masks of the four rows, "k" and "k+1" aligned
-  uint32_t m[4], s[4];
-#pragma unroll
-  for (int row = 0; row < 4; ++row) {
-    const int di = row >> 1, dj = row & 1;
-    uint32_t cur = 0u, nxt = 0u;
-    if (i + di < d.nx && j + dj < d.ny) {
-      const long long wd = ((long long)(i + di) * d.ny + (j + dj)) * d.wz + w;
-      cur = p.rec[wd].pos;
-      if (w + 1 < d.wz) nxt = p.rec[wd + 1].pos;
-    }
-    m[row] = cur;
-    s[row] = (cur >> 1) | ((nxt & 1u) << 31);
-  }
-  __syncwarp();
-
-  uint32_t cs = 0, ntri = 0;
-  if (i + 1 < d.nx && j + 1 < d.ny && k + 1 < d.nz) {
-    cs = ((m[0] >> lane) & 1u) | (((s[0] >> lane) & 1u) << 1) | (((m[1] >> lane) & 1u) << 2) |
-         (((s[1] >> lane) & 1u) << 3) | (((m[2] >> lane) & 1u) << 4) | (((s[2] >> lane) & 1u) << 5) |
-         (((m[3] >> lane) & 1u) << 6) | (((s[3] >> lane) & 1u) << 7);
-    ntri = SMB_MC_NTRI[cs];
-  }
-  uint32_t inc = ntri;
-#pragma unroll
-  for (int sft = 1; sft < 32; sft <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
-    if (lane >= sft) inc += y;
-  }
-  if (ntri == 0) return;
-  long long slot = (long long)p.tchunk[word / kScanChunk] + p.tpre[word] + (inc - ntri);
-  for (uint32_t t = 0; t < ntri; ++t) {
-    long long id[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int e = SMB_MC_TRI[cs][3 * t + q];
-      const int di = SMB_MC_EDGE_OWNER[e][0], dj = SMB_MC_EDGE_OWNER[e][1], dk = SMB_MC_EDGE_OWNER[e][2];
-      const int axis = SMB_MC_EDGE_OWNER[e][3];
-      const int bit = lane + dk;  // 0..32
-      const NbrWord& nw = nbr[warp][(di * 2 + dj) * 2 + (bit >> 5)];
-      const int bb = bit & 31;
-      const uint32_t below = (1u << bb) - 1u;
-      long long v;
-      if (axis == 0) {
-        v = (long long)nw.v1 + __popc(nw.mx & below);
-      } else {
-        v = (long long)nw.v0 + __popc(nw.my & below) + __popc(nw.mz & below);
-        if (axis == 2) v += (nw.my >> bb) & 1u;
+      // ---- stage the 4 rows x 2 words this word's cells can reference ----------
+      __syncwarp();
+      if (lane < 8) {
+        const int row = lane >> 1, ww = lane & 1;
+        const int di = row >> 1, dj = row & 1;
+        NbrWord nw;
+        nw.mx = nw.my = nw.mz = 0u;
+        nw.v0 = nw.v1 = 0u;
+        if (i + di < d.nx && j + dj < d.ny && w + ww < d.wz) {
+          const WordMasks km2 = load_masks(p.pos, d, i + di, j + dj, w + ww);
+          owned_masks(km2, nw.mx, nw.my, nw.mz);
+          const int jw2 = jw + dj * d.wz + ww;
+          const long long wd = (long long)(i + di) * d.pw + jw2;
+          const WordRec r2 = p.rec[wd];
+          const ChunkRec cb = p.cbase[(long long)(i + di) * d.cpp + jw2 / kChunkWords];
+          nw.v0 = cb.a + r2.a;
+          nw.v1 = cb.b + r2.b;
+        }
+        nbr[warp][lane] = nw;
       }
-      id[q] = v + p.id_offset;
+      const WordMasks km = load_masks(p.pos, d, i, j, w);
+      __syncwarp();
+      const NbrWord self = nbr[warp][0];
+
+      // ---- vertices owned by this word's samples --------------------------------
+      if (self.mx | self.my | self.mz) {
+        const bool by = (self.my >> lane) & 1u, bz = (self.mz >> lane) & 1u, bx = (self.mx >> lane) & 1u;
+        if (bx | by | bz) {
+          const float a = mc_val(p.grid, pt, p.sub, p.sign);
+          const float fi = (float)(p.x_origin + i), fj = (float)j, fk = (float)k;
+          const bool store_inplane = (i < d.nx - 1) || p.emit_last_plane;
+          const long long n_before = __popc(self.my & lt) + __popc(self.mz & lt);
+          if (by && store_inplane) {
+            const float bb = mc_val(p.grid, pt + sy, p.sub, p.sign);
+            const float t = __fdiv_rn(a, __fsub_rn(a, bb));
+            float* o = p.verts + 3 * ((long long)self.v0 + n_before);
+            o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
+            o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
+            o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
+          }
+          if (bz && store_inplane) {
+            const float bb = mc_val(p.grid, pt + 1, p.sub, p.sign);
+            const float t = __fdiv_rn(a, __fsub_rn(a, bb));
+            float* o = p.verts + 3 * ((long long)self.v0 + n_before + (by ? 1 : 0));
+            o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
+            o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
+            o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
+          }
+          if (bx) {
+            const float bb = mc_val(p.grid, pt + sx, p.sub, p.sign);
+            const float t = __fdiv_rn(a, __fsub_rn(a, bb));
+            float* o = p.verts + 3 * ((long long)self.v1 + __popc(self.mx & lt));
+            o[0] = mc_xform(__fadd_rn(fi, t), p.flags, p.vdiv, p.vmul, p.vadd);
+            o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
+            o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
+          }
+        }
+      }
+
+      // ---- triangles of this word's cells -----------------------------------------
+      const uint32_t act = active_cells(km);
+      if (act == 0u) continue;  // warp-uniform
+      uint32_t cs = 0, ntri = 0;
+      if ((act >> lane) & 1u) {
+        cs = cell_case(km, lane);
+        ntri = s_ntri[cs];
+      }
+      uint32_t inc = ntri;
+#pragma unroll
+      for (int sft = 1; sft < 32; sft <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
+        if (lane >= sft) inc += y;
+      }
+      if (ntri != 0) {
+        const WordRec r0 = p.rec[word];
+        const long long slot =
+            (long long)p.cbase[(long long)i * d.cpp + jw / kChunkWords].t + r0.t + (inc - ntri);
+        for (uint32_t t = 0; t < ntri; ++t) {
+          long long id[3];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            // edge e = 4*axis + 2*o1 + o2; owner offsets: axis 0 (0,o1,o2), axis 1 (o1,0,o2), axis 2 (o1,o2,0)
+            const int e = s_tri[cs][3 * t + q];
+            const int axis = e >> 2, o1 = (e >> 1) & 1, o2 = e & 1;
+            const int di = axis == 0 ? 0 : o1;
+            const int dj = axis == 0 ? o1 : (axis == 1 ? 0 : o2);
+            const int dk = axis == 2 ? 0 : o2;
+            const int bit = lane + dk;  // 0..32
+            const NbrWord& nw = nbr[warp][(di * 2 + dj) * 2 + (bit >> 5)];
+            const int bb = bit & 31;
+            const uint32_t below = (1u << bb) - 1u;
+            long long v;
+            if (axis == 0) {
+              v = (long long)nw.v1 + __popc(nw.mx & below);
+            } else {
+              v = (long long)nw.v0 + __popc(nw.my & below) + __popc(nw.mz & below);
+              if (axis == 2) v += (nw.my >> bb) & 1u;
+            }
+            id[q] = v + p.id_offset;
+          }
+          long long* o = p.faces + 3 * (slot + t);
+          if (p.flags & SMB_MC_FLIP) {
+            o[0] = id[1];
+            o[1] = id[0];
+          } else {
+            o[0] = id[0];
+            o[1] = id[1];
+          }
+          o[2] = id[2];
+        }
+      }
     }
-    long long* o = p.faces + 3 * (slot + t);
-    if (p.flags & SMB_MC_FLIP) {
-      o[0] = id[1];
-      o[1] = id[0];
-    } else {
-      o[0] = id[0];
-      o[1] = id[1];
-    }
-    o[2] = id[2];
   }
 }
 
@@ -494,6 +569,8 @@ __global__ void __launch_bounds__(256) mc_minmax(const float* __restrict__ grid,
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
   }
+  lo += 0.0f;  // canonicalise -0.0 -> +0.0 (the int ordering below would rank -0.0 below every negative)
+  hi += 0.0f;
   if ((threadIdx.x & 31) == 0) {
     // float atomic min/max through the ordered-int trick
     int* o = reinterpret_cast<int*>(out);
@@ -511,13 +588,18 @@ __global__ void mc_minmax_init(float* out) {
 
 using namespace smb;
 
+static int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
 extern "C" size_t smb_mc_workspace_bytes(int nx, int ny, int nz) {
   if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
   McDims d = make_dims(nx, ny, nz);
   return carve(nullptr, d).bytes;
 }
-
-static long long classify_blocks(const McDims& d) { return (long long)d.nx * ((d.ny + 7) / 8) * d.wz; }
 
 extern "C" int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub, float sign, int emit_last_plane,
                             void* workspace, size_t workspace_bytes, smb_mc_counts* counts_dev, void* stream) {
@@ -525,15 +607,15 @@ extern "C" int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub
   McDims d = make_dims(nx, ny, nz);
   McWorkspace w = carve(workspace, d);
   if (w.bytes > workspace_bytes) return SMB_ERR_WORKSPACE;
-  const long long blocks = classify_blocks(d);
-  if (blocks > 0x7fffffffLL) return SMB_ERR_BAD_ARG;
+  if (d.nchunks > 0x7fffffffLL) return SMB_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  mc_classify<<<(unsigned)blocks, 256, 0, st>>>(grid, d, sub, sign, w.rec, w.vcnt, w.tcnt);
-  const long long nv = 2 * d.nwords, nt = d.nwords;
-  const long long vch = (nv + kScanChunk - 1) / kScanChunk, tch = (nt + kScanChunk - 1) / kScanChunk;
-  mc_scan_chunks<<<dim3((unsigned)vch, 2), 256, 0, st>>>(w.vcnt, w.vpre, w.vchunk, nv, w.tcnt, w.tpre, w.tchunk, nt);
-  const long long last_entry = ((long long)(nx - 1) * 2) * d.ny * d.wz;
-  mc_scan_totals<<<1, 1024, 0, st>>>(w.vchunk, vch, w.tchunk, tch, last_entry, w.vpre, emit_last_plane, counts_dev);
+  const int sms = sm_count();
+  // K1: up to 8 CTAs of 8 warps per SM, each warp 8 words per iteration
+  long long sg = (d.nwords + 63) / 64;
+  if (sg > (long long)sms * 8) sg = (long long)sms * 8;
+  mc_signs<<<(unsigned)sg, 256, 0, st>>>(grid, d, sub, sign, w.pos);
+  mc_count<<<(unsigned)d.nchunks, 256, 0, st>>>(w.pos, d, w.rec, w.ctot);
+  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 
@@ -556,16 +638,16 @@ extern "C" int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub,
   p.vmul = vmul;
   p.vadd = vadd;
   p.id_offset = vertex_id_offset;
+  p.pos = w.pos;
   p.rec = w.rec;
-  p.tcnt = w.tcnt;
-  p.vpre = w.vpre;
-  p.tpre = w.tpre;
-  p.vchunk = w.vchunk;
-  p.tchunk = w.tchunk;
+  p.cbase = w.cbase;
   p.verts = verts;
   p.faces = reinterpret_cast<long long*>(faces);
-  const long long blocks = classify_blocks(d);
-  mc_emit<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  const long long nbatch = (d.nwords + 31) / 32;
+  long long blocks = (nbatch + kEmitWarps - 1) / kEmitWarps;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  mc_emit<<<(unsigned)blocks, kEmitWarps * 32, 0, (cudaStream_t)stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 

@@ -70,7 +70,7 @@ class TriplaneNeRFRenderer(BaseModule):
         input_shape = positions.shape[:-1]
         pack, scene = self._planes(decoder, triplane)
         out = runtime.query_points(scene, pack, positions.reshape(-1, 3), self.cfg.radius, self.cfg.density_bias)
-        return {k: v.view(*input_shape, -1) for k, v in out.items()}
+        return {k: v.view(*input_shape, v.shape[-1]) for k, v in out.items()}
 
     def query_lattice(
         self,

@@ -127,7 +127,9 @@ def test_lattice_vs_cpu_oracle(golden):
     ref = fo.grid_density(R, tp.numpy(), ws, bs)
     a32 = runtime.query_lattice(scene, pack, ax, R, RADIUS, -1.0, precision="fp32").cpu().numpy()
     atc = runtime.query_lattice(scene, pack, ax, R, RADIUS, -1.0, precision="tc").cpu().numpy()
-    assert np.abs(a32 / ref - 1).max() < 2e-5
+    # density_act = exp(logit): its relative error is the logit's absolute error; two fp32
+    # evaluations of a 10-layer MLP in different summation orders differ by a few 1e-5
+    assert np.abs(a32 / ref - 1).max() < 1e-4
     assert np.abs(atc / ref - 1).max() < TC_MAX_REL
 
 
