@@ -8,25 +8,35 @@
 // Work decomposition
 //   tile   = 128 consecutive z-samples of one (x,y) lattice line = the M dimension
 //            of one UMMA (M=128, N=64, K=64 per hidden layer).
-//   CTA    = kWG independent warpgroups (128 threads each), persistent, one CTA/SM.
-//            A warpgroup owns a tile end to end, so there is no cross-warpgroup
-//            hand-off; the SM's warp schedulers interleave the kWG pipelines and
-//            hide each other's MMA / TMEM latencies.
+//   slot   = the on-chip home of one tile in flight: a 16 KB fp16 A tile (K-major,
+//            128B swizzle), the layer-0 z-row table T + constant vector c (fp32) and a
+//            64-column TMEM accumulator.
+//   CTA    = persistent, one per SM, warp-specialised:
+//            * kWG consumer warpgroups (128 threads each).  A warpgroup owns TWO slots
+//              and ping-pongs between them layer by layer: while the tensor core runs
+//              layer l+1 of one tile the warpgroup runs the SiLU epilogue of the other,
+//              so neither the MMA round trip nor the hand-off is exposed.  There is no
+//              warpgroup-wide barrier: every warp publishes its 32 rows, bumps a
+//              shared-memory counter, and whichever warp arrives last issues the
+//              tcgen05.mma (one elected thread) and commits it to the slot's mbarrier.
+//            * kWG producer warps (one per consumer warpgroup) build T and c for the
+//              warpgroup's next tiles from the L2-resident projected planes, so global
+//              load latency never sits in a consumer's instruction stream.
 //   layer 0 is evaluated from the projected planes Q_p = (W0/2).plane_p (fp32):
-//            on a z-line the (x,y) plane contributes a constant vector and the
+//            on a z-line the (x,y) plane contributes a constant vector c and the
 //            (x,z),(y,z) planes share the same z taps, so the pre-activation is
-//            c + w0*T[h0] + w1*T[h1] with a per-tile table T built cooperatively
-//            in shared memory.  Exactly the reference's interpolate->Linear in exact
-//            arithmetic, evaluated in fp32.
-//   layers 1..L-1 (+ the 64->4 head): activations are written as fp16 into the
-//            K-major 128B-swizzled A tile in shared memory, one thread issues
-//            tcgen05.mma (weights resident in shared memory for the whole kernel,
-//            brought in by the bulk-copy engine), the accumulator comes back with
-//            tcgen05.ld, bias + SiLU are applied in registers.
+//            c + w0*T[h0] + w1*T[h1].  Exactly the reference's interpolate->Linear in
+//            exact arithmetic, evaluated in fp32.
+//   layers 1..L-1 (+ the 64->4 head): activations are written as fp16 into the A tile,
+//            weights stay resident in shared memory for the whole kernel (brought in by
+//            the bulk-copy engine), the accumulator comes back with tcgen05.ld, bias +
+//            SiLU are applied in registers.
 //   SiLU    silu(x) = h + h*tanh(h), h = x/2; the 1/2 is folded into weights and
-//            biases on the host, so one MUFU.TANH + one FFMA per activation.
+//            biases on the host, so one MUFU.TANH + one FFMA per activation.  The SFU
+//            (16 tanh/clk/SM, 576 per sample) is the practical bound of this kernel.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "field_common.cuh"
 #include "ptx_sm100.cuh"
@@ -34,12 +44,12 @@
 namespace smb {
 
 constexpr int kTileM = 128;
-constexpr int kTRows = 66;   // max plane rows one tile's z-range touches, incl. zero borders
-constexpr int kTPitch = 68;  // floats per T row: 64 + 4 pad (adjacent rows land 4 banks apart)
+constexpr int kTRowsMax = 66;  // Hp + 2 zero borders for Hp = 64
+constexpr int kTPitch = 68;    // floats per T row: 64 + 4 pad (adjacent rows land 4 banks apart)
 constexpr int kWBytes = kHid * kHid * 2;     // 8192: one hidden layer, fp16
 constexpr int kWFinalBytes = 16 * kHid * 2;  // 2048: head padded to N=16
 constexpr int kABytes = kTileM * kHid * 2;   // 16384
-constexpr int kWgBytes = ((kABytes + kTRows * kTPitch * 4 + kHid * 4 + 1023) / 1024) * 1024;
+constexpr int kSlotsPerWG = 2;
 
 struct TcParams {
   const float* planes_q;  // (3,H,W,64) fp32
@@ -47,20 +57,59 @@ struct TcParams {
   const float* bias0_half;          // b0/2 (64)
   const float* axis_u;
   int R, x_begin, nx, H, W, align_corners, n_hidden;
+  int trows;       // rows of a slot's T table
+  int slot_bytes;  // 1024-aligned: A | T | c
   float density_bias;
   float* out_act;
   float* out_raw;
-  int* error_flag;
+  int wait_ns;  // suspend-time hint of the consumer mbarrier waits (0: plain try_wait polling)
+  int dbg;  // developer timing experiments only (SMB_TC_DEBUG); 0 in production
 };
 
 __host__ __device__ inline int tc_weight_bytes(int n_hidden) {
-  // hidden images + head image + biases for layers 1..n_hidden-1 are not separate:
   // the blob keeps [hidden | head | bias_half (n_hidden x 64) | bias_final (4)] contiguous
   return (n_hidden - 1) * kWBytes + kWFinalBytes + n_hidden * kHid * 4 + 16;
 }
+__host__ __device__ inline int tc_slot_bytes(int trows) {
+  return ((kABytes + trows * kTPitch * 4 + kHid * 4 + 1023) / 1024) * 1024;
+}
 
-template <int kWG>
-__global__ void __launch_bounds__(kWG * 128, 1) lattice_tc_kernel(TcParams p) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_inc_acq_rel(uint32_t addr) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+  return old;
+}
+
+// developer instrumentation (kDbg & 256): clock64 stamps of block 0 / warpgroup 0
+__device__ long long g_trace[4 * 512 * 4];
+
+struct TileGeom {  // what producer and consumer both derive from a tile index
+  long long line;  // (i*R + j)
+  int i, j, k0, nvalid, hlo, nrow;
+};
+
+__device__ __forceinline__ TileGeom tile_geom(long long t, int tiles_per_line, const TcParams& p) {
+  TileGeom g;
+  const int seg = (int)(t % tiles_per_line);
+  g.line = t / tiles_per_line;
+  g.i = (int)(g.line / p.R);
+  g.j = (int)(g.line - (long long)g.i * p.R);
+  g.k0 = seg * kTileM;
+  g.nvalid = min(kTileM, p.R - g.k0);
+  const float fz_first = unnormalize(p.axis_u[g.k0], p.H, p.align_corners);
+  const float fz_last = unnormalize(p.axis_u[g.k0 + g.nvalid - 1], p.H, p.align_corners);
+  g.hlo = (int)floorf(fz_first);
+  g.nrow = min((int)floorf(fz_last) + 1 - g.hlo + 1, p.trows);
+  return g;
+}
+
+template <int kWG, int kDbg>
+__global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
+  constexpr int kSlots = kWG * kSlotsPerWG;
+  constexpr int kConsumerWarps = kWG * 4;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nh = p.n_hidden;
   const int wbytes = tc_weight_bytes(nh);
@@ -68,33 +117,32 @@ __global__ void __launch_bounds__(kWG * 128, 1) lattice_tc_kernel(TcParams p) {
   unsigned char* sWf = sW + (nh - 1) * kWBytes;               // head image
   const float* sBias = reinterpret_cast<const float*>(sWf + kWFinalBytes);  // [nh][64], row l = b_l/2
   const float* sBiasF = sBias + nh * kHid;                    // 4
-  unsigned char* wg_region = smem + ((wbytes + 1023) / 1024) * 1024;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wg_region + kWG * kWgBytes);  // [0]=weights, [1+wg]=mma
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + kWG);
+  unsigned char* slots = smem + ((wbytes + 1023) / 1024) * 1024;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + kSlots * p.slot_bytes);
+  // bars[0] = weights, then per slot s: [1+4s] t_full, [2+4s] t_empty, [3+4s] acc_full, [4+4s] a_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 4 * kSlots);
 
   const int tid_cta = threadIdx.x;
-  const int wg = tid_cta >> 7;
-  const int tid = tid_cta & 127;
-  const int warp_in_wg = tid >> 5;
-
-  unsigned char* sA = wg_region + wg * kWgBytes;
-  float* sT = reinterpret_cast<float*>(sA + kABytes);
-  float* sC = sT + kTRows * kTPitch;
-
-  const uint32_t bar_w = smem_u32(&bars[0]);
-  const uint32_t bar_mma = smem_u32(&bars[1 + wg]);
+  const int wid = tid_cta >> 5;
+  const int lane = tid_cta & 31;
 
   // ---- one-time setup ----------------------------------------------------
   if (tid_cta == 0) {
-    mbar_init(bar_w, 1);
-    for (int g = 0; g < kWG; ++g) mbar_init(smem_u32(&bars[1 + g]), 1);
+    mbar_init(smem_u32(&bars[0]), 1);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(smem_u32(&bars[1 + 4 * s]), 1);    // t_full: the producer warp (one elected lane)
+      mbar_init(smem_u32(&bars[2 + 4 * s]), 4);    // t_empty: one elected lane per consumer warp
+      mbar_init(smem_u32(&bars[3 + 4 * s]), 1);    // acc_full: tcgen05.commit
+      mbar_init(smem_u32(&bars[4 + 4 * s]), 4);    // a_full: one elected lane per consumer warp
+    }
     mbar_fence_init();
   }
-  if (tid_cta < 32) tmem_alloc<kWG * 64>(smem_u32(tmem_slot));
+  if (wid == 0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t bar_w = smem_u32(&bars[0]);
   if (tid_cta == 0) {
     mbar_expect_tx(bar_w, (uint32_t)wbytes);
     // weights + biases via the bulk-copy engine (UBLKCP), 8 KB pieces
@@ -106,181 +154,290 @@ __global__ void __launch_bounds__(kWG * 128, 1) lattice_tc_kernel(TcParams p) {
     }
   }
 
-  const uint32_t tmem_acc = tmem_base + (uint32_t)(wg * 64) + ((uint32_t)(warp_in_wg * 32) << 16);
-  const uint32_t idesc_hidden = umma_idesc_f16_f32(128, 64);
-  const uint32_t idesc_head = umma_idesc_f16_f32(128, 16);
-  const uint32_t a_addr = smem_u32(sA);
-  uint32_t phase = 0;
-  bool weights_ready = false;
-
   const int tiles_per_line = (p.R + kTileM - 1) / kTileM;
   const long long ntiles = (long long)p.nx * p.R * tiles_per_line;
   const long long HW = (long long)p.H * p.W;
-  const float* Q0 = p.planes_q;
-  const float* Q1 = Q0 + HW * kHid;
-  const float* Q2 = Q1 + HW * kHid;
 
-  for (long long t = (long long)blockIdx.x * kWG + wg; t < ntiles; t += (long long)gridDim.x * kWG) {
-    const int seg = (int)(t % tiles_per_line);
-    const long long line = t / tiles_per_line;
-    const int i = (int)(line / p.R);
-    const int j = (int)(line - (long long)i * p.R);
-    const int k0 = seg * kTileM;
-    const int nvalid = min(kTileM, p.R - k0);
-
-    // ---- per-tile constants: c vector and T table --------------------------
-    const float ux = p.axis_u[p.x_begin + i];
-    const float uy = p.axis_u[j];
-    const Tap2 txw = make_tap(ux, p.W, p.align_corners);  // x on the W axis (planes 0,1)
-    const Tap2 tyw = make_tap(uy, p.W, p.align_corners);  // y on the W axis (plane 2)
-    const Tap2 tyh = make_tap(uy, p.H, p.align_corners);  // y on the H axis (plane 0)
-    const float fz_first = unnormalize(p.axis_u[k0], p.H, p.align_corners);
-    const float fz_last = unnormalize(p.axis_u[k0 + nvalid - 1], p.H, p.align_corners);
-    const int hlo = (int)floorf(fz_first);
-    const int nrow = min((int)floorf(fz_last) + 1 - hlo + 1, kTRows);
-
-    if (tid < kHid) {
-      const int n = tid;
-      const float q00 = __ldg(Q0 + ((long long)tyh.i0 * p.W + txw.i0) * kHid + n);
-      const float q01 = __ldg(Q0 + ((long long)tyh.i0 * p.W + txw.i1) * kHid + n);
-      const float q10 = __ldg(Q0 + ((long long)tyh.i1 * p.W + txw.i0) * kHid + n);
-      const float q11 = __ldg(Q0 + ((long long)tyh.i1 * p.W + txw.i1) * kHid + n);
-      float c = __ldg(p.bias0_half + n);
-      c += tyh.w0 * (txw.w0 * q00 + txw.w1 * q01) + tyh.w1 * (txw.w0 * q10 + txw.w1 * q11);
-      sC[n] = c;
-    }
-    {
-      const int n4 = tid & 15;
-      for (int r = tid >> 4; r < nrow; r += 8) {
-        const int h = hlo + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h >= 0 && h < p.H) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i0) * kHid) + n4);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i1) * kHid) + n4);
-          const float4 c = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i0) * kHid) + n4);
-          const float4 d = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i1) * kHid) + n4);
-          v.x = txw.w0 * a.x + txw.w1 * b.x + tyw.w0 * c.x + tyw.w1 * d.x;
-          v.y = txw.w0 * a.y + txw.w1 * b.y + tyw.w0 * c.y + tyw.w1 * d.y;
-          v.z = txw.w0 * a.z + txw.w1 * b.z + tyw.w0 * c.z + tyw.w1 * d.z;
-          v.w = txw.w0 * a.w + txw.w1 * b.w + tyw.w0 * c.w + tyw.w1 * d.w;
+  if (wid >= kConsumerWarps + kWG) {
+    // =================================================================== MMA issuer
+    // One warp per consumer warpgroup, walking the warpgroup's (tile pair, layer, slot)
+    // sequence in the same order: wait until all 128 rows of the A tile are published,
+    // issue the next layer's tcgen05.mma from one lane, commit it to the slot's acc_full.
+    const int g = wid - kConsumerWarps - kWG;
+    const uint32_t idesc_hidden = umma_idesc_f16_f32(128, 64);
+    const uint32_t idesc_head = umma_idesc_f16_f32(128, 16);
+    uint32_t par_a = 0;
+    mbar_wait(bar_w, 0);  // weights resident
+    for (long long n = 0;; ++n) {
+      const long long t0 = 2 * ((n * gridDim.x + blockIdx.x) * kWG + g);
+      if (t0 >= ntiles) break;
+      const bool have1 = t0 + 1 < ntiles;
+      for (int l = 0; l < nh; ++l) {
+#pragma unroll 1
+        for (int s = 0; s < kSlotsPerWG; ++s) {
+          if (s == 1 && !have1) break;
+          const int slot = g * kSlotsPerWG + s;
+          mbar_wait_sleep(smem_u32(&bars[4 + 4 * slot]), (par_a >> s) & 1u, (uint32_t)p.wait_ns);
+          par_a ^= 1u << s;
+          tc_fence_after();
+          if (lane == 0) {
+            const int L = l + 1;
+            const bool head = (L == nh);
+            const uint64_t a_desc = umma_desc_k_sw128(smem_u32(slots + slot * p.slot_bytes));
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(head ? sWf : sW + (L - 1) * kWBytes));
+            const uint32_t idesc = head ? idesc_head : idesc_hidden;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 64);
+#pragma unroll
+            for (int kc = 0; kc < kHid / 16; ++kc)  // K = 16 per instruction: +32 B along the swizzled row
+              if (!(kDbg & 4)) umma_f16_ss(d_tmem, a_desc + 2 * kc, b_desc + 2 * kc, idesc, kc > 0 ? 1u : 0u);
+            umma_commit(smem_u32(&bars[3 + 4 * slot]));
+          }
+          __syncwarp();
         }
-        *reinterpret_cast<float4*>(sT + r * kTPitch + 4 * n4) = v;
       }
     }
-    named_bar_sync(1 + wg, 128);
+  } else if (wid >= kConsumerWarps) {
+    // =================================================================== producer
+    const int g = wid - kConsumerWarps;
+    const float* Q0 = p.planes_q;
+    const float* Q1 = Q0 + HW * kHid;
+    const float* Q2 = Q1 + HW * kHid;
+    uint32_t par_empty = 0x3;  // bit s: parity to wait on; a fresh barrier passes a wait on parity 1
+    for (long long n = 0;; ++n) {
+      const long long t0 = 2 * ((n * gridDim.x + blockIdx.x) * kWG + g);
+      if (t0 >= ntiles) break;
+#pragma unroll 1
+      for (int s = 0; s < kSlotsPerWG; ++s) {
+        const long long t = t0 + s;
+        if (t >= ntiles) break;
+        const int slot = g * kSlotsPerWG + s;
+        unsigned char* sA = slots + slot * p.slot_bytes;
+        float* sT = reinterpret_cast<float*>(sA + kABytes);
+        float* sC = sT + p.trows * kTPitch;
+        const TileGeom tg = tile_geom(t, tiles_per_line, p);
+        const float ux = p.axis_u[p.x_begin + tg.i];
+        const float uy = p.axis_u[tg.j];
+        const Tap2 txw = make_tap(ux, p.W, p.align_corners);  // x on the W axis (planes 0,1)
+        const Tap2 tyw = make_tap(uy, p.W, p.align_corners);  // y on the W axis (plane 2)
+        const Tap2 tyh = make_tap(uy, p.H, p.align_corners);  // y on the H axis (plane 0)
 
-    // ---- layer 0: this thread's sample (row m of the tile) ------------------
-    const int m = tid;
-    const uint32_t a_row = a_addr + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
-    {
-      const int kk = min(k0 + m, p.R - 1);
-      const float fz = unnormalize(p.axis_u[kk], p.H, p.align_corners);
-      const float hf = floorf(fz);
-      const float w1 = __fsub_rn(fz, hf);
-      const float w0 = __fsub_rn(1.0f, w1);
-      int r0 = (int)hf - hlo;
-      r0 = min(max(r0, 0), kTRows - 2);
-      const float4* t0 = reinterpret_cast<const float4*>(sT + r0 * kTPitch);
-      const float4* t1 = reinterpret_cast<const float4*>(sT + (r0 + 1) * kTPitch);
-      const float4* cc = reinterpret_cast<const float4*>(sC);
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        const float4 a0 = t0[2 * c8], a1 = t0[2 * c8 + 1];
-        const float4 b0 = t1[2 * c8], b1 = t1[2 * c8 + 1];
-        const float4 c0 = cc[2 * c8], c1 = cc[2 * c8 + 1];
-        float h[8];
-        h[0] = c0.x + w0 * a0.x + w1 * b0.x;
-        h[1] = c0.y + w0 * a0.y + w1 * b0.y;
-        h[2] = c0.z + w0 * a0.z + w1 * b0.z;
-        h[3] = c0.w + w0 * a0.w + w1 * b0.w;
-        h[4] = c1.x + w0 * a1.x + w1 * b1.x;
-        h[5] = c1.y + w0 * a1.y + w1 * b1.y;
-        h[6] = c1.z + w0 * a1.z + w1 * b1.z;
-        h[7] = c1.w + w0 * a1.w + w1 * b1.w;
-        uint32_t q0 = pack_half2(silu_from_half_arg(h[0]), silu_from_half_arg(h[1]));
-        uint32_t q1 = pack_half2(silu_from_half_arg(h[2]), silu_from_half_arg(h[3]));
-        uint32_t q2 = pack_half2(silu_from_half_arg(h[4]), silu_from_half_arg(h[5]));
-        uint32_t q3 = pack_half2(silu_from_half_arg(h[6]), silu_from_half_arg(h[7]));
-        const uint32_t dst = a_row + (uint32_t)((c8 ^ (m & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(q0), "r"(q1), "r"(q2), "r"(q3)
-                     : "memory");
-      }
-    }
+        mbar_wait_sleep(smem_u32(&bars[2 + 4 * slot]), (par_empty >> s) & 1u, 20000u);
+        par_empty ^= 1u << s;
 
-    if (!weights_ready) {  // first tile only: weights must have landed before the first MMA
-      mbar_wait(bar_w, 0);
-      weights_ready = true;
-    }
-
-    // ---- layers 1 .. nh-1 (hidden, N=64) and the head (N=16) -----------------
-    for (int l = 1; l <= nh; ++l) {
-      const bool head = (l == nh);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      named_bar_sync(1 + wg, 128);
-      if (tid == 0) {
-        tc_fence_after();
-        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_k_sw128(smem_u32(head ? sWf : sW + (l - 1) * kWBytes));
-        const uint32_t idesc = head ? idesc_head : idesc_hidden;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(wg * 64);
-#pragma unroll
-        for (int kc = 0; kc < kHid / 16; ++kc)  // K = 16 per instruction: +32 B along the swizzled row
-          umma_f16_ss(d_tmem, a_desc + 2 * kc, b_desc + 2 * kc, idesc, kc > 0 ? 1u : 0u);
-        umma_commit(bar_mma);
-      }
-      mbar_wait(bar_mma, phase);
-      phase ^= 1;
-      tc_fence_after();
-
-      if (!head) {
-        const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(tmem_acc + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const float4 b0 = bl[half * 8 + 2 * c8], b1 = bl[half * 8 + 2 * c8 + 1];
-            const float h0 = __uint_as_float(r[8 * c8 + 0]) + b0.x;
-            const float h1 = __uint_as_float(r[8 * c8 + 1]) + b0.y;
-            const float h2 = __uint_as_float(r[8 * c8 + 2]) + b0.z;
-            const float h3 = __uint_as_float(r[8 * c8 + 3]) + b0.w;
-            const float h4 = __uint_as_float(r[8 * c8 + 4]) + b1.x;
-            const float h5 = __uint_as_float(r[8 * c8 + 5]) + b1.y;
-            const float h6 = __uint_as_float(r[8 * c8 + 6]) + b1.z;
-            const float h7 = __uint_as_float(r[8 * c8 + 7]) + b1.w;
-            uint32_t q0 = pack_half2(silu_from_half_arg(h0), silu_from_half_arg(h1));
-            uint32_t q1 = pack_half2(silu_from_half_arg(h2), silu_from_half_arg(h3));
-            uint32_t q2 = pack_half2(silu_from_half_arg(h4), silu_from_half_arg(h5));
-            uint32_t q3 = pack_half2(silu_from_half_arg(h6), silu_from_half_arg(h7));
-            const int chunk = half * 4 + c8;
-            const uint32_t dst = a_row + (uint32_t)((chunk ^ (m & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(q0), "r"(q1), "r"(q2), "r"(q3)
-                         : "memory");
+        {  // c vector: lane owns n = 2*lane, 2*lane+1
+          const float2 q00 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i0 * p.W + txw.i0) * kHid) + lane);
+          const float2 q01 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i0 * p.W + txw.i1) * kHid) + lane);
+          const float2 q10 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i1 * p.W + txw.i0) * kHid) + lane);
+          const float2 q11 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i1 * p.W + txw.i1) * kHid) + lane);
+          const float2 b0 = __ldg(reinterpret_cast<const float2*>(p.bias0_half) + lane);
+          float2 c;
+          c.x = b0.x + (tyh.w0 * (txw.w0 * q00.x + txw.w1 * q01.x) + tyh.w1 * (txw.w0 * q10.x + txw.w1 * q11.x));
+          c.y = b0.y + (tyh.w0 * (txw.w0 * q00.y + txw.w1 * q01.y) + tyh.w1 * (txw.w0 * q10.y + txw.w1 * q11.y));
+          reinterpret_cast<float2*>(sC)[lane] = c;
+        }
+        {  // T rows: lane owns float4 column n4 of rows (lane>>4), (lane>>4)+2, ...
+          const int n4 = lane & 15;
+#pragma unroll 4
+          for (int r = lane >> 4; r < tg.nrow; r += 2) {
+            const int h = tg.hlo + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h >= 0 && h < p.H) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i0) * kHid) + n4);
+              const float4 b = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i1) * kHid) + n4);
+              const float4 c = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i0) * kHid) + n4);
+              const float4 d = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i1) * kHid) + n4);
+              v.x = txw.w0 * a.x + txw.w1 * b.x + tyw.w0 * c.x + tyw.w1 * d.x;
+              v.y = txw.w0 * a.y + txw.w1 * b.y + tyw.w0 * c.y + tyw.w1 * d.y;
+              v.z = txw.w0 * a.z + txw.w1 * b.z + tyw.w0 * c.z + tyw.w1 * d.z;
+              v.w = txw.w0 * a.w + txw.w1 * b.w + tyw.w0 * c.w + tyw.w1 * d.w;
+            }
+            *reinterpret_cast<float4*>(sT + r * kTPitch + 4 * n4) = v;
           }
         }
-      } else {
-        uint32_t r[4];
-        tmem_ld4(tmem_acc, r);
-        tmem_ld_wait();
-        const float d = __uint_as_float(r[0]) + sBiasF[0];
-        if (m < nvalid) {
-          const long long o = (line * p.R) + k0 + m;
-          if (p.out_raw) p.out_raw[o] = d;
-          p.out_act[o] = expf(__fadd_rn(d, p.density_bias));
+        __syncwarp();  // all lanes' table stores are ordered before the elected arrive (release)
+        if (lane == 0) mbar_arrive(smem_u32(&bars[1 + 4 * slot]));  // t_full
+      }
+    }
+  } else {
+    // =================================================================== consumer
+    const int wg = wid >> 2;
+    const int q = wid & 3;               // TMEM lane quarter this warp may access
+    const int m = (q << 5) | lane;       // row of the tile owned by this thread
+    uint32_t par_t = 0, par_acc = 0;     // bit s: parity of the next completion to wait for
+
+    mbar_wait(bar_w, 0);  // weights resident before anyone may issue an MMA
+
+    for (long long n = 0;; ++n) {
+      const long long t0 = 2 * ((n * gridDim.x + blockIdx.x) * kWG + wg);
+      if (t0 >= ntiles) break;
+      const bool have1 = t0 + 1 < ntiles;
+      const TileGeom g0 = tile_geom(t0, tiles_per_line, p);
+      const TileGeom g1 = tile_geom(have1 ? t0 + 1 : t0, tiles_per_line, p);
+
+      for (int l = 0; l <= nh; ++l) {
+#pragma unroll 1
+        for (int s = 0; s < kSlotsPerWG; ++s) {
+          if (s == 1 && !have1) break;
+          const int slot = wg * kSlotsPerWG + s;
+          unsigned char* sA = slots + slot * p.slot_bytes;
+          const float* sT = reinterpret_cast<const float*>(sA + kABytes);
+          const float* sC = sT + p.trows * kTPitch;
+          const uint32_t a_addr = smem_u32(sA);
+          unsigned char* a_rowp = sA + (m >> 3) * 1024 + (m & 7) * 128;  // this thread's 128-byte row
+          const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 64);
+          const uint32_t tmem_acc = d_tmem + ((uint32_t)(q * 32) << 16);
+          const int k0 = s ? g1.k0 : g0.k0;
+          long long tr0 = 0, tr1 = 0, tr2 = 0;
+          if (kDbg & 256) tr0 = clock64();
+
+          if (l == 0) {
+            // ---- layer 0 from the producer's table --------------------------------
+            const int hlo = s ? g1.hlo : g0.hlo;
+            const int kk = min(k0 + m, p.R - 1);
+            const float fz = unnormalize(p.axis_u[kk], p.H, p.align_corners);
+            const float hf = floorf(fz);
+            const float w1 = __fsub_rn(fz, hf);
+            const float w0 = __fsub_rn(1.0f, w1);
+            int r0 = (int)hf - hlo;
+            r0 = min(max(r0, 0), p.trows - 2);
+            mbar_wait_sleep(smem_u32(&bars[1 + 4 * slot]), (par_t >> s) & 1u, (uint32_t)p.wait_ns);
+            par_t ^= 1u << s;
+            const float4* t0p = reinterpret_cast<const float4*>(sT + r0 * kTPitch);
+            const float4* t1p = reinterpret_cast<const float4*>(sT + (r0 + 1) * kTPitch);
+            const float4* cc = reinterpret_cast<const float4*>(sC);
+            // 16 groups of 4 columns; the three table reads of group g+1 are issued before
+            // group g is evaluated (the compiler will not hoist them over the A-tile stores)
+            float4 ta[2], tb[2], tc[2];
+            ta[0] = t0p[0];
+            tb[0] = t1p[0];
+            tc[0] = cc[0];
+            uint32_t pk[4];
+#pragma unroll
+            for (int g4 = 0; g4 < 16; ++g4) {
+              if (g4 + 1 < 16) {
+                ta[(g4 + 1) & 1] = t0p[g4 + 1];
+                tb[(g4 + 1) & 1] = t1p[g4 + 1];
+                tc[(g4 + 1) & 1] = cc[g4 + 1];
+              }
+              const float4 a = ta[g4 & 1], b = tb[g4 & 1], c = tc[g4 & 1];
+              const float h0 = c.x + w0 * a.x + w1 * b.x;
+              const float h1 = c.y + w0 * a.y + w1 * b.y;
+              const float h2 = c.z + w0 * a.z + w1 * b.z;
+              const float h3 = c.w + w0 * a.w + w1 * b.w;
+              pk[2 * (g4 & 1) + 0] = (kDbg & 128) ? pack_half2(h0, h1) : pack_half2(silu_from_half_arg(h0), silu_from_half_arg(h1));
+              pk[2 * (g4 & 1) + 1] = (kDbg & 128) ? pack_half2(h2, h3) : pack_half2(silu_from_half_arg(h2), silu_from_half_arg(h3));
+              if (g4 & 1) {
+                const int c8 = g4 >> 1;
+                *reinterpret_cast<uint4*>(a_rowp + ((c8 ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[2 + 4 * slot]));  // t_empty: this warp is done reading T and c
+          } else {
+            mbar_wait_sleep(smem_u32(&bars[3 + 4 * slot]), (par_acc >> s) & 1u, (uint32_t)p.wait_ns);
+            par_acc ^= 1u << s;
+            tc_fence_after();
+            if (kDbg & 256) tr1 = clock64();
+            if (l < nh) {
+              // ---- hidden layer l: bias + SiLU, next A tile -------------------------
+              // 4 chunks of 16 accumulator columns; the TMEM load and the bias row of chunk
+              // c+1 are in flight while chunk c goes through bias + SiLU + pack.
+              const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
+              uint32_t r[2][16] = {};
+              float4 bb[2][4];
+              if (!(kDbg & 64)) tmem_ld16(tmem_acc, r[0]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bb[0][i] = bl[i];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < 4) {
+                  if (!(kDbg & 64)) tmem_ld16(tmem_acc + (c + 1) * 16, r[(c + 1) & 1]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = (kDbg & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : bl[(c + 1) * 4 + i];
+                }
+                const uint32_t* rc = r[c & 1];
+                const float4* bc = bb[c & 1];
+                float h[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  h[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + bc[i].x;
+                  h[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + bc[i].y;
+                  h[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + bc[i].z;
+                  h[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + bc[i].w;
+                }
+                float t[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = (kDbg & 1) ? 0.5f * h[i] : tanh_approx(h[i]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h[i] = fmaf(h[i], t[i], h[i]);
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                  const uint32_t q0 = pack_half2(h[8 * hc + 0], h[8 * hc + 1]);
+                  const uint32_t q1 = pack_half2(h[8 * hc + 2], h[8 * hc + 3]);
+                  const uint32_t q2 = pack_half2(h[8 * hc + 4], h[8 * hc + 5]);
+                  const uint32_t q3 = pack_half2(h[8 * hc + 6], h[8 * hc + 7]);
+                  const int chunk = 2 * c + hc;
+                  if (!(kDbg & 2)) *reinterpret_cast<uint4*>(a_rowp + ((chunk ^ (m & 7)) << 4)) = make_uint4(q0, q1, q2, q3);
+                }
+              }
+            } else {
+              // ---- head: density logit -> exp ---------------------------------------
+              uint32_t r[4];
+              tmem_ld4(tmem_acc, r);
+              tmem_ld_wait();
+              const float d = __uint_as_float(r[0]) + sBiasF[0];
+              const int nvalid = s ? g1.nvalid : g0.nvalid;
+              if (m < nvalid) {
+                const long long o = ((s ? g1.line : g0.line) * p.R) + k0 + m;
+                if (p.out_raw) p.out_raw[o] = d;
+                p.out_act[o] = expf(__fadd_rn(d, p.density_bias));
+              }
+            }
+          }
+
+          if (kDbg & 256) tr2 = clock64();
+          if (l < nh) {
+            // publish this thread's row of the next A tile: generic-proxy stores -> async proxy,
+            // TMEM reads ordered before the MMA that will overwrite the accumulator
+            if (!(kDbg & 16)) fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[4 + 4 * slot]));
+          }
+          if ((kDbg & 256) && blockIdx.x == 0 && wg == 0 && lane == 0) {
+            const long long ev = (n * (nh + 1) + l) * 2 + s;
+            if (ev < 512) {
+              long long* o = g_trace + ((long long)q * 512 + ev) * 4;
+              o[0] = tr0;
+              o[1] = tr1;
+              o[2] = tr2;
+              o[3] = clock64();
+            }
+          }
         }
       }
     }
-    // the next tile's T/c build and A writes are ordered after this tile's last
-    // reads by the named barriers above; TMEM reuse is ordered by wait::ld + the
-    // before_thread_sync fence issued ahead of the next MMA.
   }
 
   tc_fence_before();
   __syncthreads();
-  if (tid_cta < 32) tmem_dealloc<kWG * 64>(tmem_base);
+  if (wid == 0) tmem_dealloc<512>(tmem_base);
+}
+
+template <int kWG, int kDbg>
+static int launch_tc(const TcParams& p, int sms, cudaStream_t st) {
+  const int wbytes = tc_weight_bytes(p.n_hidden);
+  const int kSlots = kWG * kSlotsPerWG;
+  const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (size_t)kSlots * p.slot_bytes + 8 * (1 + 4 * kSlots) + 16;
+  if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
+  cudaError_t e = cudaFuncSetAttribute(lattice_tc_kernel<kWG, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return SMB_ERR_CUDA;
+  const long long ntiles = (long long)p.nx * p.R * ((p.R + kTileM - 1) / kTileM);
+  long long grid = (ntiles + kSlots - 1) / kSlots;
+  if (grid > sms) grid = sms;
+  lattice_tc_kernel<kWG, kDbg><<<(unsigned)grid, kWG * 192, smem, st>>>(p);
+  return smb_check(cudaGetLastError());
 }
 
 }  // namespace smb
@@ -297,24 +454,20 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   const int nh = (int)layout->n_hidden;
   if (nh < 2 || nh > kMaxHidden) return SMB_ERR_BAD_ARG;
   // rows of the (.,z) planes one 128-sample segment can touch (+2 for the taps, +1 slack)
+  int rows;
   {
     double span = 127.0 * cfg->Hp / (double)(R - 1);
-    int rows = (int)span + 3;
+    rows = (int)span + 3;
     if (rows > cfg->Hp + 2) rows = cfg->Hp + 2;  // rows -1 .. Hp (the two zero borders)
-    if (rows > kTRows) return SMB_ERR_BAD_ARG;
+    if (rows < 2) rows = 2;
+    if (rows > kTRowsMax) return SMB_ERR_BAD_ARG;
   }
-  constexpr int kWG = 4;
-  const int wbytes = tc_weight_bytes(nh);
-  const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (size_t)kWG * kWgBytes + 8 * (1 + kWG) + 16;
-  if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
   // layout contract: [hidden | head | bias_half | bias_final] contiguous in the blob
   if (layout->off_tc_final != layout->off_tc_hidden + (uint32_t)(nh - 1) * kWBytes ||
       layout->off_bias_half != layout->off_tc_final + kWFinalBytes ||
       layout->off_bias_final != layout->off_bias_half + (uint32_t)nh * kHid * 4)
     return SMB_ERR_BAD_ARG;
 
-  cudaError_t e = cudaFuncSetAttribute(lattice_tc_kernel<kWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return SMB_ERR_CUDA;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -331,12 +484,39 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   p.W = cfg->Wp;
   p.align_corners = cfg->align_corners;
   p.n_hidden = nh;
+  p.trows = rows;
+  p.slot_bytes = tc_slot_bytes(rows);
   p.density_bias = cfg->density_bias;
   p.out_act = out_density_act;
   p.out_raw = out_density;
-  const long long ntiles = (long long)nx * R * ((R + kTileM - 1) / kTileM);
-  long long grid = (ntiles + kWG - 1) / kWG;
-  if (grid > sms) grid = sms;
-  lattice_tc_kernel<kWG><<<(unsigned)grid, kWG * 128, smem, (cudaStream_t)stream>>>(p);
-  return smb_check(cudaGetLastError());
+  {
+    const char* e = getenv("SMB_TC_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+    e = getenv("SMB_TC_WAITNS");
+    p.wait_ns = e ? atoi(e) : 2000;
+  }
+  // as many consumer warpgroups (2 slots each) as shared memory allows
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  switch (p.dbg) {  // developer timing experiments (results are garbage for dbg != 0)
+    case 1: rc = launch_tc<3, 1>(p, sms, st); break;
+    case 4: rc = launch_tc<3, 4>(p, sms, st); break;
+    case 15: rc = launch_tc<3, 15>(p, sms, st); break;
+    case 31: rc = launch_tc<3, 31>(p, sms, st); break;
+    case 47: rc = launch_tc<3, 47>(p, sms, st); break;
+    case 79: rc = launch_tc<3, 79>(p, sms, st); break;
+    case 143: rc = launch_tc<3, 143>(p, sms, st); break;
+    case 256: rc = launch_tc<3, 256>(p, sms, st); break;
+    default:
+      rc = launch_tc<3, 0>(p, sms, st);
+      if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<2, 0>(p, sms, st);
+      if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<1, 0>(p, sms, st);
+  }
+  return rc;
+}
+
+// developer instrumentation: copies the clock64 trace of the last SMB_TC_DEBUG=256 launch
+extern "C" int smb_debug_read_trace(long long* host, int n) {
+  if (!host || n <= 0 || n > 4 * 512 * 4) return SMB_ERR_BAD_ARG;
+  return smb_check(cudaMemcpyFromSymbol(host, smb::g_trace, sizeof(long long) * n));
 }

@@ -34,6 +34,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase
+// completes or the hint expires, instead of re-polling every few tens of cycles and
+// burning issue slots that the compute warps of the same SM sub-partition need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  if (ns == 0) {
+    while (!mbar_try_wait(bar, parity)) {
+      if (++spins > (1u << 24)) __trap();
+    }
+    return;
+  }
+  while (!mbar_try_wait_hint(bar, parity, ns)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
 // Bounded wait: a lost arrival traps (error surfaces on the host) instead of
 // hanging the GPU.  try_wait suspends in hardware, so the bound is seconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
