@@ -15,12 +15,15 @@
 //                  triangle counts (popc / case table), CTA-wide exclusive scan; writes
 //                  a 16-byte record per word + the chunk totals.
 //   K3 mc_totals : one CTA turns chunk totals into chunk bases in canonical order.
-//   K4 mc_emit   : persistent warps skip inactive words 32 at a time (one ballot),
-//                  and for an active word write its owned vertices (each lattice edge
-//                  is owned by exactly one sample -> no duplicates, no atomics) and the
-//                  triangles of its 32 cells; vertex ids of neighbouring words come
-//                  from prefix[word] + popc(mask & lanes_below).  Density is re-read
-//                  only at the two end points of crossing edges.
+//   K4 mc_emit   : a warp takes 32 consecutive words, compacts their crossing samples and
+//                  their active cells across the warp (popc + warp scan), and then works
+//                  one ITEM per lane: a crossing sample writes its <= 3 owned vertices
+//                  (each lattice edge is owned by exactly one sample -> no duplicates, no
+//                  atomics), an active cell writes its <= 5 triangles; vertex ids of
+//                  neighbouring words come from prefix[word] + popc(mask & lanes_below).
+//                  The surface is sparse (a few % of the cells), so lane-per-item keeps the
+//                  SIMT lanes full where lane-per-sample left > 80 % of them idle.  Density
+//                  is re-read only at the two end points of crossing edges.
 //
 // Canonical order (identical to oracle/mc_oracle.c): vertices by x-plane i, inside a
 // plane first the in-plane crossings by (j,k) with the y-edge before the z-edge of a
@@ -60,9 +63,11 @@ __host__ __device__ inline McDims make_dims(int nx, int ny, int nz) {
 }
 
 // per word: chunk-local exclusive prefixes of (in-plane vertices, x-edge vertices,
-// triangles) and an info word (bit 0: the word owns a vertex or has a triangle).
+// triangles), an info word (bit 0: the word owns a vertex or has a triangle), the crossing
+// masks of the edges its samples own and the mask of its cells that produce triangles.
 struct __align__(16) WordRec {
   uint32_t a, b, t, info;
+  uint32_t mx, my, mz, act;
 };
 // per chunk: totals (K2) -> global exclusive bases (K3), same field meaning.
 struct __align__(16) ChunkRec {
@@ -241,17 +246,23 @@ __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos
   const int jw0 = c * kChunkWords + tid * kWordsPerThread;
 
   unsigned long long local[kWordsPerThread + 1];
+  uint32_t kmx[kWordsPerThread], kmy[kWordsPerThread], kmz[kWordsPerThread], kact[kWordsPerThread];
   unsigned long long sum = 0;
 #pragma unroll
   for (int e = 0; e < kWordsPerThread; ++e) {
     const int jw = jw0 + e;
     unsigned long long cnt = 0;
+    kmx[e] = kmy[e] = kmz[e] = kact[e] = 0u;
     if (jw < d.pw) {
       const int j = jw / d.wz, w = jw - j * d.wz;
       const WordMasks k = load_masks(pos, d, i, j, w);
       uint32_t mx, my, mz;
       owned_masks(k, mx, my, mz);
       uint32_t act = active_cells(k);
+      kmx[e] = mx;
+      kmy[e] = my;
+      kmz[e] = mz;
+      kact[e] = act;
       uint32_t nt = 0;
       while (act) {
         const int b = __ffs(act) - 1;
@@ -292,6 +303,10 @@ __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos
       r.b = (uint32_t)((p >> 21) & 0x1fffffu);
       r.t = (uint32_t)(p >> 42);
       r.info = (local[e + 1] != local[e]) ? 1u : 0u;
+      r.mx = kmx[e];
+      r.my = kmy[e];
+      r.mz = kmz[e];
+      r.act = kact[e];
       rec[(long long)i * d.pw + jw] = r;
     }
   }
@@ -401,19 +416,40 @@ __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float 
   return v;
 }
 
-struct NbrWord {  // what a triangle needs to number a vertex owned by a neighbouring word
-  uint32_t mx, my, mz;
-  uint32_t v0, v1;  // global exclusive vertex prefix of the word: in-plane group / x-edge group
-};
-
 constexpr int kEmitWarps = 8;
 
+// lane l holds cnt_l items; returns the exclusive prefix and the warp total
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+  uint32_t inc = v;
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
+    if (lane >= sft) inc += y;
+  }
+  total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// item idx of the batch -> (lane that holds its word, position of its bit in that word's mask)
+__device__ __forceinline__ void locate_item(uint32_t idx, const uint32_t* __restrict__ s_off /*[33]*/, int& src) {
+  int lo = 0;  // largest l with s_off[l] <= idx
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+    if (s_off[lo + step] <= idx) lo += step;
+  src = lo;
+}
+
 __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
-  __shared__ NbrWord nbr[kEmitWarps][8];  // [warp][row(di,dj)*2 + word(0: w, 1: w+1)]
   __shared__ signed char s_tri[256][16];
   __shared__ unsigned char s_ntri[256];
+  __shared__ unsigned short s_emask[256];
+  __shared__ uint32_t s_off[kEmitWarps][33];
+  __shared__ uint32_t s_eid[12][kEmitWarps * 32];  // per-thread column of the 12 edge vertex ids
   for (int t = threadIdx.x; t < 256 * 16; t += blockDim.x) (&s_tri[0][0])[t] = (&SMB_MC_TRI[0][0])[t];
-  for (int t = threadIdx.x; t < 256; t += blockDim.x) s_ntri[t] = SMB_MC_NTRI[t];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+    s_ntri[t] = SMB_MC_NTRI[t];
+    s_emask[t] = SMB_MC_EDGEMASK[t];
+  }
   __syncthreads();
 
   const McDims d = p.d;
@@ -423,59 +459,72 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
   const long long nwarps = (long long)gridDim.x * kEmitWarps;
   const long long nbatch = (d.nwords + 31) / 32;
   const long long sy = d.nz, sx = (long long)d.ny * d.nz;
-  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t* off = s_off[warp];
 
   for (long long batch = gwarp; batch < nbatch; batch += nwarps) {
-    const long long myword = batch * 32 + lane;
+    // ---- phase 0: lane <-> word --------------------------------------------------
+    const long long wd = batch * 32 + lane;
     uint32_t info = 0;
-    if (myword < d.nwords) info = __ldg(&p.rec[myword].info);
-    uint32_t todo = __ballot_sync(0xffffffffu, info & 1u);
-    while (todo) {  // warp-uniform
-      const int wb = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const long long word = batch * 32 + wb;
-      const int i = (int)(word / d.pw);
-      const int jw = (int)(word - (long long)i * d.pw);
-      const int j = jw / d.wz, w = jw - j * d.wz;
-      const int k = w * 32 + lane;
-      const long long pt = (long long)i * sx + (long long)j * sy + k;
+    if (wd < d.nwords) info = __ldg(&p.rec[wd].info);
+    if (__ballot_sync(0xffffffffu, info & 1u) == 0u) continue;  // warp-uniform: nothing in these 32 words
+    uint32_t mx = 0, my = 0, mz = 0, act = 0, v0 = 0, v1 = 0, t0 = 0;
+    int wi = 0, wj = 0, ww = 0;
+    WordMasks km;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) km.m[r] = km.s[r] = 0u;
+    if (info & 1u) {
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd]));
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd]) + 1);
+      mx = hi.x;
+      my = hi.y;
+      mz = hi.z;
+      act = hi.w;
+      wi = (int)(wd / d.pw);
+      const int jw = (int)(wd - (long long)wi * d.pw);
+      wj = jw / d.wz;
+      ww = jw - wj * d.wz;
+      const uint4 cb = __ldg(reinterpret_cast<const uint4*>(&p.cbase[(long long)wi * d.cpp + jw / kChunkWords]));
+      v0 = cb.x + lo.x;
+      v1 = cb.y + lo.y;
+      t0 = cb.z + lo.z;
+      if (act) km = load_masks(p.pos, d, wi, wj, ww);
+    }
 
-      // ---- stage the 4 rows x 2 words this word's cells can reference ----------
+    // ---- phase V: one lane per crossing sample -> its owned vertices -------------
+    {
+      const uint32_t own = mx | my | mz;
+      uint32_t total;
+      const uint32_t ex = warp_excl_scan(__popc(own), lane, total);
       __syncwarp();
-      if (lane < 8) {
-        const int row = lane >> 1, ww = lane & 1;
-        const int di = row >> 1, dj = row & 1;
-        NbrWord nw;
-        nw.mx = nw.my = nw.mz = 0u;
-        nw.v0 = nw.v1 = 0u;
-        if (i + di < d.nx && j + dj < d.ny && w + ww < d.wz) {
-          const WordMasks km2 = load_masks(p.pos, d, i + di, j + dj, w + ww);
-          owned_masks(km2, nw.mx, nw.my, nw.mz);
-          const int jw2 = jw + dj * d.wz + ww;
-          const long long wd = (long long)(i + di) * d.pw + jw2;
-          const WordRec r2 = p.rec[wd];
-          const ChunkRec cb = p.cbase[(long long)(i + di) * d.cpp + jw2 / kChunkWords];
-          nw.v0 = cb.a + r2.a;
-          nw.v1 = cb.b + r2.b;
-        }
-        nbr[warp][lane] = nw;
-      }
-      const WordMasks km = load_masks(p.pos, d, i, j, w);
+      off[lane] = ex;
+      if (lane == 0) off[32] = 0xffffffffu;
       __syncwarp();
-      const NbrWord self = nbr[warp][0];
-
-      // ---- vertices owned by this word's samples --------------------------------
-      if (self.mx | self.my | self.mz) {
-        const bool by = (self.my >> lane) & 1u, bz = (self.mz >> lane) & 1u, bx = (self.mx >> lane) & 1u;
-        if (bx | by | bz) {
+      for (uint32_t base = 0; base < total; base += 32) {  // warp-uniform
+        const uint32_t idx = base + lane;
+        const bool valid = idx < total;
+        int src = 0;
+        if (valid) locate_item(idx, off, src);
+        const uint32_t smx = __shfl_sync(0xffffffffu, mx, src), smy = __shfl_sync(0xffffffffu, my, src);
+        const uint32_t smz = __shfl_sync(0xffffffffu, mz, src);
+        const uint32_t sv0 = __shfl_sync(0xffffffffu, v0, src), sv1 = __shfl_sync(0xffffffffu, v1, src);
+        const int si = __shfl_sync(0xffffffffu, wi, src), sj = __shfl_sync(0xffffffffu, wj, src);
+        const int sw = __shfl_sync(0xffffffffu, ww, src);
+        const uint32_t sex = __shfl_sync(0xffffffffu, ex, src);
+        if (valid) {
+          const uint32_t sown = smx | smy | smz;
+          const int bit = __fns(sown, 0, (int)(idx - sex) + 1);
+          const uint32_t below = (1u << bit) - 1u;
+          const bool by = (smy >> bit) & 1u, bz = (smz >> bit) & 1u, bx = (smx >> bit) & 1u;
+          const int k = sw * 32 + bit;
+          const long long pt = (long long)si * sx + (long long)sj * sy + k;
           const float a = mc_val(p.grid, pt, p.sub, p.sign);
-          const float fi = (float)(p.x_origin + i), fj = (float)j, fk = (float)k;
-          const bool store_inplane = (i < d.nx - 1) || p.emit_last_plane;
-          const long long n_before = __popc(self.my & lt) + __popc(self.mz & lt);
+          const float fi = (float)(p.x_origin + si), fj = (float)sj, fk = (float)k;
+          const bool store_inplane = (si < d.nx - 1) || p.emit_last_plane;
+          const long long n_before = __popc(smy & below) + __popc(smz & below);
           if (by && store_inplane) {
             const float bb = mc_val(p.grid, pt + sy, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = p.verts + 3 * ((long long)self.v0 + n_before);
+            float* o = p.verts + 3 * ((long long)sv0 + n_before);
             o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
             o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
@@ -483,7 +532,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
           if (bz && store_inplane) {
             const float bb = mc_val(p.grid, pt + 1, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = p.verts + 3 * ((long long)self.v0 + n_before + (by ? 1 : 0));
+            float* o = p.verts + 3 * ((long long)sv0 + n_before + (by ? 1 : 0));
             o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
             o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
@@ -491,64 +540,100 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
           if (bx) {
             const float bb = mc_val(p.grid, pt + sx, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = p.verts + 3 * ((long long)self.v1 + __popc(self.mx & lt));
+            float* o = p.verts + 3 * ((long long)sv1 + __popc(smx & below));
             o[0] = mc_xform(__fadd_rn(fi, t), p.flags, p.vdiv, p.vmul, p.vadd);
             o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
           }
         }
       }
+    }
 
-      // ---- triangles of this word's cells -----------------------------------------
-      const uint32_t act = active_cells(km);
-      if (act == 0u) continue;  // warp-uniform
-      uint32_t cs = 0, ntri = 0;
-      if ((act >> lane) & 1u) {
-        cs = cell_case(km, lane);
-        ntri = s_ntri[cs];
-      }
-      uint32_t inc = ntri;
+    // ---- phase T: one lane per active cell -> its triangles ----------------------
+    {
+      uint32_t total;
+      const uint32_t ex = warp_excl_scan(__popc(act), lane, total);
+      if (total == 0u) continue;  // warp-uniform
+      __syncwarp();
+      off[lane] = ex;
+      if (lane == 0) off[32] = 0xffffffffu;
+      __syncwarp();
+      int carry_src = -1;       // word (lane) whose cells straddle the previous 32-item group ...
+      uint32_t carry_sum = 0u;  // ... and the triangles it has emitted so far
+      for (uint32_t base = 0; base < total; base += 32) {  // warp-uniform
+        const uint32_t idx = base + lane;
+        const bool valid = idx < total;
+        int src = 0;
+        if (valid) locate_item(idx, off, src);
+        WordMasks sk;
 #pragma unroll
-      for (int sft = 1; sft < 32; sft <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
-        if (lane >= sft) inc += y;
-      }
-      if (ntri != 0) {
-        const WordRec r0 = p.rec[word];
-        const long long slot =
-            (long long)p.cbase[(long long)i * d.cpp + jw / kChunkWords].t + r0.t + (inc - ntri);
-        for (uint32_t t = 0; t < ntri; ++t) {
-          long long id[3];
+        for (int r = 0; r < 4; ++r) {
+          sk.m[r] = __shfl_sync(0xffffffffu, km.m[r], src);
+          sk.s[r] = __shfl_sync(0xffffffffu, km.s[r], src);
+        }
+        const uint32_t sact = __shfl_sync(0xffffffffu, act, src);
+        const uint32_t st0 = __shfl_sync(0xffffffffu, t0, src);
+        const int si = __shfl_sync(0xffffffffu, wi, src), sj = __shfl_sync(0xffffffffu, wj, src);
+        const int sw = __shfl_sync(0xffffffffu, ww, src);
+        const uint32_t sex = __shfl_sync(0xffffffffu, ex, src);
+        int bit = 0;
+        uint32_t cs = 0, ntri = 0;
+        if (valid) {
+          bit = __fns(sact, 0, (int)(idx - sex) + 1);
+          cs = cell_case(sk, bit);
+          ntri = s_ntri[cs];
+        }
+        // triangles of the lower cells of the same word: segmented inclusive scan over the
+        // lanes (items are sorted by word, then bit) + the carry of a straddling word
+        const int key = valid ? src : -2;
+        uint32_t inc = ntri;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            // edge e = 4*axis + 2*o1 + o2; owner offsets: axis 0 (0,o1,o2), axis 1 (o1,0,o2), axis 2 (o1,o2,0)
-            const int e = s_tri[cs][3 * t + q];
-            const int axis = e >> 2, o1 = (e >> 1) & 1, o2 = e & 1;
-            const int di = axis == 0 ? 0 : o1;
-            const int dj = axis == 0 ? o1 : (axis == 1 ? 0 : o2);
-            const int dk = axis == 2 ? 0 : o2;
-            const int bit = lane + dk;  // 0..32
-            const NbrWord& nw = nbr[warp][(di * 2 + dj) * 2 + (bit >> 5)];
-            const int bb = bit & 31;
-            const uint32_t below = (1u << bb) - 1u;
-            long long v;
-            if (axis == 0) {
-              v = (long long)nw.v1 + __popc(nw.mx & below);
-            } else {
-              v = (long long)nw.v0 + __popc(nw.my & below) + __popc(nw.mz & below);
-              if (axis == 2) v += (nw.my >> bb) & 1u;
+        for (int sft = 1; sft < 32; sft <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
+          const int ky = __shfl_up_sync(0xffffffffu, key, sft);
+          if (lane >= sft && ky == key) inc += y;
+        }
+        if (key == carry_src) inc += carry_sum;
+        carry_src = __shfl_sync(0xffffffffu, key, 31);
+        carry_sum = __shfl_sync(0xffffffffu, inc, 31);
+        if (ntri != 0u) {
+          // ids of the vertices on this cell's crossing edges, grouped by the sample that
+          // owns them: owner (di,dj,dk) holds x-edge 2dj+dk (di=0), y-edge 4+2di+dk (dj=0),
+          // z-edge 8+2di+dj (dk=0)
+          const uint32_t emask = s_emask[cs];
+          const int jw = sj * d.wz + sw;
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int di = o >> 2, dj = (o >> 1) & 1, dk = o & 1;
+            uint32_t ebits = 0;
+            if (di == 0) ebits |= 1u << (2 * dj + dk);
+            if (dj == 0) ebits |= 1u << (4 + 2 * di + dk);
+            if (dk == 0) ebits |= 1u << (8 + 2 * di + dj);
+            if (emask & ebits) {
+              const int b2 = bit + dk;
+              const int wo = b2 >> 5, bb = b2 & 31;
+              const int jw2 = jw + dj * d.wz + wo;
+              const long long w2 = (long long)(si + di) * d.pw + jw2;
+              const uint4 lo = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]));
+              const uint4 hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
+              const uint4 cb = __ldg(reinterpret_cast<const uint4*>(&p.cbase[(long long)(si + di) * d.cpp + jw2 / kChunkWords]));
+              const uint32_t below = (1u << bb) - 1u;
+              const uint32_t idyz = cb.x + lo.x + __popc(hi.y & below) + __popc(hi.z & below);
+              if (di == 0) s_eid[2 * dj + dk][threadIdx.x] = cb.y + lo.y + __popc(hi.x & below);
+              if (dj == 0) s_eid[4 + 2 * di + dk][threadIdx.x] = idyz;
+              if (dk == 0) s_eid[8 + 2 * di + dj][threadIdx.x] = idyz + ((hi.y >> bb) & 1u);
             }
-            id[q] = v + p.id_offset;
           }
-          long long* o = p.faces + 3 * (slot + t);
-          if (p.flags & SMB_MC_FLIP) {
-            o[0] = id[1];
-            o[1] = id[0];
-          } else {
-            o[0] = id[0];
-            o[1] = id[1];
+          long long* o = p.faces + 3 * ((long long)st0 + (inc - ntri));
+          for (uint32_t t = 0; t < ntri; ++t) {
+            const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + p.id_offset;
+            const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + p.id_offset;
+            const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + p.id_offset;
+            const bool flip = p.flags & SMB_MC_FLIP;
+            o[3 * t + 0] = flip ? i1 : i0;
+            o[3 * t + 1] = flip ? i0 : i1;
+            o[3 * t + 2] = i2;
           }
-          o[2] = id[2];
         }
       }
     }

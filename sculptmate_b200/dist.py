@@ -93,19 +93,23 @@ def gather_slab_meshes(
     Returns (verts, faces, counts) with the merged mesh on ``dst`` (None elsewhere);
     ``counts`` is [(V_g, F_g)] for every rank.
     """
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    solo = not (dist.is_available() and dist.is_initialized())  # single process: one slab, no collective
+    world = 1 if solo else dist.get_world_size(group)
+    rank = 0 if solo else dist.get_rank(group)
     dev = backend.device
     parts = slab_partition(resolution, world)
     a, b = parts[rank]
     last = rank == world - 1
     V, F = backend.count(a, b - a + 1, last)
 
-    mine = torch.tensor([V, F], dtype=torch.int64, device=dev)
-    allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(allc, mine, group=group)
-    allc = allc.cpu().view(world, 2)
-    counts = [(int(v), int(f)) for v, f in allc.tolist()]
+    if solo:
+        counts = [(int(V), int(F))]
+    else:
+        mine = torch.tensor([V, F], dtype=torch.int64, device=dev)
+        allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        allc = allc.cpu().view(world, 2)
+        counts = [(int(v), int(f)) for v, f in allc.tolist()]
     v_off = [0]
     f_off = [0]
     for v, f in counts:
@@ -169,7 +173,7 @@ def extract_mesh_sharded(
 ):
     """TSR.extract_mesh for one scene code with the lattice sharded over the group.
     Returns (v_pos, t_pos_idx) on ``dst`` (device tensors), (None, None) elsewhere."""
-    if broadcast:
+    if broadcast and dist.is_available() and dist.is_initialized():
         broadcast_scene(scene_code, None, src=dst, group=group)
     backend = CudaSlabBackend(tsr, scene_code, resolution, threshold, precision)
     verts, faces, _ = gather_slab_meshes(backend, resolution, group=group, dst=dst)
