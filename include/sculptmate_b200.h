@@ -177,6 +177,51 @@ int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int res
                           const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                           int64_t* ntris);
 
+/* ------------------------------------------------------------ SF3D variant
+ * Stable Fast 3D ("Pro"): StableFast/sf3d/system.py:141-198, sf3d/models/network.py:148-208,
+ * sf3d/models/isosurface.py:24-229.  Planes are (3,40,Hp,Wp) (Hp=Wp=384 in the shipped config);
+ * make the channels-last copy with smb_scene_prepare(triplane, Hp, Wp, NULL, NULL, planes_cl, NULL, s).
+ *
+ * heads_blob (device, fp32, smb_sf3d_heads_floats() floats): for head in (density, vertex_offset):
+ *   W0 (64,120) b0 (64) W1 (64,64) b1 (64) W2 (out,64) b2 (out), out = 1 then 3, each head
+ *   zero-padded to a multiple of 4 floats (11972 + 12100 floats)
+ *   = MaterialMLP state-dict heads.<name>.{0,2,4}.{weight,bias} (network.py:158-178).
+ *
+ * smb_sf3d_query_f32: SF3D.query_triplane (align_corners=True; positions (n,3) in (-radius,radius))
+ * fused with the two heads; pass features_in (n,120) INSTEAD of positions to run the heads on
+ * pre-computed features (MaterialMLP.forward).  Outputs, each optional:
+ *   features_out (n,120); density_raw (n) = head + out_bias; density_act (n) = exp(density_raw)
+ *   (trunc_exp forward, network.py:85); vertex_offset (n,3).
+ */
+int smb_sf3d_heads_floats(void);
+int smb_sf3d_query_f32(const float* planes_cl, int Hp, int Wp, const float* heads_blob, float radius,
+                       float density_out_bias, const float* positions, const float* features_in, int64_t n,
+                       float* features_out, float* density_raw, float* density_act, float* vertex_offset,
+                       void* stream);
+
+/* Marching tetrahedra = MarchingTetrahedraHelper._forward (isosurface.py:144-203) on a STATIC tet grid:
+ *   edges     (E,2) int32: the grid's unique edges, each (a<b), sorted lexicographically
+ *             (= MarchingTetrahedraHelper.all_edges, isosurface.py:119-133);
+ *   tets      (T,4) int32 (npz "indices");  tet_edges (T,6) int32: index into `edges` of each tet's
+ *             edges in base_tet_edges order (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) (isosurface.py:67).
+ * Vertex k is the k-th crossing edge of `edges` -- the numbering torch.unique(dim=0) gives the
+ * reference -- and faces list all 1-triangle tets, then all 2-triangle tets (isosurface.py:187-201).
+ * Two calls: count (sizes the outputs), then emit.  smb_mtet_deform: grid + scale*tanh(offset)
+ * (normalize_grid_deformation, isosurface.py:106-113). */
+typedef struct smb_mtet_counts {
+  int64_t nverts;
+  int64_t ntris;
+  int64_t ntris1; /* triangles from 1-triangle tets (they come first) */
+  int64_t reserved;
+} smb_mtet_counts;
+size_t smb_mtet_workspace_bytes(int64_t n_edges, int64_t n_tets);
+int smb_mtet_count(const float* sdf, const int32_t* edges, int64_t n_edges, const int32_t* tets, int64_t n_tets,
+                   void* workspace, size_t workspace_bytes, smb_mtet_counts* counts_dev, void* stream);
+int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges,
+                  const int32_t* tet_edges, int64_t n_tets, const void* workspace, float* verts, int64_t* faces,
+                  void* stream);
+int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t n_vertices, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

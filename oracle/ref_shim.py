@@ -171,6 +171,39 @@ def load_sf3d():
     return types.SimpleNamespace(isosurface=iso, network=net)
 
 
+def load_sf3d_system():
+    """The reference's own ``sf3d.system`` module (for SF3D.query_triplane and
+    SF3D.triplane_to_meshes, system.py:141-198).  Its image->triplane imports need
+    third-party versions that are not installed here (transformers API drift, open_clip),
+    so those OUT-OF-SCOPE sub-modules are pre-seeded with empty stand-ins exposing only the
+    names system.py imports; the two methods that run are the reference's, unmodified."""
+    ref = load_sf3d()
+    names = {
+        "sf3d.models.tokenizers.image": ["DINOV2SingleImageTokenizer"],
+        "sf3d.models.tokenizers.triplane": ["TriplaneLearnablePositionalEmbedding"],
+        "sf3d.models.transformers.backbone": ["TwoStreamInterleaveTransformer"],
+        "sf3d.models.global_estimator.multi_head_estimator": ["MultiHeadEstimator"],
+        "sf3d.models.image_estimator.clip_based_estimator": ["ClipBasedHeadEstimator"],
+        "sf3d.models.camera": ["LinearCameraEmbedder"],
+        "sf3d.texture_baker.baker": ["TextureBaker"],
+    }
+    for mod, attrs in names.items():
+        if mod not in sys.modules:
+            parent = mod.rsplit(".", 1)[0]
+            if parent not in sys.modules:
+                pm = types.ModuleType(parent)
+                pm.__path__ = []
+                sys.modules[parent] = pm
+            m = types.ModuleType(mod)
+            for a in attrs:
+                setattr(m, a, type(a, (), {}))
+            sys.modules[mod] = m
+    import sf3d.system as system
+
+    ref.system = system
+    return ref
+
+
 TRIPOSR_DECODER_CFG = dict(in_channels=120, n_neurons=64, n_hidden_layers=9, activation="silu")
 TRIPOSR_RENDERER_CFG = dict(
     radius=0.87,

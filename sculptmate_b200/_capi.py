@@ -88,6 +88,15 @@ SIGNATURES = {
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],
     ),
+    "smb_sf3d_heads_floats": (c_int, []),
+    "smb_sf3d_query_f32": (
+        c_int,
+        [c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "smb_mtet_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "smb_mtet_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "smb_mtet_emit": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "smb_mtet_deform": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

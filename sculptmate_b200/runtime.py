@@ -338,3 +338,130 @@ def raise_for_empty_surface(grid: torch.Tensor, sub: float, sign: float) -> None
     if lo > 0.0 or hi < 0.0:
         raise ValueError("Surface level must be within volume data range.")
     raise RuntimeError("No surface found at the given iso value.")
+
+
+# ------------------------------------------------------------------- SF3D
+def prepare_planes_cl(triplane: torch.Tensor) -> ScenePlanes:
+    """Channels-last copy of a (3,40,Hp,Wp) triplane (no decoder needed)."""
+    _require_cuda(triplane, "triplane")
+    if triplane.dim() != 4 or triplane.shape[0] != 3 or triplane.shape[1] != PLANE_CHANNELS:
+        raise NotImplementedError(f"triplane must be (3,{PLANE_CHANNELS},Hp,Wp); got {tuple(triplane.shape)}")
+    tp = triplane.detach().to(torch.float32).contiguous()
+    _, _, Hp, Wp = tp.shape
+    cl = torch.empty((3, Hp, Wp, PLANE_CHANNELS), dtype=torch.float32, device=tp.device)
+    with torch.cuda.device(tp.device):
+        check(_capi.load().smb_scene_prepare(tp.data_ptr(), Hp, Wp, None, None, cl.data_ptr(), None, _stream_ptr(tp.device)), "smb_scene_prepare")
+    return ScenePlanes(cl, None, Hp, Wp)
+
+
+_sf3d_heads_cache: Dict[int, Tuple[Tuple, torch.Tensor]] = {}
+
+
+def get_sf3d_heads(decoder: torch.nn.Module, device: torch.device) -> torch.Tensor:
+    """MaterialMLP heads ``density`` and ``vertex_offset`` (network.py:158-178) packed into the
+    fp32 device blob of include/sculptmate_b200.h; rebuilt when a parameter changes."""
+    params = []
+    for name in ("density", "vertex_offset"):
+        seq = decoder.heads[name]
+        lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        if len(lin) != 3:
+            raise NotImplementedError(f"head {name!r}: the CUDA path expects 2 hidden layers (config.yaml:50-65)")
+        for m in lin:
+            params += [m.weight, m.bias]
+    key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (str(device),)
+    hit = _sf3d_heads_cache.get(id(decoder))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    total = _capi.load().smb_sf3d_heads_floats()
+    blob = torch.zeros(total, dtype=torch.float32)
+    off = 0
+    for h in range(2):
+        start = off
+        for p_ in params[6 * h : 6 * h + 6]:
+            flat = p_.detach().to(device="cpu", dtype=torch.float32).reshape(-1)
+            blob[off : off + flat.numel()] = flat
+            off += flat.numel()
+        off = start + (off - start + 3) // 4 * 4  # each head is padded to a multiple of 4 floats
+    assert off == total, (off, total)
+    blob = blob.to(device)
+    _sf3d_heads_cache[id(decoder)] = (key, blob)
+    return blob
+
+
+def sf3d_query(
+    planes: Optional[ScenePlanes],
+    heads_blob: Optional[torch.Tensor],
+    density_out_bias: float,
+    radius: float,
+    positions: Optional[torch.Tensor] = None,
+    features: Optional[torch.Tensor] = None,
+    want: Sequence[str] = ("density_act", "vertex_offset"),
+) -> Dict[str, torch.Tensor]:
+    """SF3D.query_triplane (+ the two MaterialMLP heads) for (n,3) positions, or the heads alone
+    on (n,120) features.  ``want`` from {features, density_raw, density_act, vertex_offset}."""
+    src = positions if positions is not None else features
+    _require_cuda(src, "positions" if positions is not None else "features")
+    src = src.detach().to(torch.float32).contiguous()
+    n = src.shape[0]
+    dev = src.device
+    widths = {"features": 3 * PLANE_CHANNELS, "density_raw": 1, "density_act": 1, "vertex_offset": 3}
+    outs = {k: torch.empty((n, widths[k]), dtype=torch.float32, device=dev) for k in want}
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_sf3d_query_f32(
+                _ptr(planes.planes_cl) if planes is not None else None, planes.Hp if planes is not None else 0,
+                planes.Wp if planes is not None else 0, _ptr(heads_blob), float(radius), float(density_out_bias),
+                src.data_ptr() if positions is not None else None, src.data_ptr() if positions is None else None, n,
+                _ptr(outs.get("features")), _ptr(outs.get("density_raw")), _ptr(outs.get("density_act")),
+                _ptr(outs.get("vertex_offset")), _stream_ptr(dev),
+            ),
+            "smb_sf3d_query_f32",
+        )
+    return outs
+
+
+def mtet_deform(base: torch.Tensor, deform: torch.Tensor, scale: float) -> torch.Tensor:
+    _require_cuda(deform, "deformation")
+    base = base.to(deform.device, torch.float32).contiguous()
+    deform = deform.contiguous()
+    out = torch.empty_like(base)
+    with torch.cuda.device(base.device):
+        check(_capi.load().smb_mtet_deform(base.data_ptr(), deform.data_ptr(), float(scale), base.shape[0], out.data_ptr(), _stream_ptr(base.device)), "smb_mtet_deform")
+    return out
+
+
+_mtet_ws: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+
+
+def marching_tets(
+    positions: torch.Tensor, sdf: torch.Tensor, edges: torch.Tensor, tets: torch.Tensor, tet_edges: torch.Tensor
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """MarchingTetrahedraHelper._forward on static int32 topology -> (verts (V,3) f32, faces (F,3) i64)."""
+    _require_cuda(sdf, "level")
+    dev = sdf.device
+    ne, nt = int(edges.shape[0]), int(tets.shape[0])
+    lib = _capi.load()
+    key = (str(dev), ne, nt)
+    if key not in _mtet_ws:
+        if len(_mtet_ws) > 2:
+            _mtet_ws.clear()
+        _mtet_ws[key] = (
+            torch.empty(lib.smb_mtet_workspace_bytes(ne, nt), dtype=torch.uint8, device=dev),
+            torch.zeros(4, dtype=torch.int64, device=dev), torch.zeros(4, dtype=torch.int64).pin_memory(),
+        )
+    ws, counts_dev, counts_pin = _mtet_ws[key]
+    positions = positions.contiguous()
+    with torch.cuda.device(dev):
+        check(lib.smb_mtet_count(sdf.data_ptr(), edges.data_ptr(), ne, tets.data_ptr(), nt, ws.data_ptr(), ws.numel(), counts_dev.data_ptr(), _stream_ptr(dev)), "smb_mtet_count")
+        counts_pin.copy_(counts_dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        V, F = int(counts_pin[0]), int(counts_pin[1])
+        verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((F, 3), dtype=torch.int64, device=dev)
+        if V or F:
+            check(
+                lib.smb_mtet_emit(positions.data_ptr(), sdf.data_ptr(), edges.data_ptr(), ne, tet_edges.data_ptr(), nt, ws.data_ptr(),
+                                  verts.data_ptr(), faces.data_ptr(), _stream_ptr(dev)),
+                "smb_mtet_emit",
+            )
+    return verts, faces

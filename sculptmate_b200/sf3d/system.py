@@ -1,0 +1,94 @@
+"""Drop-in for the mesh-extraction half of /root/reference/StableFast/sf3d/system.py:
+
+  query_triplane(positions, triplanes) -> (B,N,3*Cp)             system.py:170-198
+  triplane_to_meshes(triplanes) -> list[Mesh]                    system.py:141-168
+
+``SF3D`` here carries only ``decoder`` (MaterialMLP), ``isosurface_helper`` and ``bbox``;
+the image -> triplane half, texture baking and material estimation stay in the reference
+(INTEGRATION.md shows how the reference's SF3D binds these two methods).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from .. import runtime
+from ..tsr.utils import BaseModule, scale_tensor
+from .models.isosurface import MarchingTetrahedraHelper
+from .models.mesh import Mesh
+from .models.network import MaterialMLP
+
+# StableFast/checkpoints/config.yaml:45-65 (the two heads of the mesh path)
+DEFAULT_DECODER_CFG = dict(
+    in_channels=120, n_neurons=64, activation="silu",
+    heads=[
+        dict(name="density", out_channels=1, out_bias=-1.0, n_hidden_layers=2, output_activation="trunc_exp"),
+        dict(name="vertex_offset", out_channels=3, n_hidden_layers=2),
+    ],
+)
+
+
+class SF3D(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        isosurface_resolution: int = 160
+        isosurface_threshold: float = 10.0
+        radius: float = 0.87
+        tets_path: str = ""
+        decoder: dict = field(default_factory=lambda: dict(DEFAULT_DECODER_CFG))
+
+    cfg: Config
+
+    def configure(self) -> None:
+        self.decoder = MaterialMLP(self.cfg.decoder)
+        r = self.cfg.radius
+        self.register_buffer("bbox", torch.as_tensor([[-r, -r, -r], [r, r, r]], dtype=torch.float32))
+        self.isosurface_helper = MarchingTetrahedraHelper(self.cfg.isosurface_resolution, self.cfg.tets_path)
+        self._grid_positions = None
+
+    # ------------------------------------------------------------------ API
+    def query_triplane(self, positions: torch.Tensor, triplanes: torch.Tensor) -> torch.Tensor:
+        batched = positions.ndim == 3
+        if not batched:
+            triplanes = triplanes[None, ...]
+            positions = positions[None, ...]
+        assert triplanes.ndim == 5 and positions.ndim == 3
+        outs = []
+        for b in range(triplanes.shape[0]):
+            planes = runtime.prepare_planes_cl(triplanes[b])
+            res = runtime.sf3d_query(planes, None, 0.0, self.cfg.radius, positions=positions[b], want=("features",))
+            outs.append(res["features"])
+        return torch.stack(outs, dim=0)  # the reference keeps the batch dim it adds (system.py:175-179,196)
+
+    def _positions(self, device: torch.device) -> torch.Tensor:
+        if self._grid_positions is None or self._grid_positions.device != device:
+            h = self.isosurface_helper
+            self._grid_positions = scale_tensor(h.grid_vertices.to(device), h.points_range, self.bbox.to(device)).contiguous()
+        return self._grid_positions
+
+    def triplane_to_meshes(self, triplanes: torch.Tensor) -> List[Mesh]:
+        meshes = []
+        h = self.isosurface_helper
+        for i in range(triplanes.shape[0]):
+            triplane = triplanes[i]
+            dev = triplane.device
+            grid_vertices = self._positions(dev)  # scale_tensor(grid, points_range, bbox)   :147-151
+            if self.decoder.cuda_heads_supported():
+                planes = runtime.prepare_planes_cl(triplane)
+                dens_spec = self.decoder.head_spec("density")
+                dec = runtime.sf3d_query(  # query_triplane + decoder(include=[vertex_offset, density]) fused  :153-154
+                    planes, runtime.get_sf3d_heads(self.decoder, dev), float(dens_spec.out_bias), self.cfg.radius,
+                    positions=grid_vertices, want=("density_act", "vertex_offset"),
+                )
+                density, deform = dec["density_act"], dec["vertex_offset"]
+            else:
+                values = self.query_triplane(grid_vertices, triplane)
+                decoded = self.decoder(values, include=["vertex_offset", "density"])
+                density, deform = decoded["density"], decoded["vertex_offset"].squeeze(0)
+            sdf = density - self.cfg.isosurface_threshold  # :155
+            mesh = h(sdf.view(-1, 1), deform.view(-1, 3) if deform is not None else None)
+            mesh.v_pos = scale_tensor(mesh.v_pos, h.points_range, self.bbox.to(dev))  # :162-164
+            meshes.append(mesh)
+        return meshes

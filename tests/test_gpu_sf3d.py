@@ -1,0 +1,116 @@
+"""GPU parity of the Stable Fast 3D mesh path (csrc/sf3d.cu through the C ABI) against the
+fixtures produced by the unmodified reference and against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sf3d_oracle as so
+from sculptmate_b200.sf3d.tets import kuhn_tet_grid, save_tet_grid
+
+pytestmark = pytest.mark.gpu
+RADIUS = 0.87
+
+
+def _sd(g):
+    return {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+
+
+@pytest.fixture(scope="module")
+def tets_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("tets")
+    for n in (10, 12, 40):
+        save_tet_grid(os.path.join(d, f"tets{n}.npz"), n)
+    return str(d)
+
+
+def _model(g, tets_dir, n, thr):
+    from sculptmate_b200.sf3d import SF3D
+
+    m = SF3D(dict(isosurface_resolution=n, isosurface_threshold=thr, radius=RADIUS, tets_path=os.path.join(tets_dir, f"tets{n}.npz")))
+    m.decoder.load_state_dict(_sd(g))
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", ["sphere", "torus", "noise"])
+def test_marching_tets_bit_exact_vs_reference(golden, tets_dir, name):
+    from sculptmate_b200.sf3d import MarchingTetrahedraHelper
+
+    g = golden("sf3d_mtet.npz")
+    n = int(g["n"])
+    h = MarchingTetrahedraHelper(n, os.path.join(tets_dir, f"tets{n}.npz")).cuda()
+    np.testing.assert_array_equal(h.all_edges.cpu().numpy(), g["all_edges"])
+    level = torch.from_numpy(g[f"{name}_sdf"]).cuda().view(-1, 1)
+    deform = torch.from_numpy(g[f"{name}_deform"]).cuda() if f"{name}_deform" in g.files else None
+    mesh = h(level, deform)
+    assert mesh.v_pos.dtype == torch.float32 and mesh.t_pos_idx.dtype == torch.int64 and mesh.v_pos.is_cuda
+    np.testing.assert_array_equal(mesh.t_pos_idx.cpu().numpy(), g[f"{name}_f"])
+    if deform is None:
+        np.testing.assert_array_equal(mesh.v_pos.cpu().numpy(), g[f"{name}_v"])  # same fp32 operation order
+    else:  # tanhf (CUDA) vs the reference's CPU tanh: <= 1 ulp on the deformed grid
+        assert np.abs(mesh.extras["grid_vertices"].cpu().numpy() - g[f"{name}_grid"]).max() < 2e-7
+        assert np.abs(mesh.v_pos.cpu().numpy() - g[f"{name}_v"]).max() < 1e-5
+    assert set(mesh.extras) == {"grid_vertices", "tet_edges", "grid_level", "grid_deformation"}
+
+
+def test_query_triplane_and_heads_vs_reference(golden, tets_dir):
+    g = golden("sf3d_path.npz")
+    m = _model(g, tets_dir, int(g["n"]), float(g["threshold"]))
+    pos = torch.from_numpy(g["positions"]).cuda()
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    feats = m.query_triplane(pos, tp)
+    assert feats.shape == (1, pos.shape[0], 120)  # the reference keeps the batch dim it adds
+    assert np.abs(feats.cpu().numpy() - g["features"]).max() < 2e-6
+    fb = m.query_triplane(pos[None].repeat(2, 1, 1), tp[None].repeat(2, 1, 1, 1, 1))
+    assert fb.shape == (2, pos.shape[0], 120) and torch.equal(fb[0], feats[0]) and torch.equal(fb[1], feats[0])
+    dec = m.decoder(feats, include=["vertex_offset", "density"])
+    assert dec["density"].shape == (1, pos.shape[0], 1) and dec["vertex_offset"].shape == (1, pos.shape[0], 3)
+    assert np.abs(dec["density"].cpu().numpy() / g["density"] - 1).max() < 2e-5
+    assert np.abs(dec["vertex_offset"].cpu().numpy() - g["vertex_offset"]).max() < 2e-5
+    only = m.decoder(feats, exclude=["vertex_offset"])
+    assert list(only) == ["density"] and torch.equal(only["density"], dec["density"])
+
+
+def test_triplane_to_meshes_vs_reference(golden, tets_dir):
+    g = golden("sf3d_path.npz")
+    n = int(g["n"])
+    m = _model(g, tets_dir, n, float(g["threshold"]))
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    meshes = m.triplane_to_meshes(tp[None].repeat(2, 1, 1, 1, 1))
+    assert len(meshes) == 2
+    mesh = meshes[0]
+    level = mesh.extras["grid_level"].cpu().numpy().reshape(-1)
+    flips = (np.sign(level) != np.sign(g["grid_level"].reshape(-1))).mean()
+    assert flips < 1e-3
+    assert np.abs(mesh.extras["grid_vertices"].cpu().numpy() - g["grid_vertices"]).max() < 1e-6
+    if flips == 0:
+        np.testing.assert_array_equal(mesh.t_pos_idx.cpu().numpy(), g["t_pos_idx"])
+        assert np.abs(mesh.v_pos.cpu().numpy() - g["v_pos"]).max() < 5e-4
+    assert torch.equal(meshes[1].t_pos_idx, mesh.t_pos_idx) and torch.equal(meshes[1].v_pos, mesh.v_pos)
+    # and bit-exact against the oracle fed the GPU's own level / deformed grid
+    _, tets = kuhn_tet_grid(n)
+    v, f = so.marching_tets(mesh.extras["grid_vertices"].cpu().numpy(), level, tets)
+    np.testing.assert_array_equal(mesh.t_pos_idx.cpu().numpy(), f)
+    v = (v * np.float32(2 * RADIUS) + np.float32(-RADIUS)).astype(np.float32)
+    np.testing.assert_array_equal(mesh.v_pos.cpu().numpy(), v)
+
+
+def test_larger_grid_properties(tets_dir):
+    """n = 40 (68 921 vertices, 384 000 tets): closed surface, Euler characteristic 2."""
+    from conftest import mesh_topology
+    from sculptmate_b200.sf3d import MarchingTetrahedraHelper
+
+    n = 40
+    h = MarchingTetrahedraHelper(n, os.path.join(tets_dir, f"tets{n}.npz")).cuda()
+    gv = h.grid_vertices
+    sdf = (0.33 - (gv - 0.5).norm(dim=-1)).view(-1, 1)
+    mesh = h(sdf, None)
+    v, f = mesh.v_pos.cpu().numpy(), mesh.t_pos_idx.cpu().numpy()
+    closed, chi, vol = mesh_topology(v, f)
+    assert closed and chi == 2 and abs(abs(vol) - 4 / 3 * np.pi * 0.33**3) < 2e-3
+    again = h(sdf, None)
+    assert torch.equal(again.v_pos, mesh.v_pos) and torch.equal(again.t_pos_idx, mesh.t_pos_idx)  # deterministic
+    # empty surface: no vertices, no faces, no exception (the reference returns empty tensors)
+    none = h(torch.ones_like(sdf), None)
+    assert none.v_pos.shape == (0, 3) and none.t_pos_idx.shape == (0, 3)
