@@ -177,8 +177,82 @@ def workload_config(args, world: int):
         return {"workload": f"TripoSR extract_mesh {args.resolution}^3, one lattice x-slab sharded over {world} GPU(s), synthetic 3x40x64x64 baked triplane, random-init NeRFMLP, threshold=median",
                 "resolution": args.resolution, "parallelism": f"xslab{world}", "l2": "inputs rotated + 256 MiB L2 flush between steps"}
     return {"workload": f"TripoSR extract_mesh {args.resolution}^3 per GPU (BASELINE configs[1]), synthetic 3x40x64x64 baked triplane, random-init NeRFMLP, threshold=median",
-            "resolution": args.resolution, "scene_codes_per_gpu_per_step": 1, "parallelism": f"dp{world}",
+            "resolution": args.resolution, "scene_codes_per_gpu_per_step": args.batch, "parallelism": f"dp{world}",
             "l2": "inputs rotated + 256 MiB L2 flush between steps"}
+
+
+# ------------------------------------------------------------------ SF3D (configs[4])
+def run_sf3d(args) -> int:
+    """One step = SF3D.triplane_to_meshes on one synthetic 3x40x384x384 triplane per GPU (independent
+    objects: weak scaling).  Tet grid: Kuhn grid of tet_n^3 cubes (the reference's blob is missing)."""
+    import tempfile
+
+    import torch.distributed as dist
+
+    from sculptmate_b200 import _capi, runtime
+    from sculptmate_b200.sf3d import SF3D, save_tet_grid
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _capi.check(_capi.load().smb_device_check(), "smb_device_check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.tet_n
+    path = save_tet_grid(os.path.join(tempfile.mkdtemp(), f"tets{n}.npz"), n)
+    torch.manual_seed(0)
+    m = SF3D(dict(isosurface_resolution=n, radius=RADIUS, tets_path=path)).to(dev)
+    scenes = [baked_triplane(200 + rank * 2 + s, 384, 384).to(dev) for s in range(2)]
+    h = m.isosurface_helper
+    h.topology(dev)  # static index arrays, built once (the reference caches all_edges the same way)
+    pos = m._positions(dev)
+    heads = runtime.get_sf3d_heads(m.decoder, dev)
+    thr = []
+    for tp in scenes:
+        d = runtime.sf3d_query(runtime.prepare_planes_cl(tp), heads, -1.0, RADIUS, positions=pos, want=("density_act",))["density_act"]
+        thr.append(float(d.median()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(i):
+        m.cfg.isosurface_threshold = thr[i % 2]
+        return m.triplane_to_meshes(scenes[i % 2][None])[0]
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    rec = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        a, b = ev(), ev()
+        a.record()
+        mesh = step(i)
+        b.record()
+        rec.append((a, b))
+    torch.cuda.synchronize()
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in rec)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        nv = int(h.grid_vertices.shape[0])
+        ms = float(total_ms.item()) / args.steps
+        print(json.dumps({
+            "metric": "sf3d_triplane_to_meshes_grid_vertices_per_s", "value": nv * world / (ms * 1e-3), "unit": "pts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"SF3D triplane_to_meshes (BASELINE configs[4]): 3x40x384x384 triplane, MaterialMLP density+vertex_offset heads, "
+                                   f"marching tets on a Kuhn grid n={n} (Nv={nv}, Nt={int(h.indices.shape[0])}); reference blob 160_tets.npz missing",
+                       "parallelism": f"dp{world}", "l2": "inputs rotated + 256 MiB L2 flush between steps"},
+            "mesh": {"verts": int(mesh.v_pos.shape[0]), "tris": int(mesh.t_pos_idx.shape[0])},
+            "gpu_launches": 8 * args.steps * world,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -189,10 +263,14 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--resolution", type=int, default=None)
-    ap.add_argument("--mode", default="dp", choices=["dp", "sharded"])
+    ap.add_argument("--mode", default="dp", choices=["dp", "sharded", "sf3d"])
+    ap.add_argument("--batch", type=int, default=1, help="scene codes per GPU per step in dp mode (configs[3]: 8 per GPU on 8 GPUs)")
+    ap.add_argument("--tet-n", type=int, default=160, help="sf3d mode: Kuhn tet grid of n^3 cubes (the reference's 160_tets.npz blob is missing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
+    if args.mode == "sf3d" and args.impl == "ours":
+        return run_sf3d(args)
     if args.resolution is None:
         args.resolution = 512 if args.mode == "sharded" else 256
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -225,6 +303,7 @@ def main() -> int:
     if args.mode == "sharded":
         seeds = [100 + s for s in range(n_rot)]  # same scene on every rank
     else:
+        n_rot = max(n_rot, args.batch)
         seeds = [100 + rank * n_rot + s for s in range(n_rot)]
     scenes = [baked_triplane(s).to(dev) for s in seeds]
     thresholds = []
@@ -250,12 +329,15 @@ def main() -> int:
             return v, f
         e0, k0, k1, e1 = ev(), ev(), ev(), ev()
         e0.record()
-        scene = runtime.prepare_scene(tp, pack, want_cl=False, want_q=True)
-        k0.record()
-        dens = runtime.query_lattice(scene, pack, axis, R, RADIUS, -1.0)
-        k1.record()
-        pend = runtime.mc_count(dens, sub=thr, sign=1.0)
-        v, f = runtime.mc_emit(pend, flags=7, vdiv=float(R - 1.0), vmul=float(RADIUS - (-RADIUS)), vadd=float(-RADIUS))
+        for b in range(args.batch):  # serial over the batch like the reference (system.py:173)
+            tp, thr = scenes[(i + b) % n_rot], thresholds[(i + b) % n_rot]
+            scene = runtime.prepare_scene(tp, pack, want_cl=False, want_q=True)
+            if b == 0:
+                k0.record()
+            dens = runtime.query_lattice(scene, pack, axis, R, RADIUS, -1.0)
+            if b == 0:
+                k1.record()
+            v, f, _ = runtime.mc_extract(dens, sub=thr, sign=1.0, flags=7, vdiv=float(R - 1.0), vmul=float(RADIUS - (-RADIUS)), vadd=float(-RADIUS))
         e1.record()
         if record is not None:
             record.append((e0, e1, k0, k1))
@@ -282,10 +364,11 @@ def main() -> int:
     step_ms = [a.elapsed_time(b) for a, b, _, _ in rec]
     total_ms = float(sum(step_ms))
     kern_ms = [k0.elapsed_time(k1) for _, _, k0, k1 in rec if k0 is not None]
+    mc_ms = [k1.elapsed_time(e1) for _, e1, k0, k1 in rec if k0 is not None] if args.batch == 1 else []
 
     # ---- e2e: C-ABI host-buffer call (H2D triplane, D2H mesh inside the timed region)
     e2e_s, h2d, d2h = None, 0, 0
-    if args.mode == "dp":
+    if args.mode == "dp" and args.batch == 1:
         lib = _capi.load()
         _, ws, bs = decoder_numpy(0)
         fpp = ctypes.POINTER(ctypes.c_float)
@@ -319,13 +402,14 @@ def main() -> int:
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- max over ranks
-    stats = torch.tensor([total_ms, (e2e_s or 0.0) * 1e3, float(np.mean(kern_ms)) if kern_ms else 0.0], device=dev, dtype=torch.float64)
+    stats = torch.tensor([total_ms, (e2e_s or 0.0) * 1e3, float(np.mean(kern_ms)) if kern_ms else 0.0,
+                          float(np.mean(mc_ms)) if mc_ms else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms_avg = [float(x) for x in stats.tolist()]
+    total_ms, e2e_ms, kern_ms_avg, mc_ms_avg = [float(x) for x in stats.tolist()]
 
     if rank == 0:
-        units_per_step = float(R) ** 3 * (1 if args.mode == "sharded" else world)
+        units_per_step = float(R) ** 3 * (1 if args.mode == "sharded" else world * args.batch)
         value = units_per_step * args.steps / (total_ms * 1e-3)
         peaks, peak_kind = measured_peaks()
         line = {
@@ -335,7 +419,7 @@ def main() -> int:
             "dtype": "f16 operands, f32 accumulate (layer 0 and head bias/exp in f32)", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "extract_mesh_ms": total_ms / args.steps, "mesh": {"verts": nV, "tris": nF},
-            "gpu_launches": KERNELS_PER_STEP * args.steps * world,
+            "gpu_launches": KERNELS_PER_STEP * args.steps * world * (args.batch if args.mode == "dp" else 1),
         }
         if e2e_s is not None:
             line["e2e"] = {"value": units_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pts/s", "ms_per_step": e2e_ms / args.steps,
@@ -354,6 +438,16 @@ def main() -> int:
                 "kernel_ms": kern_ms_avg, "query_points_per_s": float(R) ** 3 / (kern_ms_avg * 1e-3),
                 "flop_per_point": FLOP_PER_POINT,
                 "note": "algorithmic FLOPs = the reference NeRFMLP count (SURVEY 8d); layer 0 runs as a projected-plane interpolation in fp32, not as an MMA",
+            }
+        if mc_ms_avg > 0 and nV:
+            # marching cubes is HBM-bound: algorithmic bytes = 4 R^3 (density read) + 12 V + 24 F (mesh write),
+            # SURVEY 8d; the time spans signs + count + totals + emit (+ the read-back of the sizes)
+            mc_bytes = 4.0 * float(R) ** 3 + 12.0 * nV + 24.0 * nF
+            line["roofline_mc"] = {
+                "kernels": "mc_signs+mc_count+mc_totals+mc_emit (emit launched behind count; the sizes are read back after it)", "bound": "hbm",
+                "achieved": mc_bytes / (mc_ms_avg * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": mc_bytes / (mc_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": mc_ms_avg, "algorithmic_bytes": mc_bytes,
+                "peak_source": peak_kind,
             }
         if not args.no_cpu_baseline and world == 1:
             v, desc, info = cpu_reference_sample(R, args.cpu_seconds, thresholds[0])

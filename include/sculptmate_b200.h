@@ -151,6 +151,13 @@ int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub, float sig
 int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
                 int emit_last_plane, int flags, float vdiv, float vmul, float vadd, int64_t vertex_id_offset,
                 const void* workspace, float* verts, int64_t* faces, void* stream);
+/* Same, into buffers of a given capacity (in vertices / triangles): elements beyond the capacity are
+ * dropped.  Lets a caller that remembers the size of its last mesh launch emit right behind count --
+ * no host round trip between them -- and read the counts afterwards; it re-emits only on overflow. */
+int smb_mc_emit_bounded(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                        int emit_last_plane, int flags, float vdiv, float vmul, float vadd, int64_t vertex_id_offset,
+                        const void* workspace, float* verts, int64_t verts_capacity, int64_t* faces,
+                        int64_t faces_capacity, void* stream);
 /* cube-case index of every cell, (nx-1,ny-1,nz-1) uint8 (parity/debug). */
 int smb_mc_cases(const float* grid, int nx, int ny, int nz, float sub, float sign, unsigned char* cases,
                  void* stream);

@@ -79,6 +79,10 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "smb_mc_emit_bounded": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
+    ),
     "smb_mc_cases": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "smb_grid_minmax": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
     "smb_extractor_create": (c_int, [_FLOATPP, _FLOATPP, c_int, c_float, c_float, c_int, c_int, POINTER(c_void_p)]),

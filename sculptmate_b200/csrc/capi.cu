@@ -298,6 +298,18 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
   // system.py:184  helper(-(density - threshold))  ->  level = density - threshold, iso 0
   rc = smb_mc_count(ex->density, R, R, R, threshold, 1.0f, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
   if (rc != SMB_OK) return rc;
+  // isosurface.py:52-53 (flip, /(R-1)) and system.py:185-189 (scale to +-radius)
+  const double r = (double)ex->cfg.radius;
+  const int mc_flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE;
+  const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
+  // emit right behind count into the buffers kept from the previous mesh (no host round trip);
+  // the sizes are read afterwards and emit is repeated only if the mesh outgrew them
+  const bool speculative = ex->verts_cap > 0 && ex->faces_cap > 0;
+  if (speculative) {
+    rc = smb_mc_emit_bounded(ex->density, R, R, R, threshold, 1.0f, 0, 1, mc_flags, vdiv, vmul, vadd, 0, ex->mc_ws, ex->verts_dev,
+                             (int64_t)ex->verts_cap, ex->faces_dev, (int64_t)ex->faces_cap, st);
+    if (rc != SMB_OK) return rc;
+  }
   EX_CUDA(cudaMemcpyAsync(ex->counts_pin, ex->counts_dev, sizeof(smb_mc_counts), cudaMemcpyDeviceToHost, st));
   EX_CUDA(cudaStreamSynchronize(st));
   const int64_t V = ex->counts_pin->nverts, F = ex->counts_pin->ntris;
@@ -311,6 +323,7 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
     if (ex->minmax_pin[0] > 0.0f || ex->minmax_pin[1] < 0.0f) return SMB_ERR_LEVEL_RANGE;
     return SMB_ERR_NO_SURFACE;
   }
+  const bool fits = speculative && (size_t)V <= ex->verts_cap && (size_t)F <= ex->faces_cap;
   if ((size_t)V > ex->verts_cap) {
     cudaFree(ex->verts_dev);
     ex->verts_cap = 0;
@@ -335,11 +348,11 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
     EX_CUDA(cudaMallocHost(&ex->faces_pin, sizeof(int64_t) * 3 * (size_t)F * 5 / 4));
     ex->faces_pin_cap = (size_t)F * 5 / 4;
   }
-  // isosurface.py:52-53 (flip, /(R-1)) and system.py:185-189 (scale to +-radius)
-  const double r = (double)ex->cfg.radius;
-  rc = smb_mc_emit(ex->density, R, R, R, threshold, 1.0f, 0, 1, SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE,
-                   (float)(R - 1.0), (float)(r - (-r)), (float)(-r), 0, ex->mc_ws, ex->verts_dev, ex->faces_dev, st);
-  if (rc != SMB_OK) return rc;
+  if (!fits) {
+    rc = smb_mc_emit(ex->density, R, R, R, threshold, 1.0f, 0, 1, mc_flags, vdiv, vmul, vadd, 0, ex->mc_ws, ex->verts_dev,
+                     ex->faces_dev, st);
+    if (rc != SMB_OK) return rc;
+  }
   EX_CUDA(cudaMemcpyAsync(ex->verts_pin, ex->verts_dev, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
   EX_CUDA(cudaMemcpyAsync(ex->faces_pin, ex->faces_dev, sizeof(int64_t) * 3 * F, cudaMemcpyDeviceToHost, st));
   EX_CUDA(cudaStreamSynchronize(st));

@@ -408,6 +408,7 @@ struct EmitParams {
   const ChunkRec* cbase;
   float* verts;
   long long* faces;
+  long long vcap, fcap;  // capacity of verts / faces in vertices / triangles (writes beyond are dropped)
 };
 
 __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float vmul, float vadd) {
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
           const float fi = (float)(p.x_origin + si), fj = (float)sj, fk = (float)k;
           const bool store_inplane = (si < d.nx - 1) || p.emit_last_plane;
           const long long n_before = __popc(smy & below) + __popc(smz & below);
-          if (by && store_inplane) {
+          if (by && store_inplane && (long long)sv0 + n_before < p.vcap) {
             const float bb = mc_val(p.grid, pt + sy, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
             float* o = p.verts + 3 * ((long long)sv0 + n_before);
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
             o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
           }
-          if (bz && store_inplane) {
+          if (bz && store_inplane && (long long)sv0 + n_before + (by ? 1 : 0) < p.vcap) {
             const float bb = mc_val(p.grid, pt + 1, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
             float* o = p.verts + 3 * ((long long)sv0 + n_before + (by ? 1 : 0));
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
             o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
           }
-          if (bx) {
+          if (bx && (long long)sv1 + __popc(smx & below) < p.vcap) {
             const float bb = mc_val(p.grid, pt + sx, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
             float* o = p.verts + 3 * ((long long)sv1 + __popc(smx & below));
@@ -624,8 +625,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
               if (dk == 0) s_eid[8 + 2 * di + dj][threadIdx.x] = idyz + ((hi.y >> bb) & 1u);
             }
           }
-          long long* o = p.faces + 3 * ((long long)st0 + (inc - ntri));
-          for (uint32_t t = 0; t < ntri; ++t) {
+          const long long slot0 = (long long)st0 + (inc - ntri);
+          long long* o = p.faces + 3 * slot0;
+          for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
             const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + p.id_offset;
             const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + p.id_offset;
             const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + p.id_offset;
@@ -704,11 +706,11 @@ extern "C" int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 
-extern "C" int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
-                           int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
-                           int64_t vertex_id_offset, const void* workspace, float* verts, int64_t* faces,
-                           void* stream) {
-  if (!grid || !workspace || nx <= 0 || ny <= 0 || nz <= 0) return SMB_ERR_BAD_ARG;
+extern "C" int smb_mc_emit_bounded(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                                   int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
+                                   int64_t vertex_id_offset, const void* workspace, float* verts, int64_t verts_capacity,
+                                   int64_t* faces, int64_t faces_capacity, void* stream) {
+  if (!grid || !workspace || nx <= 0 || ny <= 0 || nz <= 0 || verts_capacity < 0 || faces_capacity < 0) return SMB_ERR_BAD_ARG;
   McDims d = make_dims(nx, ny, nz);
   McWorkspace w = carve(const_cast<void*>(workspace), d);
   EmitParams p;
@@ -728,12 +730,22 @@ extern "C" int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub,
   p.cbase = w.cbase;
   p.verts = verts;
   p.faces = reinterpret_cast<long long*>(faces);
+  p.vcap = verts ? verts_capacity : 0;
+  p.fcap = faces ? faces_capacity : 0;
   const long long nbatch = (d.nwords + 31) / 32;
   long long blocks = (nbatch + kEmitWarps - 1) / kEmitWarps;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   mc_emit<<<(unsigned)blocks, kEmitWarps * 32, 0, (cudaStream_t)stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+
+extern "C" int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                           int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
+                           int64_t vertex_id_offset, const void* workspace, float* verts, int64_t* faces,
+                           void* stream) {
+  return smb_mc_emit_bounded(grid, nx, ny, nz, sub, sign, x_origin, emit_last_plane, flags, vdiv, vmul, vadd, vertex_id_offset,
+                             workspace, verts, INT64_MAX, faces, INT64_MAX, stream);
 }
 
 extern "C" int smb_mc_cases(const float* grid, int nx, int ny, int nz, float sub, float sign, unsigned char* cases,

@@ -308,6 +308,54 @@ def mc_emit(
     return verts, faces
 
 
+_mc_caps: Dict[Tuple, Tuple[int, int]] = {}
+
+
+def mc_extract(
+    grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, flags: int = 0, vdiv: float = 1.0, vmul: float = 1.0, vadd: float = 0.0
+) -> Tuple[torch.Tensor, torch.Tensor, McPending]:
+    """count + emit for a whole grid with no host round trip between them: emit is launched right
+    behind count into buffers sized from the previous mesh of this shape (+25 %), the counts are
+    read afterwards and the outputs are views of exactly (V,3) / (F,3).  Falls back to the
+    two-phase path on the first call for a shape and on overflow."""
+    _require_cuda(grid, "grid")
+    if grid.dim() != 3 or grid.dtype != torch.float32 or not grid.is_contiguous():
+        raise ValueError("grid must be a contiguous (nx,ny,nz) float32 tensor")
+    nx, ny, nz = grid.shape
+    dev = grid.device
+    key = (str(dev), (nx, ny, nz))
+    cap = _mc_caps.get(key)
+    if cap is None:
+        pend = mc_count(grid, sub=sub, sign=sign, emit_last_plane=True)
+        verts, faces = mc_emit(pend, flags=flags, vdiv=vdiv, vmul=vmul, vadd=vadd)
+    else:
+        ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
+        lib = _capi.load()
+        verts = torch.empty((cap[0], 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((cap[1], 3), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            check(lib.smb_mc_count(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), 1, ws.data_ptr(), ws.numel(), counts_dev.data_ptr(), st), "smb_mc_count")
+            check(
+                lib.smb_mc_emit_bounded(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), 0, 1, int(flags), float(vdiv), float(vmul),
+                                        float(vadd), 0, ws.data_ptr(), verts.data_ptr(), cap[0], faces.data_ptr(), cap[1], st),
+                "smb_mc_emit_bounded",
+            )
+            counts_pin.copy_(counts_dev, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        pend = McPending(grid, float(sub), float(sign), True, int(counts_pin[0]), int(counts_pin[1]), int(counts_pin[2]))
+        if pend.nverts <= cap[0] and pend.ntris <= cap[1]:
+            verts, faces = verts[: pend.nverts], faces[: pend.ntris]
+        else:  # the surface grew past the remembered capacity: emit again at the exact size
+            verts, faces = mc_emit(pend, flags=flags, vdiv=vdiv, vmul=vmul, vadd=vadd)
+    old = cap or (0, 0)
+    _mc_caps[key] = (max(old[0], pend.nverts * 5 // 4 + 1024), max(old[1], pend.ntris * 5 // 4 + 1024))
+    if len(_mc_caps) > 8:
+        for k in list(_mc_caps)[:-8]:
+            del _mc_caps[k]
+    return verts, faces, pend
+
+
 def mc_cases(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0) -> torch.Tensor:
     _require_cuda(grid, "grid")
     nx, ny, nz = grid.shape

@@ -47,9 +47,8 @@ class MarchingCubeHelper(IsosurfaceHelper):
         # isosurface.py:45 negates the input and extracts the 0-level set; the kernel
         # applies val = (grid - 0) * (-1) on the fly instead of writing a negated copy.
         grid = level.detach().to(torch.float32).contiguous().view(R, R, R)
-        pend = runtime.mc_count(grid, sub=0.0, sign=-1.0, emit_last_plane=True)
+        # isosurface.py:52-53: faces[:, [1,0,2]] and verts / (R - 1)
+        v_pos, t_pos_idx, pend = runtime.mc_extract(grid, sub=0.0, sign=-1.0, flags=MC_FLIP | MC_DIV, vdiv=float(R - 1.0))
         if pend.nverts == 0 or pend.ntris == 0:
             runtime.raise_for_empty_surface(grid, 0.0, -1.0)
-        # isosurface.py:52-53: faces[:, [1,0,2]] and verts / (R - 1)
-        v_pos, t_pos_idx = runtime.mc_emit(pend, flags=MC_FLIP | MC_DIV, vdiv=float(R - 1.0))
         return v_pos, t_pos_idx

@@ -96,16 +96,13 @@ class TSR(BaseModule):
                 self.decoder, scene_code, R, axis_u=self._axis(R, scene_code.device), precision=precision
             )
         # helper(-(density - threshold)) then level = -input  ==  val = density - threshold
-        pend = runtime.mc_count(density, sub=float(threshold), sign=1.0, emit_last_plane=True)
+        v_pos, t_pos_idx, pend = runtime.mc_extract(
+            density, sub=float(threshold), sign=1.0, flags=MC_FLIP | MC_DIV | MC_AFFINE,
+            vdiv=float(R - 1.0), vmul=float(radius - (-radius)), vadd=float(-radius),
+        )
         if pend.nverts == 0 or pend.ntris == 0:
             runtime.raise_for_empty_surface(density, float(threshold), 1.0)
-        return runtime.mc_emit(
-            pend,
-            flags=MC_FLIP | MC_DIV | MC_AFFINE,
-            vdiv=float(R - 1.0),
-            vmul=float(radius - (-radius)),
-            vadd=float(-radius),
-        )
+        return v_pos, t_pos_idx
 
     def extract_mesh(self, scene_codes, enable_texture=False, mesh_name="NewMesh", resolution: int = 256, threshold: float = 25.0):
         for scene_code in scene_codes:

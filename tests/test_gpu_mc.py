@@ -123,3 +123,22 @@ def test_error_behaviour_matches_skimage():
     z[77] = 0.0
     with pytest.raises(RuntimeError, match="No surface"):
         h(z.cuda())
+
+
+def test_speculative_extract_equals_two_phase_incl_overflow():
+    """mc_extract launches emit behind count into buffers sized from the previous mesh of the
+    same shape; a mesh that outgrows them must be re-emitted, a smaller one sliced."""
+    from sculptmate_b200 import runtime
+
+    R = 48
+    runtime._mc_caps.clear()
+    a = np.linspace(-1, 1, R, dtype=np.float32)
+    x, y, z = np.meshgrid(a, a, a, indexing="ij")
+    rr = np.sqrt(x * x + y * y + z * z)
+    for radius in (0.2, 0.9, 0.5, 0.21):  # first call (two-phase), overflow, fits, fits with slack
+        g = torch.from_numpy((radius - rr).astype(np.float32)).cuda()
+        v, f, pend = runtime.mc_extract(g, sub=0.0, sign=1.0, flags=3, vdiv=float(R - 1))
+        p2 = runtime.mc_count(g, sub=0.0, sign=1.0)
+        v2, f2 = runtime.mc_emit(p2, flags=3, vdiv=float(R - 1))
+        assert (pend.nverts, pend.ntris) == (p2.nverts, p2.ntris) == (v.shape[0], f.shape[0])
+        assert torch.equal(v, v2) and torch.equal(f, f2), radius

@@ -1,0 +1,63 @@
+"""Live re-validation of the oracle and of the CPU port against the UNMODIFIED reference,
+where /root/reference exists (skipped on the GPU box, which only has the committed goldens)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference is not present on this machine")
+RADIUS = 0.87
+
+
+def test_query_triplane_restatement_vs_live_reference():
+    from oracle import field_oracle as fo
+
+    ref = ref_shim.load_triposr()
+    dec = ref_shim.make_reference_decoder(5)
+    rend = ref_shim.make_reference_renderer(1000)
+    torch.manual_seed(6)
+    tp = torch.randn(3, 40, 20, 20)
+    pos = (torch.rand(3000, 3) * 2 - 1) * 1.05 * RADIUS  # a few % outside the radius: zero padding
+    with torch.no_grad():
+        out = rend.query_triplane(dec, pos, tp)
+    ws, bs = fo.decoder_params_from_state_dict({k: v.numpy() for k, v in dec.state_dict().items()})
+    mine = fo.query_triplane(pos.numpy(), tp.numpy(), ws, bs, radius=RADIUS)
+    for k in ("density", "features", "density_act", "color"):
+        assert np.abs(mine[k] - out[k].numpy()).max() < 2e-5, k
+
+
+def test_cpu_port_matches_live_reference_extract_mesh_inputs():
+    """oracle/cpu_reference_port.py issues the same aten calls as the reference: same density."""
+    from oracle import cpu_reference_port as port
+
+    ref = ref_shim.load_triposr()
+    dec = ref_shim.make_reference_decoder(2)
+    rend = ref_shim.make_reference_renderer(8192)
+    torch.manual_seed(3)
+    tp = torch.randn(3, 40, 16, 16)
+    R = 20
+    h = ref.isosurface.MarchingCubeHelper(R)
+    pos = ref.utils.scale_tensor(h.grid_vertices, (0, 1), (-RADIUS, RADIUS))
+    with torch.no_grad():
+        want = rend.query_triplane(dec, pos, tp)["density_act"]
+    sd = dec.state_dict()
+    layers = port.make_layers([sd[f"layers.{i}.weight"].numpy() for i in range(0, 20, 2)], [sd[f"layers.{i}.bias"].numpy() for i in range(0, 20, 2)])
+    got = port.query_triplane(layers, pos, tp)["density_act"]
+    assert torch.equal(got, want)  # identical calls, identical bits
+
+
+def test_marching_tets_restatement_vs_live_reference(tmp_path):
+    from oracle import sf3d_oracle as so
+    from sculptmate_b200.sf3d.tets import kuhn_tet_grid, save_tet_grid
+
+    ref = ref_shim.load_sf3d()
+    n = 7
+    helper = ref.isosurface.MarchingTetrahedraHelper(n, save_tet_grid(str(tmp_path / "t.npz"), n))
+    g = torch.Generator().manual_seed(1)
+    sdf = torch.randn(helper.grid_vertices.shape[0], 1, generator=g)
+    with torch.no_grad():
+        mesh = helper(sdf, None)
+    v, f = so.marching_tets(*kuhn_tet_grid(n)[:1], sdf.numpy(), kuhn_tet_grid(n)[1])
+    np.testing.assert_array_equal(f, mesh.t_pos_idx.numpy())
+    np.testing.assert_array_equal(v, mesh.v_pos.numpy())

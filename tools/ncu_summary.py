@@ -65,9 +65,14 @@ def main() -> int:
             blocks.append(cur)
         elif cur is not None:
             cur["rows"].append(row)
+    seen = set()
     for b in blocks:
         if len(b["rows"]) < 2:
             continue
+        sig = (b["name"], len(b["rows"]), tuple(b["rows"][1][:3]) if len(b["rows"]) > 1 else ())
+        if sig in seen:  # the source page repeats a kernel's table once per view
+            continue
+        seen.add(sig)
         h = b["rows"][0]
         ix = {n: i for i, n in enumerate(h)}
         if "# Samples" not in ix:
