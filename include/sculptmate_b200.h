@@ -158,6 +158,23 @@ int smb_mc_emit_bounded(const float* grid, int nx, int ny, int nz, float sub, fl
                         int emit_last_plane, int flags, float vdiv, float vmul, float vadd, int64_t vertex_id_offset,
                         const void* workspace, float* verts, int64_t verts_capacity, int64_t* faces,
                         int64_t faces_capacity, void* stream);
+/* Gather mode (multi-GPU, one process per GPU): all_counts_dev is (world,4) int64 = every rank's
+ * smb_mc_counts (an all-gather of the counts_dev of smb_mc_count, device to device); the kernel derives this
+ * slab's vertex / triangle offsets from the lower ranks' counts and stores its part of the mesh, with global
+ * vertex ids, straight into verts_dst / faces_dst -- the DESTINATION rank's buffers, mapped into this process
+ * with smb_ipc_open (NVLink peer stores; no staging buffer, no send/recv).  Elements beyond the capacities are
+ * dropped (the caller re-runs with larger buffers). */
+int smb_mc_emit_gather(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                       int emit_last_plane, int flags, float vdiv, float vmul, float vadd, const void* workspace,
+                       const int64_t* all_counts_dev, int rank, float* verts_dst, int64_t verts_capacity,
+                       int64_t* faces_dst, int64_t faces_capacity, void* stream);
+/* Peer-memory plumbing for the above: the destination rank allocates its mesh buffers with smb_dev_alloc,
+ * exports a 64-byte handle, the other ranks map it (this also enables peer access). */
+int smb_dev_alloc(size_t bytes, void** out);
+int smb_dev_free(void* ptr);
+int smb_ipc_export(const void* dev_ptr, void* handle64);
+int smb_ipc_open(const void* handle64, void** out);
+int smb_ipc_close(void* mapped_ptr);
 /* cube-case index of every cell, (nx-1,ny-1,nz-1) uint8 (parity/debug). */
 int smb_mc_cases(const float* grid, int nx, int ny, int nz, float sub, float sign, unsigned char* cases,
                  void* stream);

@@ -83,6 +83,16 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     ),
+    "smb_mc_emit_gather": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_int,
+         c_void_p, c_int64, c_void_p, c_int64, c_void_p],
+    ),
+    "smb_dev_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "smb_dev_free": (c_int, [c_void_p]),
+    "smb_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "smb_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "smb_ipc_close": (c_int, [c_void_p]),
     "smb_mc_cases": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "smb_grid_minmax": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p]),
     "smb_extractor_create": (c_int, [_FLOATPP, _FLOATPP, c_int, c_float, c_float, c_int, c_int, POINTER(c_void_p)]),

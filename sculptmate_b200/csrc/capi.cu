@@ -362,3 +362,26 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
   *ntris = F;
   return SMB_OK;
 }
+
+// ------------------------------------------------- peer memory (multi-GPU gather)
+// The sharded path lets every rank's emit kernel store its slab straight into the destination
+// rank's mesh buffers over NVLink.  The destination allocates them here (cudaMalloc: the pointer
+// IS the allocation base, which cudaIpcGetMemHandle requires), exports a handle, and the other
+// processes map it; cudaIpcOpenMemHandle enables peer access between the two devices.
+extern "C" int smb_dev_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return SMB_ERR_BAD_ARG;
+  return smb_check(cudaMalloc(out, bytes));
+}
+extern "C" int smb_dev_free(void* ptr) { return smb_check(cudaFree(ptr)); }
+extern "C" int smb_ipc_export(const void* dev_ptr, void* handle64) {
+  if (!dev_ptr || !handle64) return SMB_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  return smb_check(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), const_cast<void*>(dev_ptr)));
+}
+extern "C" int smb_ipc_open(const void* handle64, void** out) {
+  if (!handle64 || !out) return SMB_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return smb_check(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+}
+extern "C" int smb_ipc_close(void* mapped_ptr) { return smb_check(cudaIpcCloseMemHandle(mapped_ptr)); }

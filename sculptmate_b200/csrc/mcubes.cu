@@ -409,6 +409,10 @@ struct EmitParams {
   float* verts;
   long long* faces;
   long long vcap, fcap;  // capacity of verts / faces in vertices / triangles (writes beyond are dropped)
+  // gather mode: (world,4) int64 = every rank's smb_mc_counts; this slab's output offsets are the
+  // sums over the lower ranks, and verts/faces point at the destination rank's buffers (peer memory)
+  const long long* all_counts;
+  int rank;
 };
 
 __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float vmul, float vadd) {
@@ -454,6 +458,14 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
   __syncthreads();
 
   const McDims d = p.d;
+  long long v_off = 0, f_off = 0;
+  if (p.all_counts) {
+    for (int g = 0; g < p.rank; ++g) {
+      v_off += p.all_counts[4 * g + 0];
+      f_off += p.all_counts[4 * g + 1];
+    }
+  }
+  const long long id_off = p.id_offset + v_off;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long gwarp = (long long)blockIdx.x * kEmitWarps + warp;
@@ -522,26 +534,26 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
           const float fi = (float)(p.x_origin + si), fj = (float)sj, fk = (float)k;
           const bool store_inplane = (si < d.nx - 1) || p.emit_last_plane;
           const long long n_before = __popc(smy & below) + __popc(smz & below);
-          if (by && store_inplane && (long long)sv0 + n_before < p.vcap) {
+          if (by && store_inplane && v_off + sv0 + n_before < p.vcap) {
             const float bb = mc_val(p.grid, pt + sy, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = p.verts + 3 * ((long long)sv0 + n_before);
+            float* o = p.verts + 3 * (v_off + sv0 + n_before);
             o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
             o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
           }
-          if (bz && store_inplane && (long long)sv0 + n_before + (by ? 1 : 0) < p.vcap) {
+          if (bz && store_inplane && v_off + sv0 + n_before + (by ? 1 : 0) < p.vcap) {
             const float bb = mc_val(p.grid, pt + 1, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = p.verts + 3 * ((long long)sv0 + n_before + (by ? 1 : 0));
+            float* o = p.verts + 3 * (v_off + sv0 + n_before + (by ? 1 : 0));
             o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
             o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
           }
-          if (bx && (long long)sv1 + __popc(smx & below) < p.vcap) {
+          if (bx && v_off + sv1 + __popc(smx & below) < p.vcap) {
             const float bb = mc_val(p.grid, pt + sx, p.sub, p.sign);
             const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = p.verts + 3 * ((long long)sv1 + __popc(smx & below));
+            float* o = p.verts + 3 * (v_off + sv1 + __popc(smx & below));
             o[0] = mc_xform(__fadd_rn(fi, t), p.flags, p.vdiv, p.vmul, p.vadd);
             o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
             o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
@@ -625,12 +637,12 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
               if (dk == 0) s_eid[8 + 2 * di + dj][threadIdx.x] = idyz + ((hi.y >> bb) & 1u);
             }
           }
-          const long long slot0 = (long long)st0 + (inc - ntri);
+          const long long slot0 = f_off + st0 + (inc - ntri);
           long long* o = p.faces + 3 * slot0;
           for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
-            const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + p.id_offset;
-            const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + p.id_offset;
-            const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + p.id_offset;
+            const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + id_off;
+            const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + id_off;
+            const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + id_off;
             const bool flip = p.flags & SMB_MC_FLIP;
             o[3 * t + 0] = flip ? i1 : i0;
             o[3 * t + 1] = flip ? i0 : i1;
@@ -640,6 +652,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
       }
     }
   }
+  if (p.all_counts) __threadfence_system();  // peer-memory stores are performed before the grid retires
 }
 
 // ----------------------------------------------------------- min / max
@@ -706,10 +719,10 @@ extern "C" int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 
-extern "C" int smb_mc_emit_bounded(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
-                                   int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
-                                   int64_t vertex_id_offset, const void* workspace, float* verts, int64_t verts_capacity,
-                                   int64_t* faces, int64_t faces_capacity, void* stream) {
+static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                       int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
+                       int64_t vertex_id_offset, const void* workspace, float* verts, int64_t verts_capacity,
+                       int64_t* faces, int64_t faces_capacity, const int64_t* all_counts, int rank, void* stream) {
   if (!grid || !workspace || nx <= 0 || ny <= 0 || nz <= 0 || verts_capacity < 0 || faces_capacity < 0) return SMB_ERR_BAD_ARG;
   McDims d = make_dims(nx, ny, nz);
   McWorkspace w = carve(const_cast<void*>(workspace), d);
@@ -732,12 +745,31 @@ extern "C" int smb_mc_emit_bounded(const float* grid, int nx, int ny, int nz, fl
   p.faces = reinterpret_cast<long long*>(faces);
   p.vcap = verts ? verts_capacity : 0;
   p.fcap = faces ? faces_capacity : 0;
+  p.all_counts = reinterpret_cast<const long long*>(all_counts);
+  p.rank = rank;
   const long long nbatch = (d.nwords + 31) / 32;
   long long blocks = (nbatch + kEmitWarps - 1) / kEmitWarps;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   mc_emit<<<(unsigned)blocks, kEmitWarps * 32, 0, (cudaStream_t)stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+
+extern "C" int smb_mc_emit_bounded(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                                   int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
+                                   int64_t vertex_id_offset, const void* workspace, float* verts, int64_t verts_capacity,
+                                   int64_t* faces, int64_t faces_capacity, void* stream) {
+  return launch_emit(grid, nx, ny, nz, sub, sign, x_origin, emit_last_plane, flags, vdiv, vmul, vadd, vertex_id_offset, workspace,
+                     verts, verts_capacity, faces, faces_capacity, nullptr, 0, stream);
+}
+
+extern "C" int smb_mc_emit_gather(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                                  int emit_last_plane, int flags, float vdiv, float vmul, float vadd, const void* workspace,
+                                  const int64_t* all_counts_dev, int rank, float* verts_dst, int64_t verts_capacity,
+                                  int64_t* faces_dst, int64_t faces_capacity, void* stream) {
+  if (!all_counts_dev || rank < 0 || !verts_dst || !faces_dst) return SMB_ERR_BAD_ARG;
+  return launch_emit(grid, nx, ny, nz, sub, sign, x_origin, emit_last_plane, flags, vdiv, vmul, vadd, 0, workspace, verts_dst,
+                     verts_capacity, faces_dst, faces_capacity, all_counts_dev, rank, stream);
 }
 
 extern "C" int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,

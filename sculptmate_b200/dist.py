@@ -9,12 +9,19 @@ locally as ``V_g + n``; adding the running offset sum(V_0..V_{g-1}) to every fac
 and concatenating slabs in rank order reproduces the single-GPU mesh bit for bit --
 no seam search, no welding pass.
 
-Collectives (NCCL over NVLink on the GPU box, gloo in the CPU tests):
-  broadcast   triplane (+ decoder parameters when asked)     rank 0 -> all
-  all_gather  (V_g, F_g)                                     2 int64 per rank
-  send/recv   slab vertices and faces                        ranks -> dst, placed directly
-                                                             at their final offsets
-There is no collective on the data path of the kernels themselves.
+Two transports for the gather:
+
+``p2p`` (default on CUDA, world > 1) -- fused with the emit kernel.  The destination rank owns
+  the mesh buffers (cudaMalloc + CUDA IPC, mapped into every process once); per call each rank
+  runs  lattice -> mc_count -> [NCCL all_gather of the 4-int64 counts, device to device] ->
+  mc_emit in gather mode, whose kernel derives its output offsets from the gathered counts ON THE
+  DEVICE and stores vertices and faces (with global ids) straight into the destination's buffers
+  over NVLink peer memory -> [tiny NCCL all_reduce as the completion fence].  No staging buffer,
+  no send/recv pass, no host round trip between the kernels; one host sync per call (the sizes).
+``nccl`` -- count -> all_gather -> emit locally -> grouped isend/irecv of the slab meshes to
+  their final offsets.  Also what the gloo CPU tests exercise with the oracle as the backend.
+
+Other collectives: ``broadcast`` of the triplane (+ decoder parameters when asked), rank 0 -> all.
 """
 from __future__ import annotations
 
@@ -161,6 +168,167 @@ def broadcast_scene(scene_code: torch.Tensor, decoder: Optional[torch.nn.Module]
             dist.broadcast(p.data, src=src, group=group)
 
 
+# ------------------------------------------------------------------ p2p transport
+class _CaiView:
+    """Exposes a region of a raw device allocation to torch (zero-copy) through
+    ``__cuda_array_interface__``; keeps the owning allocation alive."""
+
+    def __init__(self, owner, ptr: int, shape, typestr: str):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class _DevAlloc:
+    def __init__(self, nbytes: int):
+        import ctypes
+
+        from . import _capi
+
+        self._lib = _capi.load()
+        p = ctypes.c_void_p()
+        _capi.check(self._lib.smb_dev_alloc(int(nbytes), ctypes.byref(p)), "smb_dev_alloc")
+        self.ptr, self.nbytes = int(p.value), int(nbytes)
+
+    def handle(self) -> torch.Tensor:
+        import ctypes
+
+        from . import _capi
+
+        h = (ctypes.c_ubyte * 64)()
+        _capi.check(self._lib.smb_ipc_export(self.ptr, h), "smb_ipc_export")
+        return torch.tensor(list(h), dtype=torch.uint8)
+
+    def __del__(self):
+        try:
+            self._lib.smb_dev_free(self.ptr)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+class PeerGather:
+    """Persistent state of the ``p2p`` transport for one (process group, destination): the
+    destination's double-buffered mesh storage, its mapping in every other process, and the
+    device/pinned count buffers.  Capacities grow by re-running ``setup`` collectively."""
+
+    SETS = 2  # results stay valid until the call after the next one
+
+    def __init__(self, device: torch.device, group=None, dst: int = 0):
+        self.device, self.group, self.dst = device, group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.vcap = self.fcap = 0
+        self.allocs: list = []  # dst: [(_DevAlloc verts, _DevAlloc faces)] * SETS
+        self.ptrs: list = []  # every rank: [(verts ptr, faces ptr)] * SETS in THIS process' address space
+        self.turn = 0
+        self.counts_dev = torch.zeros(4, dtype=torch.int64, device=device)
+        self.all_counts_dev = torch.zeros(4 * self.world, dtype=torch.int64, device=device)
+        self.all_counts_pin = torch.zeros(4 * self.world, dtype=torch.int64).pin_memory()
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def setup(self, vcap: int, fcap: int) -> None:
+        """Collective.  (Re)allocate the destination buffers and map them everywhere."""
+        import ctypes
+
+        from . import _capi
+
+        lib = _capi.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)  # nobody is still writing into the old buffers
+        if self.rank != self.dst:
+            for pv, pf in self.ptrs:
+                lib.smb_ipc_close(pv)
+                lib.smb_ipc_close(pf)
+        self.ptrs, self.allocs = [], []
+        handles = torch.zeros(self.SETS * 2 * 64, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            if self.rank == self.dst:
+                hs = []
+                for _ in range(self.SETS):
+                    av, af = _DevAlloc(12 * vcap), _DevAlloc(24 * fcap)
+                    self.allocs.append((av, af))
+                    self.ptrs.append((av.ptr, af.ptr))
+                    hs += [av.handle(), af.handle()]
+                handles.copy_(torch.cat(hs))
+            dist.broadcast(handles, src=_global_rank(self.group, self.dst), group=self.group)
+            if self.rank != self.dst:
+                hb = handles.cpu().numpy().tobytes()
+                for k in range(self.SETS):
+                    out = []
+                    for j in range(2):
+                        h = (ctypes.c_ubyte * 64).from_buffer_copy(hb[(2 * k + j) * 64 : (2 * k + j + 1) * 64])
+                        p = ctypes.c_void_p()
+                        _capi.check(lib.smb_ipc_open(h, ctypes.byref(p)), "smb_ipc_open")
+                        out.append(int(p.value))
+                    self.ptrs.append(tuple(out))
+        self.vcap, self.fcap = int(vcap), int(fcap)
+        dist.barrier(self.group)
+
+    def views(self, k: int, V: int, F: int):
+        av, af = self.allocs[k]
+        verts = torch.as_tensor(_CaiView(av, av.ptr, (V, 3), "<f4"), device=self.device)
+        faces = torch.as_tensor(_CaiView(af, af.ptr, (F, 3), "<i8"), device=self.device)
+        return verts, faces
+
+
+def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precision):
+    import ctypes  # noqa: F401
+
+    from . import _capi, runtime
+    from ._capi import MC_AFFINE, MC_DIV, MC_FLIP
+
+    dev = scene_code.device
+    key = (id(group), dst, str(dev))
+    cache = tsr.__dict__.setdefault("_peer_gather", {})
+    pg = cache.get(key)
+    if pg is None:
+        pg = cache[key] = PeerGather(dev, group, dst)
+    world, rank = pg.world, pg.rank
+    a, b = slab_partition(resolution, world)[rank]
+    nx, R, last = b - a + 1, resolution, rank == world - 1
+    lib = _capi.load()
+    tsr.set_marching_cubes_resolution(R)
+    with torch.no_grad():
+        slab = tsr.renderer.query_lattice(tsr.decoder, scene_code, R, axis_u=tsr._axis(R, dev), x_begin=a, nx=nx, precision=precision)
+    ws, _, _ = runtime._mc_cache.get(dev, (nx, R, R))
+    r = tsr.renderer.cfg.radius
+    flags = MC_FLIP | MC_DIV | MC_AFFINE
+
+    def counts_to_host():
+        pg.all_counts_pin.copy_(pg.all_counts_dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        c = pg.all_counts_pin.view(world, 4)
+        return int(c[:, 0].sum()), int(c[:, 1].sum())
+
+    with torch.cuda.device(dev):
+        st = runtime._stream_ptr(dev)
+        _capi.check(lib.smb_mc_count(slab.data_ptr(), nx, R, R, float(threshold), 1.0, int(last), ws.data_ptr(), ws.numel(),
+                                     pg.counts_dev.data_ptr(), st), "smb_mc_count")
+        dist.all_gather_into_tensor(pg.all_counts_dev, pg.counts_dev, group=group)
+        totals = None
+        if pg.vcap == 0:  # first call: learn the sizes, then map buffers with 25 % head room
+            totals = counts_to_host()
+            pg.setup(totals[0] * 5 // 4 + 4096, totals[1] * 5 // 4 + 4096)
+        while True:
+            k = pg.turn % pg.SETS
+            pv, pf = pg.ptrs[k]
+            _capi.check(
+                lib.smb_mc_emit_gather(slab.data_ptr(), nx, R, R, float(threshold), 1.0, a, int(last), flags, float(R - 1.0),
+                                       float(r - (-r)), float(-r), ws.data_ptr(), pg.all_counts_dev.data_ptr(), rank,
+                                       pv, pg.vcap, pf, pg.fcap, st),
+                "smb_mc_emit_gather",
+            )
+            dist.all_reduce(pg.token, group=group)  # completion fence: every slab has been stored
+            if totals is None:
+                totals = counts_to_host()
+            if totals[0] <= pg.vcap and totals[1] <= pg.fcap:
+                break
+            pg.setup(totals[0] * 5 // 4 + 4096, totals[1] * 5 // 4 + 4096)  # outgrown (every rank sees the same counts)
+        pg.turn += 1
+        if rank == dst:
+            torch.cuda.current_stream(dev).synchronize()
+            return pg.views(k, totals[0], totals[1])
+    return None, None
+
+
 def extract_mesh_sharded(
     tsr,
     scene_code: torch.Tensor,
@@ -170,11 +338,17 @@ def extract_mesh_sharded(
     dst: int = 0,
     precision: str = "tc",
     broadcast: bool = True,
+    transport: str = "p2p",
 ):
     """TSR.extract_mesh for one scene code with the lattice sharded over the group.
-    Returns (v_pos, t_pos_idx) on ``dst`` (device tensors), (None, None) elsewhere."""
-    if broadcast and dist.is_available() and dist.is_initialized():
+    Returns (v_pos, t_pos_idx) on ``dst`` (device tensors), (None, None) elsewhere.  With the
+    ``p2p`` transport the tensors are views of persistent buffers, valid until the call after
+    the next one."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if broadcast and multi:
         broadcast_scene(scene_code, None, src=dst, group=group)
+    if multi and transport == "p2p" and scene_code.is_cuda:
+        return _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precision)
     backend = CudaSlabBackend(tsr, scene_code, resolution, threshold, precision)
     verts, faces, _ = gather_slab_meshes(backend, resolution, group=group, dst=dst)
     return verts, faces

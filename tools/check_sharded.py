@@ -31,11 +31,23 @@ def main() -> int:
         tp = baked_triplane(seed).to(dev) if rank == 0 else torch.zeros(3, 40, 64, 64, device=dev)
         broadcast_scene(tp, model.decoder, src=0)
         thr = float(model.renderer.query_lattice(model.decoder, tp, 64).median())
-        v, f = extract_mesh_sharded(model, tp, R, thr, broadcast=False)
+        for transport in ("p2p", "nccl", "p2p"):
+            v, f = extract_mesh_sharded(model, tp, R, thr, broadcast=False, transport=transport)
+            if rank == 0:
+                v1, f1 = model.extract_mesh_tensors(tp, R, thr)
+                same = v.shape == v1.shape and f.shape == f1.shape and torch.equal(v, v1) and torch.equal(f, f1)
+                print(f"sharded x{world} R={R} seed={seed} {transport}: V={v.shape[0]} F={f.shape[0]} bit-exact vs 1 GPU: {same}", flush=True)
+                ok &= bool(same)
+    # a bigger surface than the mapped buffers hold: the p2p transport must regrow collectively
+    tp = baked_triplane(100).to(dev) if rank == 0 else torch.zeros(3, 40, 64, 64, device=dev)
+    broadcast_scene(tp, None, src=0)
+    for Rb in (R, R + 32):
+        thr = float(model.renderer.query_lattice(model.decoder, tp, 64).median())
+        v, f = extract_mesh_sharded(model, tp, Rb, thr, broadcast=False)
         if rank == 0:
-            v1, f1 = model.extract_mesh_tensors(tp, R, thr)
-            same = v.shape == v1.shape and f.shape == f1.shape and torch.equal(v, v1) and torch.equal(f, f1)
-            print(f"sharded x{world} R={R} seed={seed}: V={v.shape[0]} F={f.shape[0]} bit-exact vs 1 GPU: {same}", flush=True)
+            v1, f1 = model.extract_mesh_tensors(tp, Rb, thr)
+            same = torch.equal(v, v1) and torch.equal(f, f1)
+            print(f"sharded x{world} R={Rb} regrow p2p: V={v.shape[0]} F={f.shape[0]} bit-exact vs 1 GPU: {same}", flush=True)
             ok &= bool(same)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
