@@ -201,6 +201,36 @@ int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int res
                           const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                           int64_t* ntris);
 
+/* ------------------------------------------- field query on tensor cores, any positions
+ * One kernel for both decoders of the path: bilinear gathers from the channels-last planes feed an MLP
+ * whose every layer is a tcgen05 UMMA (fp16 operands, fp32 accumulate), activations kept on-chip.
+ *   TripoSR: query_triplane + NeRFMLP (nerf_renderer.py:41-91) -- the colour query at mesh vertices
+ *            (system.py:191-198): layers 120->64, 8 x 64->64, 64->4.
+ *   SF3D:    query_triplane + MaterialMLP heads density / vertex_offset (sf3d/system.py:153-154) fused as
+ *            120->128 (both first layers), 128->128 (block-diagonal), 128->4.
+ * The MLP is packed on the host from dense row-major (out,in) matrices: layer l has k_in[l] inputs
+ * (<= 128, padded to 64 or 128) and n_out[l] outputs (hidden: padded to 64 or 128 and equal to the next
+ * layer's padded K; last: <= 4).  Every layer but the last is followed by SiLU.
+ * Outputs (each optional): out0_raw (n) = y0 + out0_bias, out0_act (n) = exp(out0_raw),
+ * out_vec (n,3) = y1..y3, out_vec_act (n,3) = sigmoid(y1..y3) when sigmoid_vec != 0.
+ */
+#define SMB_MLP_TC_MAX_LAYERS 12
+typedef struct smb_mlp_tc_layout {
+  uint32_t total_bytes;
+  uint32_t n_layers;
+  uint32_t kblocks[SMB_MLP_TC_MAX_LAYERS]; /* 64-wide K blocks of the layer's input (1 or 2) */
+  uint32_t n_out[SMB_MLP_TC_MAX_LAYERS];   /* padded N of the UMMA (16, 64 or 128) */
+  uint32_t w_off[SMB_MLP_TC_MAX_LAYERS];   /* byte offset of the K-major 128B-swizzled fp16 image */
+  uint32_t b_off[SMB_MLP_TC_MAX_LAYERS];   /* byte offset of the fp32 bias row */
+} smb_mlp_tc_layout;
+int smb_mlp_tc_layout_for(int n_layers, const int* k_in, const int* n_out, smb_mlp_tc_layout* out);
+int smb_mlp_tc_pack_host(const float* const* weights_host, const float* const* biases_host, const int* k_in,
+                         const int* n_out, const smb_mlp_tc_layout* layout, void* blob_host);
+int smb_query_points_tc(const float* planes_cl, int Hp, int Wp, int align_corners, const void* mlp_blob_dev,
+                        const smb_mlp_tc_layout* layout, float radius, float out0_bias, int sigmoid_vec,
+                        const float* positions, int64_t n, float* out0_raw, float* out0_act, float* out_vec,
+                        float* out_vec_act, void* stream);
+
 /* ------------------------------------------------------------ SF3D variant
  * Stable Fast 3D ("Pro"): StableFast/sf3d/system.py:141-198, sf3d/models/network.py:148-208,
  * sf3d/models/isosurface.py:24-229.  Planes are (3,40,Hp,Wp) (Hp=Wp=384 in the shipped config);

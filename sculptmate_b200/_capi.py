@@ -42,6 +42,17 @@ class QueryCfg(ctypes.Structure):
     ]
 
 
+class MlpTcLayout(ctypes.Structure):
+    _fields_ = [
+        ("total_bytes", c_uint32),
+        ("n_layers", c_uint32),
+        ("kblocks", c_uint32 * 12),
+        ("n_out", c_uint32 * 12),
+        ("w_off", c_uint32 * 12),
+        ("b_off", c_uint32 * 12),
+    ]
+
+
 class McCounts(ctypes.Structure):
     _fields_ = [
         ("nverts", c_int64),
@@ -101,6 +112,13 @@ SIGNATURES = {
     "smb_extract_mesh_host": (
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],
+    ),
+    "smb_mlp_tc_layout_for": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(MlpTcLayout)]),
+    "smb_mlp_tc_pack_host": (c_int, [_FLOATPP, _FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(MlpTcLayout), c_void_p]),
+    "smb_query_points_tc": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_void_p, POINTER(MlpTcLayout), c_float, c_float, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p],
     ),
     "smb_sf3d_heads_floats": (c_int, []),
     "smb_sf3d_query_f32": (

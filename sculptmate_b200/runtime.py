@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _capi
-from ._capi import DecoderLayout, McCounts, QueryCfg, check
+from ._capi import DecoderLayout, McCounts, MlpTcLayout, QueryCfg, check
 
 PLANE_CHANNELS = 40
 HIDDEN = 64
@@ -513,3 +513,91 @@ def marching_tets(
                 "smb_mtet_emit",
             )
     return verts, faces
+
+
+# ----------------------------------------------- tensor-core MLP on arbitrary positions
+@dataclass
+class MlpTcPack:
+    blob: torch.Tensor  # uint8 on the device
+    layout: MlpTcLayout
+    key: Tuple
+
+
+def _pack_mlp_tc(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], device: torch.device, key: Tuple) -> MlpTcPack:
+    ws = [w.detach().to(device="cpu", dtype=torch.float32).contiguous() for w in weights]
+    bs = [b.detach().to(device="cpu", dtype=torch.float32).contiguous() for b in biases]
+    n = len(ws)
+    k_in = (ctypes.c_int * n)(*[int(w.shape[1]) for w in ws])
+    n_out = (ctypes.c_int * n)(*[int(w.shape[0]) for w in ws])
+    lay = MlpTcLayout()
+    lib = _capi.load()
+    check(lib.smb_mlp_tc_layout_for(n, k_in, n_out, ctypes.byref(lay)), "smb_mlp_tc_layout_for")
+    blob = torch.zeros(lay.total_bytes, dtype=torch.uint8)
+    fpp = ctypes.POINTER(ctypes.c_float)
+    W = (fpp * n)(*[ctypes.cast(w.data_ptr(), fpp) for w in ws])
+    B = (fpp * n)(*[ctypes.cast(b.data_ptr(), fpp) for b in bs])
+    check(lib.smb_mlp_tc_pack_host(W, B, k_in, n_out, ctypes.byref(lay), ctypes.c_void_p(blob.data_ptr())), "smb_mlp_tc_pack_host")
+    return MlpTcPack(blob.to(device), lay, key)
+
+
+_mlp_tc_cache: Dict[Tuple, MlpTcPack] = {}
+
+
+def _param_key(params, device) -> Tuple:
+    return tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (str(device),)
+
+
+def get_tsr_points_pack(decoder: torch.nn.Module, device: torch.device) -> MlpTcPack:
+    """NeRFMLP (network_utils.py:48-79) as a tensor-core MLP for arbitrary positions."""
+    ws, bs = decoder_params(decoder)
+    key = _param_key((*ws, *bs), device)
+    hit = _mlp_tc_cache.get(("tsr", id(decoder)))
+    if hit is None or hit.key != key:
+        hit = _mlp_tc_cache[("tsr", id(decoder))] = _pack_mlp_tc(ws, bs, device, key)
+    return hit
+
+
+def get_sf3d_points_pack(decoder: torch.nn.Module, device: torch.device) -> MlpTcPack:
+    """MaterialMLP heads density + vertex_offset (network.py:158-178) fused into one 3-layer MLP:
+    [W0_d;W0_o] (128x120), blockdiag(W1_d, W1_o) (128x128), [[w2_d,0],[0,W2_o]] (4x128)."""
+    d = [m for m in decoder.heads["density"] if isinstance(m, torch.nn.Linear)]
+    o = [m for m in decoder.heads["vertex_offset"] if isinstance(m, torch.nn.Linear)]
+    if len(d) != 3 or len(o) != 3:
+        raise NotImplementedError("the CUDA path expects 2 hidden layers per head (config.yaml:50-65)")
+    params = [q for m in (*d, *o) for q in (m.weight, m.bias)]
+    key = _param_key(params, device)
+    hit = _mlp_tc_cache.get(("sf3d", id(decoder)))
+    if hit is None or hit.key != key:
+        f = lambda t: t.detach().to("cpu", torch.float32)  # noqa: E731
+        w0 = torch.cat([f(d[0].weight), f(o[0].weight)], 0)
+        b0 = torch.cat([f(d[0].bias), f(o[0].bias)], 0)
+        w1 = torch.block_diag(f(d[1].weight), f(o[1].weight))
+        b1 = torch.cat([f(d[1].bias), f(o[1].bias)], 0)
+        w2 = torch.zeros(4, 128)
+        w2[0, :64] = f(d[2].weight)[0]
+        w2[1:, 64:] = f(o[2].weight)
+        b2 = torch.cat([f(d[2].bias), f(o[2].bias)], 0)
+        hit = _mlp_tc_cache[("sf3d", id(decoder))] = _pack_mlp_tc([w0, w1, w2], [b0, b1, b2], device, key)
+    return hit
+
+
+def query_points_tc(
+    planes: ScenePlanes, pack: MlpTcPack, positions: torch.Tensor, radius: float, out0_bias: float,
+    align_corners: bool, sigmoid_vec: bool, want: Sequence[str] = ("out0_act",),
+) -> Dict[str, torch.Tensor]:
+    """Tensor-core field query at (n,3) positions.  ``want`` from {out0_raw, out0_act, vec, vec_act}."""
+    _require_cuda(positions, "positions")
+    pos = positions.detach().to(torch.float32).contiguous().view(-1, 3)
+    n, dev = pos.shape[0], pos.device
+    widths = {"out0_raw": 1, "out0_act": 1, "vec": 3, "vec_act": 3}
+    outs = {k: torch.empty((n, widths[k]), dtype=torch.float32, device=dev) for k in want}
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_query_points_tc(
+                planes.planes_cl.data_ptr(), planes.Hp, planes.Wp, int(bool(align_corners)), pack.blob.data_ptr(), ctypes.byref(pack.layout),
+                float(radius), float(out0_bias), int(bool(sigmoid_vec)), pos.data_ptr(), n, _ptr(outs.get("out0_raw")),
+                _ptr(outs.get("out0_act")), _ptr(outs.get("vec")), _ptr(outs.get("vec_act")), _stream_ptr(dev),
+            ),
+            "smb_query_points_tc",
+        )
+    return outs

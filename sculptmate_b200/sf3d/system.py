@@ -37,6 +37,7 @@ class SF3D(BaseModule):
         isosurface_threshold: float = 10.0
         radius: float = 0.87
         tets_path: str = ""
+        precision: str = "tc"  # "tc": tcgen05 kernel (fp16 operands); "fp32": CUDA-core kernel at reference precision
         decoder: dict = field(default_factory=lambda: dict(DEFAULT_DECODER_CFG))
 
     cfg: Config
@@ -78,11 +79,19 @@ class SF3D(BaseModule):
             if self.decoder.cuda_heads_supported():
                 planes = runtime.prepare_planes_cl(triplane)
                 dens_spec = self.decoder.head_spec("density")
-                dec = runtime.sf3d_query(  # query_triplane + decoder(include=[vertex_offset, density]) fused  :153-154
-                    planes, runtime.get_sf3d_heads(self.decoder, dev), float(dens_spec.out_bias), self.cfg.radius,
-                    positions=grid_vertices, want=("density_act", "vertex_offset"),
-                )
-                density, deform = dec["density_act"], dec["vertex_offset"]
+                # query_triplane + decoder(include=[vertex_offset, density]) fused into one kernel  :153-154
+                if self.cfg.precision == "tc":
+                    dec = runtime.query_points_tc(
+                        planes, runtime.get_sf3d_points_pack(self.decoder, dev), grid_vertices, self.cfg.radius,
+                        float(dens_spec.out_bias), align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"),
+                    )
+                    density, deform = dec["out0_act"], dec["vec"]
+                else:
+                    dec = runtime.sf3d_query(
+                        planes, runtime.get_sf3d_heads(self.decoder, dev), float(dens_spec.out_bias), self.cfg.radius,
+                        positions=grid_vertices, want=("density_act", "vertex_offset"),
+                    )
+                    density, deform = dec["density_act"], dec["vertex_offset"]
             else:
                 values = self.query_triplane(grid_vertices, triplane)
                 decoded = self.decoder(values, include=["vertex_offset", "density"])

@@ -35,6 +35,8 @@ class TriplaneNeRFRenderer(BaseModule):
     def configure(self) -> None:
         assert self.cfg.feature_reduction in ["concat", "mean"]
         self.chunk_size = 0
+        # "fp32": CUDA-core kernel, reference precision (default); "tc": tcgen05 kernel, fp16 operands
+        self.point_precision = "fp32"
         self._scene_key = None
         self._scene: Optional[runtime.ScenePlanes] = None
 
@@ -65,11 +67,23 @@ class TriplaneNeRFRenderer(BaseModule):
         decoder: torch.nn.Module,
         positions: torch.Tensor,
         triplane: torch.Tensor,
+        precision: Optional[str] = None,
     ) -> Dict[str, torch.Tensor]:
         self._check_supported()
         input_shape = positions.shape[:-1]
         pack, scene = self._planes(decoder, triplane)
-        out = runtime.query_points(scene, pack, positions.reshape(-1, 3), self.cfg.radius, self.cfg.density_bias)
+        precision = precision or self.point_precision
+        if precision == "tc":
+            tc = runtime.get_tsr_points_pack(decoder, triplane.device)
+            r = runtime.query_points_tc(
+                scene, tc, positions.reshape(-1, 3), self.cfg.radius, self.cfg.density_bias, align_corners=False, sigmoid_vec=True,
+                want=("out0_raw", "out0_act", "vec", "vec_act"),
+            )
+            out = {"density": r["out0_raw"] - self.cfg.density_bias, "features": r["vec"], "density_act": r["out0_act"], "color": r["vec_act"]}
+        elif precision == "fp32":
+            out = runtime.query_points(scene, pack, positions.reshape(-1, 3), self.cfg.radius, self.cfg.density_bias)
+        else:
+            raise ValueError(f"precision must be 'fp32' or 'tc', got {precision!r}")
         return {k: v.view(*input_shape, v.shape[-1]) for k, v in out.items()}
 
     def query_lattice(

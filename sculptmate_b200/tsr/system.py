@@ -110,7 +110,7 @@ class TSR(BaseModule):
             color = None
             if enable_texture:
                 with torch.no_grad():
-                    color = self.renderer.query_triplane(self.decoder, v_pos, scene_code)["color"]
+                    color = self.renderer.query_triplane(self.decoder, v_pos, scene_code, precision="tc")["color"]
                 color = color.cpu().numpy()
             self.import_obj_blender(v_pos.cpu().numpy(), t_pos_idx.cpu().numpy(), color, name=mesh_name)
 

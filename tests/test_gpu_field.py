@@ -164,3 +164,26 @@ def test_full_size_256_sampled_planes(golden):
         assert d.max().item() <= TC_MAX_ABS and d.mean().item() <= TC_MEAN_ABS
         assert (full[x0 : x0 + 2] / a32 - 1).abs().max().item() <= TC_MAX_REL
     assert torch.equal(runtime.query_lattice(scene, pack, ax, R, RADIUS, -1.0), full)
+
+
+@pytest.mark.parametrize("name", ["field_small.npz", "field_64.npz"])
+def test_query_points_tensor_core_vs_reference_golden(golden, name):
+    """tcgen05 points kernel (fp16 operands, fp32 accumulate, tanh.approx) vs the reference's fp32
+    outputs at arbitrary positions, incl. border / out-of-range positions (zero padding)."""
+    g = golden(name)
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda() if "triplane" in g.files else _triplane64(g).cuda()
+    pos = torch.from_numpy(g["positions"]).cuda()
+    out = m.renderer.query_triplane(m.decoder, pos, tp, precision="tc")
+    ref32 = m.renderer.query_triplane(m.decoder, pos, tp, precision="fp32")
+    for k in ("density", "features", "density_act", "color"):
+        assert out[k].shape == g[k].shape and out[k].dtype == torch.float32
+    assert np.abs(out["density"].cpu().numpy() - g["density"]).max() < TC_MAX_ABS
+    assert np.abs(out["density"].cpu().numpy() - g["density"]).mean() < 10 * TC_MEAN_ABS
+    assert np.abs(out["features"].cpu().numpy() - g["features"]).max() < TC_MAX_ABS
+    assert np.abs(out["density_act"].cpu().numpy() / g["density_act"] - 1).max() < TC_MAX_REL
+    assert np.abs(out["color"].cpu().numpy() - g["color"]).max() < 5e-3
+    assert torch.equal(m.renderer.query_triplane(m.decoder, pos, tp, precision="tc")["density"], out["density"])  # deterministic
+    assert (out["density"] - ref32["density"]).abs().max() < TC_MAX_ABS
+    ragged = m.renderer.query_triplane(m.decoder, pos[:131], tp, precision="tc")  # one full tile + 3 rows
+    assert torch.equal(ragged["density"], out["density"][:131])

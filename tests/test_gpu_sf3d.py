@@ -25,10 +25,11 @@ def tets_dir(tmp_path_factory):
     return str(d)
 
 
-def _model(g, tets_dir, n, thr):
+def _model(g, tets_dir, n, thr, precision="fp32"):
     from sculptmate_b200.sf3d import SF3D
 
-    m = SF3D(dict(isosurface_resolution=n, isosurface_threshold=thr, radius=RADIUS, tets_path=os.path.join(tets_dir, f"tets{n}.npz")))
+    m = SF3D(dict(isosurface_resolution=n, isosurface_threshold=thr, radius=RADIUS, precision=precision,
+                  tets_path=os.path.join(tets_dir, f"tets{n}.npz")))
     m.decoder.load_state_dict(_sd(g))
     return m.cuda()
 
@@ -114,3 +115,28 @@ def test_larger_grid_properties(tets_dir):
     # empty surface: no vertices, no faces, no exception (the reference returns empty tensors)
     none = h(torch.ones_like(sdf), None)
     assert none.v_pos.shape == (0, 3) and none.t_pos_idx.shape == (0, 3)
+
+
+def test_tensor_core_query_vs_fp32_and_mesh(golden, tets_dir):
+    """precision="tc" (tcgen05, fp16 operands): density / offsets within the stated tolerance of the
+    fp32 path, and the mesh it yields is the oracle's mesh for the level it produced."""
+    from sculptmate_b200 import runtime
+
+    g = golden("sf3d_path.npz")
+    n = int(g["n"])
+    m = _model(g, tets_dir, n, float(g["threshold"]), precision="tc")
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    pos = torch.from_numpy(g["positions"]).cuda()
+    planes = runtime.prepare_planes_cl(tp)
+    r = runtime.query_points_tc(planes, runtime.get_sf3d_points_pack(m.decoder, pos.device), pos, RADIUS, -1.0,
+                                align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"))
+    assert np.abs(r["out0_act"].cpu().numpy() / g["density"][0] - 1).max() < 2e-2  # stated fp16-operand tolerance
+    assert np.abs(r["vec"].cpu().numpy() - g["vertex_offset"][0]).max() < 2e-2
+    mesh = m.triplane_to_meshes(tp[None])[0]
+    level = mesh.extras["grid_level"].cpu().numpy().reshape(-1)
+    assert (np.sign(level) != np.sign(g["grid_level"].reshape(-1))).mean() < 2e-2
+    _, tets = kuhn_tet_grid(n)
+    v, f = so.marching_tets(mesh.extras["grid_vertices"].cpu().numpy(), level, tets)
+    np.testing.assert_array_equal(mesh.t_pos_idx.cpu().numpy(), f)
+    v = (v * np.float32(2 * RADIUS) + np.float32(-RADIUS)).astype(np.float32)
+    np.testing.assert_array_equal(mesh.v_pos.cpu().numpy(), v)
