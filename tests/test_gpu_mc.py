@@ -142,3 +142,18 @@ def test_speculative_extract_equals_two_phase_incl_overflow():
         v2, f2 = runtime.mc_emit(p2, flags=3, vdiv=float(R - 1))
         assert (pend.nverts, pend.ntris) == (p2.nverts, p2.ntris) == (v.shape[0], f.shape[0])
         assert torch.equal(v, v2) and torch.equal(f, f2), radius
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 5, 33), (7, 4, 65), (40, 70, 31), (5, 300, 9)])
+def test_ragged_and_minimum_shapes_bit_exact(shape):
+    """Non-cubic slabs, rows that are not a multiple of the 32-sample word, planes larger than one
+    2048-word chunk, and the 2x2x2 minimum -- all bit-exact against the oracle."""
+    rng = np.random.RandomState(sum(shape))
+    g = rng.randn(*shape).astype(np.float32)
+    for a in range(3):  # a little smoothing so that surfaces are not pure noise
+        g = (g + np.roll(g, 1, a)) * 0.5
+    v_ref, f_ref, _ = _oracle_mc(g, np.float32(0.05), 1.0)
+    v, f, pend = _gpu_mc(g, 0.05, 1.0)
+    assert pend.nverts == len(v_ref) and pend.ntris == len(f_ref)
+    np.testing.assert_array_equal(v, v_ref)
+    np.testing.assert_array_equal(f, f_ref)
