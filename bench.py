@@ -243,7 +243,7 @@ def run_sf3d(args) -> int:
         print(json.dumps({
             "metric": "sf3d_triplane_to_meshes_grid_vertices_per_s", "value": nv * world / (ms * 1e-3), "unit": "pts/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (query + heads); f32 / int32 marching tets", "data": "synthetic",
             "config": {"workload": f"SF3D triplane_to_meshes (BASELINE configs[4]): 3x40x384x384 triplane, MaterialMLP density+vertex_offset heads, "
                                    f"marching tets on a Kuhn grid n={n} (Nv={nv}, Nt={int(h.indices.shape[0])}); reference blob 160_tets.npz missing",
                        "parallelism": f"dp{world}", "l2": "inputs rotated + 256 MiB L2 flush between steps"},

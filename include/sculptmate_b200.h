@@ -101,6 +101,11 @@ int smb_query_points_f32(const float* planes_cl, const void* decoder_blob, const
                          const smb_query_cfg* cfg, const float* positions, int64_t n, float* density,
                          float* features, float* density_act, float* color, void* stream);
 
+/* NeRFMLP.forward (network_utils.py:116-124) on pre-computed features (n,120): density (n) = out[...,0],
+ * features (n,3) = out[...,1:4]; fp32, either output may be NULL. */
+int smb_decoder_forward_f32(const void* decoder_blob, const smb_decoder_layout* layout, const float* features_in,
+                            int64_t n, float* density, float* features, void* stream);
+
 /* Lattice query = the density half of TSR.extract_mesh (tsr/system.py:171-184):
  * evaluates density_act on x-planes [x_begin, x_begin+nx) of the R^3 lattice
  * (row (i*R+j)*R+k = (x_i,y_j,z_k), isosurface.py:25-39) without materialising

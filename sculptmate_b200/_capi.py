@@ -75,6 +75,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "smb_decoder_forward_f32": (c_int, [c_void_p, POINTER(DecoderLayout), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "smb_lattice_axis_host": (c_int, [c_int, c_float, POINTER(c_float)]),
     "smb_query_lattice_tc": (
         c_int,

@@ -63,6 +63,7 @@ struct F32Params {
   PosScale ps;
   // arbitrary positions
   const float* positions;  // (n,3) or nullptr for lattice mode
+  const float* features_in;  // (n,120): run the decoder on given features (NeRFMLP.forward) instead of gathering
   long long n;
   // lattice mode
   const float* axis_u;
@@ -107,8 +108,9 @@ __global__ void __launch_bounds__(kThreads) query_f32_kernel(F32Params p) {
   const long long RR = (long long)p.R * p.R;
   for (long long s = blockIdx.x * (long long)kThreads + threadIdx.x; s < p.n;
        s += (long long)gridDim.x * kThreads) {
-    float ux, uy, uz;
-    if (p.positions) {
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (p.features_in) {
+    } else if (p.positions) {
       ux = scale_pos(p.positions[3 * s + 0], p.ps);
       uy = scale_pos(p.positions[3 * s + 1], p.ps);
       uz = scale_pos(p.positions[3 * s + 2], p.ps);
@@ -124,10 +126,22 @@ __global__ void __launch_bounds__(kThreads) query_f32_kernel(F32Params p) {
     float nxt[kHid];
     {
       float f[kFeat];
-      const long long psz = (long long)p.H * p.W * kCp;
-      gather_plane(p.planes_cl + 0 * psz, p.H, p.W, p.align_corners, ux, uy, f + 0 * kCp);
-      gather_plane(p.planes_cl + 1 * psz, p.H, p.W, p.align_corners, ux, uz, f + 1 * kCp);
-      gather_plane(p.planes_cl + 2 * psz, p.H, p.W, p.align_corners, uy, uz, f + 2 * kCp);
+      if (p.features_in) {
+        const float4* src = reinterpret_cast<const float4*>(p.features_in + s * kFeat);
+#pragma unroll
+        for (int k4 = 0; k4 < kFeat / 4; ++k4) {
+          const float4 q = __ldg(src + k4);
+          f[4 * k4 + 0] = q.x;
+          f[4 * k4 + 1] = q.y;
+          f[4 * k4 + 2] = q.z;
+          f[4 * k4 + 3] = q.w;
+        }
+      } else {
+        const long long psz = (long long)p.H * p.W * kCp;
+        gather_plane(p.planes_cl + 0 * psz, p.H, p.W, p.align_corners, ux, uy, f + 0 * kCp);
+        gather_plane(p.planes_cl + 1 * psz, p.H, p.W, p.align_corners, ux, uz, f + 1 * kCp);
+        gather_plane(p.planes_cl + 2 * psz, p.H, p.W, p.align_corners, uy, uz, f + 2 * kCp);
+      }
       const float* W = sw;
       const float* b = sw + kHid * kFeat;
       for (int n = 0; n < kHid; ++n) {
@@ -309,5 +323,22 @@ extern "C" int smb_query_lattice_f32(const float* planes_cl, const void* decoder
   p.x_begin = x_begin;
   p.density = out_density;
   p.density_act = out_density_act;
+  return launch_f32(p, (cudaStream_t)stream);
+}
+
+// NeRFMLP.forward (network_utils.py:116-124) on pre-computed features: (n,120) -> density (n), features (n,3)
+extern "C" int smb_decoder_forward_f32(const void* decoder_blob, const smb_decoder_layout* layout, const float* features_in,
+                                       int64_t n, float* density, float* features, void* stream) {
+  if (!decoder_blob || !layout || n < 0 || (!density && !features)) return SMB_ERR_BAD_ARG;
+  if (n == 0) return SMB_OK;
+  if (!features_in) return SMB_ERR_BAD_ARG;
+  F32Params p{};
+  p.wts = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_f32);
+  p.n_hidden = (int)layout->n_hidden;
+  p.features_in = features_in;
+  p.n = n;
+  p.R = 1;
+  p.density = density;
+  p.features = features;
   return launch_f32(p, (cudaStream_t)stream);
 }

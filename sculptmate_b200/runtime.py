@@ -168,6 +168,18 @@ def query_points(
     return outs
 
 
+def decoder_forward(pack: DecoderPack, features: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """NeRFMLP.forward on (n,120) features -> {"density": (n,1), "features": (n,3)} (fp32 CUDA kernel)."""
+    _require_cuda(features, "x")
+    x = features.detach().to(torch.float32).contiguous().view(-1, 3 * PLANE_CHANNELS)
+    n, dev = x.shape[0], x.device
+    d = torch.empty((n, 1), dtype=torch.float32, device=dev)
+    f = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_capi.load().smb_decoder_forward_f32(pack.blob.data_ptr(), ctypes.byref(pack.layout), x.data_ptr(), n, d.data_ptr(), f.data_ptr(), _stream_ptr(dev)), "smb_decoder_forward_f32")
+    return {"density": d, "features": f}
+
+
 def lattice_axis(resolution: int, radius: float, points_range=(0, 1), device=None) -> torch.Tensor:
     """Per-axis lattice coordinate mapped to (-1,1) with the reference's own torch ops:
     linspace (isosurface.py:30-32) -> scale_tensor (system.py:177-181) -> scale_tensor

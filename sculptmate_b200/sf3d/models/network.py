@@ -125,6 +125,8 @@ class MaterialMLP(BaseModule):
             if "vertex_offset" in fused:
                 out["vertex_offset"] = res["vertex_offset"].view(*lead, 3)
         for head in heads:
-            if head.name not in out:  # heads outside the mesh path (texture / material): eager
+            if head.name not in out:  # heads outside the mesh path (texture / material): torch ops on the GPU
+                if not x.is_cuda:
+                    raise RuntimeError("sculptmate_b200: MaterialMLP needs CUDA tensors; the B200 path has no CPU fallback")
                 out[head.name] = get_activation(head.output_activation)(self.heads[head.name](x) + head.out_bias)
         return {h.name: out[h.name] for h in heads}

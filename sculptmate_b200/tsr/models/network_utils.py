@@ -3,8 +3,8 @@
 Parameter container with the reference's state-dict keys
 (``layers.{0,2,...}.{weight,bias}``) so checkpoints load unchanged.  On the hot path
 the renderer never calls ``forward``: it hands these parameters to the fused CUDA
-kernels (``runtime.get_decoder_pack``).  ``forward`` on pre-computed features keeps
-the reference's eager semantics for callers outside the fused path.
+kernels (``runtime.get_decoder_pack``).  ``forward`` on pre-computed features runs the
+decoder in the CUDA library too (fp32 kernel); there is no CPU path.
 """
 from __future__ import annotations
 
@@ -60,6 +60,8 @@ class NeRFMLP(BaseModule):
         raise NotImplementedError
 
     def forward(self, x):
+        from ... import runtime
+
         lead = x.shape[:-1]
-        y = self.layers(x.reshape(-1, x.shape[-1])).reshape(*lead, -1)
-        return {"density": y[..., 0:1], "features": y[..., 1:4]}
+        out = runtime.decoder_forward(runtime.get_decoder_pack(self, x.device), x.reshape(-1, x.shape[-1]))
+        return {"density": out["density"].view(*lead, 1), "features": out["features"].view(*lead, 3)}

@@ -187,3 +187,19 @@ def test_query_points_tensor_core_vs_reference_golden(golden, name):
     assert (out["density"] - ref32["density"]).abs().max() < TC_MAX_ABS
     ragged = m.renderer.query_triplane(m.decoder, pos[:131], tp, precision="tc")  # one full tile + 3 rows
     assert torch.equal(ragged["density"], out["density"][:131])
+
+
+def test_nerfmlp_forward_on_features(golden):
+    """NeRFMLP.forward (network_utils.py:116-124) on pre-computed features runs in the CUDA library."""
+    from oracle import field_oracle as fo
+
+    g = golden("field_small.npz")
+    m = _model(g)
+    ws, bs = golden_decoder(g)
+    rng = np.random.RandomState(0)
+    x = rng.randn(3, 70, 120).astype(np.float32)
+    out = m.decoder(torch.from_numpy(x).cuda())
+    ref = fo.nerf_mlp(x.reshape(-1, 120), ws, bs)
+    assert out["density"].shape == (3, 70, 1) and out["features"].shape == (3, 70, 3)
+    assert np.abs(out["density"].cpu().numpy().reshape(-1, 1) - ref["density"]).max() < 2e-5
+    assert np.abs(out["features"].cpu().numpy().reshape(-1, 3) - ref["features"]).max() < 2e-5
