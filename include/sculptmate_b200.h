@@ -231,7 +231,10 @@ typedef struct smb_mlp_tc_layout {
 int smb_mlp_tc_layout_for(int n_layers, const int* k_in, const int* n_out, smb_mlp_tc_layout* out);
 int smb_mlp_tc_pack_host(const float* const* weights_host, const float* const* biases_host, const int* k_in,
                          const int* n_out, const smb_mlp_tc_layout* layout, void* blob_host);
-int smb_query_points_tc(const float* planes_cl, int Hp, int Wp, int align_corners, const void* mlp_blob_dev,
+/* planes_cl: channels-last (3,Hp,Wp,40) planes, fp32 (smb_scene_prepare) or -- planes_fp16 != 0 -- fp16
+ * (smb_scene_prepare_half): half the gather traffic, which bounds this kernel; taps are blended in fp32. */
+int smb_scene_prepare_half(const float* triplane, int Hp, int Wp, void* planes_cl_half, void* stream);
+int smb_query_points_tc(const void* planes_cl, int planes_fp16, int Hp, int Wp, int align_corners, const void* mlp_blob_dev,
                         const smb_mlp_tc_layout* layout, float radius, float out0_bias, int sigmoid_vec,
                         const float* positions, int64_t n, float* out0_raw, float* out0_act, float* out_vec,
                         float* out_vec_act, void* stream);

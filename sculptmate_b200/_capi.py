@@ -116,9 +116,10 @@ SIGNATURES = {
     ),
     "smb_mlp_tc_layout_for": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(MlpTcLayout)]),
     "smb_mlp_tc_pack_host": (c_int, [_FLOATPP, _FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(MlpTcLayout), c_void_p]),
+    "smb_scene_prepare_half": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "smb_query_points_tc": (
         c_int,
-        [c_void_p, c_int, c_int, c_int, c_void_p, POINTER(MlpTcLayout), c_float, c_float, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(MlpTcLayout), c_float, c_float, c_int, c_void_p, c_int64, c_void_p, c_void_p,
          c_void_p, c_void_p, c_void_p],
     ),
     "smb_sf3d_heads_floats": (c_int, []),

@@ -27,7 +27,8 @@ constexpr int kPtsWG = 4;
 constexpr int kABlock = kPtsTile * 64 * 2;  // one 64-wide K block of the A tile: 16 KB
 
 struct PtsTcParams {
-  const float* planes_cl;  // (3,H,W,40) fp32
+  const void* planes_cl;  // (3,H,W,40) fp32, or fp16 when planes_fp16
+  int planes_fp16;
   int H, W, align_corners;
   PosScale ps;
   const unsigned char* blob;  // device copy of the packed MLP
@@ -61,6 +62,35 @@ __device__ __forceinline__ void gather_to_a(const float* __restrict__ plane, int
     const uint32_t q3 = pack_half2(a1.z * w00 + b1.z * w01 + c1.z * w10 + d1.z * w11, a1.w * w00 + b1.w * w01 + c1.w * w10 + d1.w * w11);
     const int idx = 5 * plane_idx + q;  // 16-byte chunk index along K
     *reinterpret_cast<uint4*>(a_rowp + (idx >> 3) * kABlock + (((idx & 7) ^ (m & 7)) << 4)) = make_uint4(q0, q1, q2, q3);
+  }
+}
+
+// same from fp16 channels-last planes: half the L2 traffic and half the load instructions of the
+// gather (which bounds this kernel); taps are widened to fp32, blended in fp32, rounded once
+__device__ __forceinline__ void gather_to_a_h(const __half* __restrict__ plane, int H, int W, int align, float u, float v,
+                                              unsigned char* __restrict__ a_rowp, int m, int plane_idx) {
+  Tap2 tx = make_tap(u, W, align);
+  Tap2 ty = make_tap(v, H, align);
+  const uint4* p00 = reinterpret_cast<const uint4*>(plane + ((long long)ty.i0 * W + tx.i0) * kCp);
+  const uint4* p01 = reinterpret_cast<const uint4*>(plane + ((long long)ty.i0 * W + tx.i1) * kCp);
+  const uint4* p10 = reinterpret_cast<const uint4*>(plane + ((long long)ty.i1 * W + tx.i0) * kCp);
+  const uint4* p11 = reinterpret_cast<const uint4*>(plane + ((long long)ty.i1 * W + tx.i1) * kCp);
+  const float w00 = ty.w0 * tx.w0, w01 = ty.w0 * tx.w1, w10 = ty.w1 * tx.w0, w11 = ty.w1 * tx.w1;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const uint4 a = __ldg(p00 + q), b = __ldg(p01 + q), c = __ldg(p10 + q), d = __ldg(p11 + q);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&av[e]));
+      const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bv[e]));
+      const float2 fc = __half22float2(*reinterpret_cast<const __half2*>(&cv[e]));
+      const float2 fd = __half22float2(*reinterpret_cast<const __half2*>(&dv[e]));
+      o[e] = pack_half2(fa.x * w00 + fb.x * w01 + fc.x * w10 + fd.x * w11, fa.y * w00 + fb.y * w01 + fc.y * w10 + fd.y * w11);
+    }
+    const int idx = 5 * plane_idx + q;
+    *reinterpret_cast<uint4*>(a_rowp + (idx >> 3) * kABlock + (((idx & 7) ^ (m & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -115,9 +145,17 @@ __global__ void __launch_bounds__(kPtsWG * 128, 1) points_tc_kernel(PtsTcParams 
       const float ux = scale_pos(p.positions[3 * s + 0], p.ps);
       const float uy = scale_pos(p.positions[3 * s + 1], p.ps);
       const float uz = scale_pos(p.positions[3 * s + 2], p.ps);
-      gather_to_a(p.planes_cl + 0 * psz, p.H, p.W, p.align_corners, ux, uy, a_rowp, m, 0);  // (x,y)
-      gather_to_a(p.planes_cl + 1 * psz, p.H, p.W, p.align_corners, ux, uz, a_rowp, m, 1);  // (x,z)
-      gather_to_a(p.planes_cl + 2 * psz, p.H, p.W, p.align_corners, uy, uz, a_rowp, m, 2);  // (y,z)
+      if (p.planes_fp16) {
+        const __half* pl = static_cast<const __half*>(p.planes_cl);
+        gather_to_a_h(pl + 0 * psz, p.H, p.W, p.align_corners, ux, uy, a_rowp, m, 0);  // (x,y)
+        gather_to_a_h(pl + 1 * psz, p.H, p.W, p.align_corners, ux, uz, a_rowp, m, 1);  // (x,z)
+        gather_to_a_h(pl + 2 * psz, p.H, p.W, p.align_corners, uy, uz, a_rowp, m, 2);  // (y,z)
+      } else {
+        const float* pl = static_cast<const float*>(p.planes_cl);
+        gather_to_a(pl + 0 * psz, p.H, p.W, p.align_corners, ux, uy, a_rowp, m, 0);  // (x,y)
+        gather_to_a(pl + 1 * psz, p.H, p.W, p.align_corners, ux, uz, a_rowp, m, 1);  // (x,z)
+        gather_to_a(pl + 2 * psz, p.H, p.W, p.align_corners, uy, uz, a_rowp, m, 2);  // (y,z)
+      }
       *reinterpret_cast<uint4*>(a_rowp + kABlock + ((7 ^ (m & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);  // k = 120..127
     }
     if (!weights_ready) {
@@ -246,7 +284,26 @@ extern "C" int smb_mlp_tc_pack_host(const float* const* W, const float* const* B
   return SMB_OK;
 }
 
-extern "C" int smb_query_points_tc(const float* planes_cl, int Hp, int Wp, int align_corners, const void* mlp_blob_dev,
+// NCHW fp32 (3,Cp,H,W) -> channels-last fp16 (3,H,W,Cp)
+__global__ void planes_to_channels_last_half(const float* __restrict__ src, __half* __restrict__ dst, int H, int W) {
+  const int HW = H * W;
+  const long long total = 3LL * HW * smb::kCp;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % smb::kCp);
+    const long long r = t / smb::kCp;
+    const int hw = (int)(r % HW);
+    const int pl = (int)(r / HW);
+    dst[t] = __float2half_rn(src[((long long)pl * smb::kCp + c) * HW + hw]);
+  }
+}
+
+extern "C" int smb_scene_prepare_half(const float* triplane, int Hp, int Wp, void* planes_cl_half, void* stream) {
+  if (!triplane || !planes_cl_half || Hp <= 0 || Wp <= 0) return SMB_ERR_BAD_ARG;
+  planes_to_channels_last_half<<<1184, 256, 0, (cudaStream_t)stream>>>(triplane, static_cast<__half*>(planes_cl_half), Hp, Wp);
+  return smb_check(cudaGetLastError());
+}
+
+extern "C" int smb_query_points_tc(const void* planes_cl, int planes_fp16, int Hp, int Wp, int align_corners, const void* mlp_blob_dev,
                                    const smb_mlp_tc_layout* layout, float radius, float out0_bias, int sigmoid_vec,
                                    const float* positions, int64_t n, float* out0_raw, float* out0_act, float* out_vec,
                                    float* out_vec_act, void* stream) {
@@ -256,6 +313,7 @@ extern "C" int smb_query_points_tc(const float* planes_cl, int Hp, int Wp, int a
   if (layout->n_layers < 2 || layout->n_layers > SMB_MLP_TC_MAX_LAYERS || layout->kblocks[0] != 2) return SMB_ERR_BAD_ARG;
   PtsTcParams p{};
   p.planes_cl = planes_cl;
+  p.planes_fp16 = planes_fp16;
   p.H = Hp;
   p.W = Wp;
   p.align_corners = align_corners;

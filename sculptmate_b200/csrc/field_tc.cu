@@ -63,7 +63,7 @@ struct TcParams {
   float* out_act;
   float* out_raw;
   int wait_ns;  // suspend-time hint of the consumer mbarrier waits (0: plain try_wait polling)
-  int dbg;  // developer timing experiments only (SMB_TC_DEBUG); 0 in production
+  int dbg;  // 1: developer timeline instrumentation (SMB_TC_TRACE); 0 in production
 };
 
 __host__ __device__ inline int tc_weight_bytes(int n_hidden) {
@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t atom_inc_acq_rel(uint32_t addr) {
   return old;
 }
 
-// developer instrumentation (kDbg & 256): clock64 stamps of block 0 / warpgroup 0
+// developer instrumentation (kTrace, SMB_TC_TRACE=1): clock64 stamps of block 0 / warpgroup 0
 __device__ long long g_trace[4 * 512 * 4];
 
 struct TileGeom {  // what producer and consumer both derive from a tile index
@@ -106,7 +106,7 @@ __device__ __forceinline__ TileGeom tile_geom(long long t, int tiles_per_line, c
   return g;
 }
 
-template <int kWG, int kDbg>
+template <int kWG, bool kTrace>
 __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
   constexpr int kSlots = kWG * kSlotsPerWG;
   constexpr int kConsumerWarps = kWG * 4;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 64);
 #pragma unroll
             for (int kc = 0; kc < kHid / 16; ++kc)  // K = 16 per instruction: +32 B along the swizzled row
-              if (!(kDbg & 4)) umma_f16_ss(d_tmem, a_desc + 2 * kc, b_desc + 2 * kc, idesc, kc > 0 ? 1u : 0u);
+              umma_f16_ss(d_tmem, a_desc + 2 * kc, b_desc + 2 * kc, idesc, kc > 0 ? 1u : 0u);
             umma_commit(smem_u32(&bars[3 + 4 * slot]));
           }
           __syncwarp();
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
           const uint32_t tmem_acc = d_tmem + ((uint32_t)(q * 32) << 16);
           const int k0 = s ? g1.k0 : g0.k0;
           long long tr0 = 0, tr1 = 0, tr2 = 0;
-          if (kDbg & 256) tr0 = clock64();
+          if (kTrace) tr0 = clock64();
 
           if (l == 0) {
             // ---- layer 0 from the producer's table --------------------------------
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
               const float h1 = c.y + w0 * a.y + w1 * b.y;
               const float h2 = c.z + w0 * a.z + w1 * b.z;
               const float h3 = c.w + w0 * a.w + w1 * b.w;
-              pk[2 * (g4 & 1) + 0] = (kDbg & 128) ? pack_half2(h0, h1) : pack_half2(silu_from_half_arg(h0), silu_from_half_arg(h1));
-              pk[2 * (g4 & 1) + 1] = (kDbg & 128) ? pack_half2(h2, h3) : pack_half2(silu_from_half_arg(h2), silu_from_half_arg(h3));
+              pk[2 * (g4 & 1) + 0] = pack_half2(silu_from_half_arg(h0), silu_from_half_arg(h1));
+              pk[2 * (g4 & 1) + 1] = pack_half2(silu_from_half_arg(h2), silu_from_half_arg(h3));
               if (g4 & 1) {
                 const int c8 = g4 >> 1;
                 *reinterpret_cast<uint4*>(a_rowp + ((c8 ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -337,24 +337,24 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
             mbar_wait_sleep(smem_u32(&bars[3 + 4 * slot]), (par_acc >> s) & 1u, (uint32_t)p.wait_ns);
             par_acc ^= 1u << s;
             tc_fence_after();
-            if (kDbg & 256) tr1 = clock64();
+            if (kTrace) tr1 = clock64();
             if (l < nh) {
               // ---- hidden layer l: bias + SiLU, next A tile -------------------------
               // 4 chunks of 16 accumulator columns; the TMEM load and the bias row of chunk
               // c+1 are in flight while chunk c goes through bias + SiLU + pack.
               const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
-              uint32_t r[2][16] = {};
+              uint32_t r[2][16];
               float4 bb[2][4];
-              if (!(kDbg & 64)) tmem_ld16(tmem_acc, r[0]);
+              tmem_ld16(tmem_acc, r[0]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) bb[0][i] = bl[i];
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 tmem_ld_wait();
                 if (c + 1 < 4) {
-                  if (!(kDbg & 64)) tmem_ld16(tmem_acc + (c + 1) * 16, r[(c + 1) & 1]);
+                  tmem_ld16(tmem_acc + (c + 1) * 16, r[(c + 1) & 1]);
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = (kDbg & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : bl[(c + 1) * 4 + i];
+                  for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = bl[(c + 1) * 4 + i];
                 }
                 const uint32_t* rc = r[c & 1];
                 const float4* bc = bb[c & 1];
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
                 }
                 float t[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = (kDbg & 1) ? 0.5f * h[i] : tanh_approx(h[i]);
+                for (int i = 0; i < 16; ++i) t[i] = tanh_approx(h[i]);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) h[i] = fmaf(h[i], t[i], h[i]);
 #pragma unroll
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
                   const uint32_t q2 = pack_half2(h[8 * hc + 4], h[8 * hc + 5]);
                   const uint32_t q3 = pack_half2(h[8 * hc + 6], h[8 * hc + 7]);
                   const int chunk = 2 * c + hc;
-                  if (!(kDbg & 2)) *reinterpret_cast<uint4*>(a_rowp + ((chunk ^ (m & 7)) << 4)) = make_uint4(q0, q1, q2, q3);
+                  *reinterpret_cast<uint4*>(a_rowp + ((chunk ^ (m & 7)) << 4)) = make_uint4(q0, q1, q2, q3);
                 }
               }
             } else {
@@ -396,16 +396,16 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
             }
           }
 
-          if (kDbg & 256) tr2 = clock64();
+          if (kTrace) tr2 = clock64();
           if (l < nh) {
             // publish this thread's row of the next A tile: generic-proxy stores -> async proxy,
             // TMEM reads ordered before the MMA that will overwrite the accumulator
-            if (!(kDbg & 16)) fence_proxy_async_smem();
+            fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars[4 + 4 * slot]));
           }
-          if ((kDbg & 256) && blockIdx.x == 0 && wg == 0 && lane == 0) {
+          if (kTrace && blockIdx.x == 0 && wg == 0 && lane == 0) {
             const long long ev = (n * (nh + 1) + l) * 2 + s;
             if (ev < 512) {
               long long* o = g_trace + ((long long)q * 512 + ev) * 4;
@@ -425,18 +425,18 @@ __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
   if (wid == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int kWG, int kDbg>
+template <int kWG, bool kTrace>
 static int launch_tc(const TcParams& p, int sms, cudaStream_t st) {
   const int wbytes = tc_weight_bytes(p.n_hidden);
   const int kSlots = kWG * kSlotsPerWG;
   const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (size_t)kSlots * p.slot_bytes + 8 * (1 + 4 * kSlots) + 16;
   if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
-  cudaError_t e = cudaFuncSetAttribute(lattice_tc_kernel<kWG, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(lattice_tc_kernel<kWG, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SMB_ERR_CUDA;
   const long long ntiles = (long long)p.nx * p.R * ((p.R + kTileM - 1) / kTileM);
   long long grid = (ntiles + kSlots - 1) / kSlots;
   if (grid > sms) grid = sms;
-  lattice_tc_kernel<kWG, kDbg><<<(unsigned)grid, kWG * 192, smem, st>>>(p);
+  lattice_tc_kernel<kWG, kTrace><<<(unsigned)grid, kWG * 192, smem, st>>>(p);
   return smb_check(cudaGetLastError());
 }
 
@@ -490,7 +490,7 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   p.out_act = out_density_act;
   p.out_raw = out_density;
   {
-    const char* e = getenv("SMB_TC_DEBUG");
+    const char* e = getenv("SMB_TC_TRACE");
     p.dbg = e ? atoi(e) : 0;
     e = getenv("SMB_TC_WAITNS");
     p.wait_ns = e ? atoi(e) : 2000;
@@ -498,24 +498,17 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   // as many consumer warpgroups (2 slots each) as shared memory allows
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  switch (p.dbg) {  // developer timing experiments (results are garbage for dbg != 0)
-    case 1: rc = launch_tc<3, 1>(p, sms, st); break;
-    case 4: rc = launch_tc<3, 4>(p, sms, st); break;
-    case 15: rc = launch_tc<3, 15>(p, sms, st); break;
-    case 31: rc = launch_tc<3, 31>(p, sms, st); break;
-    case 47: rc = launch_tc<3, 47>(p, sms, st); break;
-    case 79: rc = launch_tc<3, 79>(p, sms, st); break;
-    case 143: rc = launch_tc<3, 143>(p, sms, st); break;
-    case 256: rc = launch_tc<3, 256>(p, sms, st); break;
-    default:
-      rc = launch_tc<3, 0>(p, sms, st);
-      if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<2, 0>(p, sms, st);
-      if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<1, 0>(p, sms, st);
+  if (p.dbg) {  // SMB_TC_TRACE=1: developer timeline instrumentation (tools/trace_lattice.py)
+    rc = launch_tc<3, true>(p, sms, st);
+  } else {
+    rc = launch_tc<3, false>(p, sms, st);
+    if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<2, false>(p, sms, st);
+    if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<1, false>(p, sms, st);
   }
   return rc;
 }
 
-// developer instrumentation: copies the clock64 trace of the last SMB_TC_DEBUG=256 launch
+// developer instrumentation: copies the clock64 trace of the last SMB_TC_TRACE=1 launch
 extern "C" int smb_debug_read_trace(long long* host, int n) {
   if (!host || n <= 0 || n > 4 * 512 * 4) return SMB_ERR_BAD_ARG;
   return smb_check(cudaMemcpyFromSymbol(host, smb::g_trace, sizeof(long long) * n));

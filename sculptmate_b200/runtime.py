@@ -113,6 +113,7 @@ class ScenePlanes:
     planes_q: Optional[torch.Tensor]  # (3,H,W,64) fp32
     Hp: int
     Wp: int
+    planes_h: Optional[torch.Tensor] = None  # (3,H,W,40) fp16, for the tensor-core points kernel
 
 
 def prepare_scene(triplane: torch.Tensor, pack: DecoderPack, want_cl: bool = True, want_q: bool = True) -> ScenePlanes:
@@ -401,6 +402,19 @@ def raise_for_empty_surface(grid: torch.Tensor, sub: float, sign: float) -> None
 
 
 # ------------------------------------------------------------------- SF3D
+def prepare_planes_half(triplane: torch.Tensor) -> ScenePlanes:
+    """Channels-last fp16 copy of a (3,40,Hp,Wp) triplane for the tensor-core points kernel."""
+    _require_cuda(triplane, "triplane")
+    if triplane.dim() != 4 or triplane.shape[0] != 3 or triplane.shape[1] != PLANE_CHANNELS:
+        raise NotImplementedError(f"triplane must be (3,{PLANE_CHANNELS},Hp,Wp); got {tuple(triplane.shape)}")
+    tp = triplane.detach().to(torch.float32).contiguous()
+    _, _, Hp, Wp = tp.shape
+    ph = torch.empty((3, Hp, Wp, PLANE_CHANNELS), dtype=torch.float16, device=tp.device)
+    with torch.cuda.device(tp.device):
+        check(_capi.load().smb_scene_prepare_half(tp.data_ptr(), Hp, Wp, ph.data_ptr(), _stream_ptr(tp.device)), "smb_scene_prepare_half")
+    return ScenePlanes(None, None, Hp, Wp, planes_h=ph)
+
+
 def prepare_planes_cl(triplane: torch.Tensor) -> ScenePlanes:
     """Channels-last copy of a (3,40,Hp,Wp) triplane (no decoder needed)."""
     _require_cuda(triplane, "triplane")
@@ -603,10 +617,11 @@ def query_points_tc(
     n, dev = pos.shape[0], pos.device
     widths = {"out0_raw": 1, "out0_act": 1, "vec": 3, "vec_act": 3}
     outs = {k: torch.empty((n, widths[k]), dtype=torch.float32, device=dev) for k in want}
+    half = planes.planes_h is not None
     with torch.cuda.device(dev):
         check(
             _capi.load().smb_query_points_tc(
-                planes.planes_cl.data_ptr(), planes.Hp, planes.Wp, int(bool(align_corners)), pack.blob.data_ptr(), ctypes.byref(pack.layout),
+                (planes.planes_h if half else planes.planes_cl).data_ptr(), int(half), planes.Hp, planes.Wp, int(bool(align_corners)), pack.blob.data_ptr(), ctypes.byref(pack.layout),
                 float(radius), float(out0_bias), int(bool(sigmoid_vec)), pos.data_ptr(), n, _ptr(outs.get("out0_raw")),
                 _ptr(outs.get("out0_act")), _ptr(outs.get("vec")), _ptr(outs.get("vec_act")), _stream_ptr(dev),
             ),

@@ -77,10 +77,11 @@ class SF3D(BaseModule):
             dev = triplane.device
             grid_vertices = self._positions(dev)  # scale_tensor(grid, points_range, bbox)   :147-151
             if self.decoder.cuda_heads_supported():
-                planes = runtime.prepare_planes_cl(triplane)
+                tc = self.cfg.precision == "tc"
+                planes = runtime.prepare_planes_half(triplane) if tc else runtime.prepare_planes_cl(triplane)
                 dens_spec = self.decoder.head_spec("density")
                 # query_triplane + decoder(include=[vertex_offset, density]) fused into one kernel  :153-154
-                if self.cfg.precision == "tc":
+                if tc:
                     dec = runtime.query_points_tc(
                         planes, runtime.get_sf3d_points_pack(self.decoder, dev), grid_vertices, self.cfg.radius,
                         float(dens_spec.out_bias), align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"),

@@ -132,6 +132,10 @@ def test_tensor_core_query_vs_fp32_and_mesh(golden, tets_dir):
                                 align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"))
     assert np.abs(r["out0_act"].cpu().numpy() / g["density"][0] - 1).max() < 2e-2  # stated fp16-operand tolerance
     assert np.abs(r["vec"].cpu().numpy() - g["vertex_offset"][0]).max() < 2e-2
+    rh = runtime.query_points_tc(runtime.prepare_planes_half(tp), runtime.get_sf3d_points_pack(m.decoder, pos.device), pos, RADIUS, -1.0,
+                                 align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"))  # fp16 planes (the default of "tc")
+    assert np.abs(rh["out0_act"].cpu().numpy() / g["density"][0] - 1).max() < 2e-2
+    assert np.abs(rh["vec"].cpu().numpy() - g["vertex_offset"][0]).max() < 2e-2
     mesh = m.triplane_to_meshes(tp[None])[0]
     level = mesh.extras["grid_level"].cpu().numpy().reshape(-1)
     assert (np.sign(level) != np.sign(g["grid_level"].reshape(-1))).mean() < 2e-2

@@ -88,3 +88,22 @@ def test_kuhn_grid_is_a_valid_partition():
     p = v[t].astype(np.float64)
     vol = np.abs(np.einsum("ij,ij->i", p[:, 1] - p[:, 0], np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 0]))) / 6
     assert np.allclose(vol.sum(), 1.0) and np.allclose(vol, vol[0])  # 6n^3 congruent tets tile the unit cube
+
+
+def test_static_topology_of_the_mirror_helper(tmp_path, golden):
+    """MarchingTetrahedraHelper.topology (host-side, torch ops): the int32 edge list is the
+    reference's all_edges and tet_edges indexes each tet's six base edges into it."""
+    from sculptmate_b200.sf3d import MarchingTetrahedraHelper, save_tet_grid
+
+    g = golden("sf3d_mtet.npz")
+    n = int(g["n"])
+    h = MarchingTetrahedraHelper(n, save_tet_grid(str(tmp_path / "t.npz"), n))
+    np.testing.assert_array_equal(h.all_edges.numpy(), g["all_edges"])
+    edges, tets, tet_edges = h.topology(torch.device("cpu"))
+    assert edges.dtype == tets.dtype == tet_edges.dtype == torch.int32 and tet_edges.shape == (tets.shape[0], 6)
+    e, t, te = edges.numpy(), tets.numpy(), tet_edges.numpy()
+    pairs = np.sort(t[:, so.BASE_TET_EDGES].reshape(-1, 2), axis=1)
+    np.testing.assert_array_equal(e[te.reshape(-1)], pairs)
+    assert h.normalize_grid_deformation(torch.zeros(3, 3)).abs().max() == 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        h(torch.zeros(h.grid_vertices.shape[0], 1), None)  # forward needs the CUDA library

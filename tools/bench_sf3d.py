@@ -47,10 +47,11 @@ for i in range(iters + 2):
     if i >= 2:
         ts.append(a.elapsed_time(e)); tq.append(a.elapsed_time(b)); tm.append(c.elapsed_time(e))
 print(f"sf3d (fp32 query) triplane_to_mesh n={n}: total {np.median(ts):.3f} ms  (query+heads {np.median(tq):.3f} ms, marching tets {np.median(tm):.3f} ms)  V={mesh.v_pos.shape[0]} F={mesh.t_pos_idx.shape[0]}")
-# tensor-core query
+# tensor-core query: fp32 planes, then fp16 planes
 tcp = runtime.get_sf3d_points_pack(m.decoder, dev)
-tq = []
-for i in range(iters + 2):
+for label, planes in (("fp32 planes", runtime.prepare_planes_cl(tp)), ("fp16 planes", runtime.prepare_planes_half(tp))):
+  tq = []
+  for i in range(iters + 2):
     a, b = ev(), ev()
     a.record()
     r = runtime.query_points_tc(planes, tcp, pos, 0.87, -1.0, align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"))
@@ -58,6 +59,6 @@ for i in range(iters + 2):
     torch.cuda.synchronize()
     if i >= 2:
         tq.append(a.elapsed_time(b))
-rel = float((r["out0_act"] / dec["density_act"] - 1).abs().max())
-print(f"sf3d tensor-core query n={n}: {np.median(tq):.3f} ms for {pos.shape[0]} points ({pos.shape[0] / np.median(tq) / 1e6:.2f} Gpts/s); density max rel diff vs fp32 {rel:.2e}; "
-      f"offset max abs diff {float((r['vec'] - dec['vertex_offset']).abs().max()):.2e}")
+  rel = float((r["out0_act"] / dec["density_act"] - 1).abs().max())
+  print(f"sf3d tensor-core query ({label}) n={n}: {np.median(tq):.3f} ms for {pos.shape[0]} points ({pos.shape[0] / np.median(tq) / 1e6:.2f} Gpts/s); density max rel diff vs fp32 {rel:.2e}; "
+        f"offset max abs diff {float((r['vec'] - dec['vertex_offset']).abs().max()):.2e}")

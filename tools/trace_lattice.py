@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Developer tool: per-step clock64 timeline of block 0 / warpgroup 0 of the lattice kernel
-(SMB_TC_DEBUG=256 build variant).  python tools/trace_lattice.py [R]"""
+(SMB_TC_TRACE=1 kernel variant).  python tools/trace_lattice.py [R]"""
 import ctypes, os, sys
 import numpy as np
 import torch
-os.environ["SMB_TC_DEBUG"] = "256"
+os.environ["SMB_TC_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import baked_triplane
