@@ -121,6 +121,18 @@ def test_capi_host_extractor_matches_python_path(golden):
         v = np.ctypeslib.as_array(vp, shape=(nv.value, 3)).copy()
         f = np.ctypeslib.as_array(fp_, shape=(nt.value, 3)).copy()
         assert np.array_equal(f, f2.cpu().numpy()) and np.array_equal(v, v2.cpu().numpy())
+        # a larger lattice: the first call takes the single-pass path, the following ones the slab pipeline
+        # (x-slabs, each copied to the host while the next is computed); all must be the same mesh
+        Rb = 72
+        axis = np.ascontiguousarray(runtime.lattice_axis(Rb, RADIUS).numpy())
+        assert lib.smb_extractor_set_axis(ex, Rb, axis.ctypes.data_as(fpp)) == 0
+        vb, fb = m.extract_mesh_tensors(torch.from_numpy(tp).cuda(), Rb, thr)
+        for _ in range(3):
+            rc = lib.smb_extract_mesh_host(ex, tp.ctypes.data_as(fpp), Rb, thr, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
+            assert rc == 0
+            v = np.ctypeslib.as_array(vp, shape=(nv.value, 3)).copy()
+            f = np.ctypeslib.as_array(fp_, shape=(nt.value, 3)).copy()
+            assert np.array_equal(f, fb.cpu().numpy()) and np.array_equal(v, vb.cpu().numpy())
         rc = lib.smb_extract_mesh_host(ex, tp.ctypes.data_as(fpp), R, 1e9, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
         assert rc == _capi.ERR_LEVEL_RANGE
     finally:
