@@ -38,73 +38,12 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "field_common.cuh"
-#include "ptx_sm100.cuh"
+#include "field_tc_common.cuh"
 
 namespace smb {
 
-constexpr int kTileM = 128;
-constexpr int kTRowsMax = 66;  // Hp + 2 zero borders for Hp = 64
-constexpr int kTPitch = 68;    // floats per T row: 64 + 4 pad (adjacent rows land 4 banks apart)
-constexpr int kWBytes = kHid * kHid * 2;     // 8192: one hidden layer, fp16
-constexpr int kWFinalBytes = 16 * kHid * 2;  // 2048: head padded to N=16
-constexpr int kABytes = kTileM * kHid * 2;   // 16384
-constexpr int kSlotsPerWG = 2;
-
-struct TcParams {
-  const float* planes_q;  // (3,H,W,64) fp32
-  const unsigned char* tc_weights;  // blob + off_tc_hidden: hidden images, head image, biases (contiguous)
-  const float* bias0_half;          // b0/2 (64)
-  const float* axis_u;
-  int R, x_begin, nx, H, W, align_corners, n_hidden;
-  int trows;       // rows of a slot's T table
-  int slot_bytes;  // 1024-aligned: A | T | c
-  float density_bias;
-  float* out_act;
-  float* out_raw;
-  int wait_ns;  // suspend-time hint of the consumer mbarrier waits (0: plain try_wait polling)
-  int dbg;  // 1: developer timeline instrumentation (SMB_TC_TRACE); 0 in production
-};
-
-__host__ __device__ inline int tc_weight_bytes(int n_hidden) {
-  // the blob keeps [hidden | head | bias_half (n_hidden x 64) | bias_final (4)] contiguous
-  return (n_hidden - 1) * kWBytes + kWFinalBytes + n_hidden * kHid * 4 + 16;
-}
-__host__ __device__ inline int tc_slot_bytes(int trows) {
-  return ((kABytes + trows * kTPitch * 4 + kHid * 4 + 1023) / 1024) * 1024;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t atom_inc_acq_rel(uint32_t addr) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
-  return old;
-}
-
 // developer instrumentation (kTrace, SMB_TC_TRACE=1): clock64 stamps of block 0 / warpgroup 0
 __device__ long long g_trace[4 * 512 * 4];
-
-struct TileGeom {  // what producer and consumer both derive from a tile index
-  long long line;  // (i*R + j)
-  int i, j, k0, nvalid, hlo, nrow;
-};
-
-__device__ __forceinline__ TileGeom tile_geom(long long t, int tiles_per_line, const TcParams& p) {
-  TileGeom g;
-  const int seg = (int)(t % tiles_per_line);
-  g.line = t / tiles_per_line;
-  g.i = (int)(g.line / p.R);
-  g.j = (int)(g.line - (long long)g.i * p.R);
-  g.k0 = seg * kTileM;
-  g.nvalid = min(kTileM, p.R - g.k0);
-  const float fz_first = unnormalize(p.axis_u[g.k0], p.H, p.align_corners);
-  const float fz_last = unnormalize(p.axis_u[g.k0 + g.nvalid - 1], p.H, p.align_corners);
-  g.hlo = (int)floorf(fz_first);
-  g.nrow = min((int)floorf(fz_last) + 1 - g.hlo + 1, p.trows);
-  return g;
-}
 
 template <int kWG, bool kTrace>
 __global__ void __launch_bounds__(kWG * 192, 1) lattice_tc_kernel(TcParams p) {
@@ -498,6 +437,12 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   // as many consumer warpgroups (2 slots each) as shared memory allows
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  // default: activations-in-TMEM kernel (field_tc_ta.cu); SMB_TC_VARIANT=smem selects this file's
+  // shared-memory-A kernel (kept for comparison and as the home of the timeline instrumentation)
+  {
+    const char* v = getenv("SMB_TC_VARIANT");
+    if (!p.dbg && !(v && v[0] == 's')) return launch_tc_ta(p, sms, st);
+  }
   if (p.dbg) {  // SMB_TC_TRACE=1: developer timeline instrumentation (tools/trace_lattice.py)
     rc = launch_tc<3, true>(p, sms, st);
   } else {
