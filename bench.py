@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 RADIUS = 0.87
 FLOP_PER_POINT = 2 * (120 * 64 + 8 * 64 * 64 + 64 * 4)  # 81408: the reference's NeRFMLP (all 4 outputs), SURVEY 8d
-KERNELS_PER_STEP = 6  # project_planes, lattice_tc_kernel, mc_classify, mc_scan_chunks, mc_scan_totals, mc_emit
+KERNELS_PER_STEP = 6  # project_planes, lattice_tc_ta_kernel, mc_signs, mc_count, mc_totals, mc_emit
 
 
 def baked_triplane(seed: int, H: int = 64, W: int = 64, noise: float = 0.05) -> torch.Tensor:
@@ -433,7 +433,7 @@ def main() -> int:
                 with open(tpath) as fh:
                     traffic = json.load(fh).get(f"lattice_tc_kernel_R{R}")
             line["roofline"] = {
-                "kernel": "lattice_tc_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "kernel": "lattice_tc_ta_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": f"{peak_kind} (burst)",
                 "kernel_ms": kern_ms_avg, "query_points_per_s": float(R) ** 3 / (kern_ms_avg * 1e-3),
                 "flop_per_point": FLOP_PER_POINT,
