@@ -1,5 +1,8 @@
 // Fused lattice field kernel for sm_100a: triplane interpolation + NeRFMLP chain
-// on tcgen05 tensor cores with TMEM accumulators.  This is the density half of
+// on tcgen05 tensor cores with TMEM accumulators -- the variant with the activation (A) tile in
+// SHARED memory.  The default is field_tc_ta.cu (activations in tensor memory, 14 % faster); this
+// kernel stays as SMB_TC_VARIANT=smem, as the comparison point of DESIGN.md and as the home of the
+// timeline instrumentation (SMB_TC_TRACE=1, tools/trace_lattice.py).  This is the density half of
 // TSR.extract_mesh (/root/reference/TripoSR/tsr/system.py:171-184), i.e.
 // query_triplane (tsr/models/nerf_renderer.py:41-91) + NeRFMLP.forward
 // (tsr/models/network_utils.py:116-124) evaluated on the R^3 lattice of

@@ -444,7 +444,7 @@ __device__ __forceinline__ void locate_item(uint32_t idx, const uint32_t* __rest
   src = lo;
 }
 
-__global__ void __launch_bounds__(kEmitWarps * 32) mc_emit(EmitParams p) {
+__global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
   __shared__ signed char s_tri[256][16];
   __shared__ unsigned char s_ntri[256];
   __shared__ unsigned short s_emask[256];
