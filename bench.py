@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 RADIUS = 0.87
 FLOP_PER_POINT = 2 * (120 * 64 + 8 * 64 * 64 + 64 * 4)  # 81408: the reference's NeRFMLP (all 4 outputs), SURVEY 8d
-KERNELS_PER_STEP = 6  # project_planes, lattice_tc_ta_kernel, mc_signs, mc_count, mc_totals, mc_emit
+KERNELS_PER_STEP = 5  # project_planes, lattice_tc_ta_kernel (also ballots the MC sign masks), mc_count, mc_totals, mc_emit
 
 
 def baked_triplane(seed: int, H: int = 64, W: int = 64, noise: float = 0.05) -> torch.Tensor:
@@ -334,10 +334,11 @@ def main() -> int:
             scene = runtime.prepare_scene(tp, pack, want_cl=False, want_q=True)
             if b == 0:
                 k0.record()
-            dens = runtime.query_lattice(scene, pack, axis, R, RADIUS, -1.0)
+            dens = runtime.query_lattice(scene, pack, axis, R, RADIUS, -1.0, mc_signs=(thr, 1.0))  # case bits balloted in-kernel
             if b == 0:
                 k1.record()
-            v, f, _ = runtime.mc_extract(dens, sub=thr, sign=1.0, flags=7, vdiv=float(R - 1.0), vmul=float(RADIUS - (-RADIUS)), vadd=float(-RADIUS))
+            v, f, _ = runtime.mc_extract(dens, sub=thr, sign=1.0, flags=7, vdiv=float(R - 1.0), vmul=float(RADIUS - (-RADIUS)), vadd=float(-RADIUS),
+                                         presigned=True)
         e1.record()
         if record is not None:
             record.append((e0, e1, k0, k1))
@@ -444,7 +445,7 @@ def main() -> int:
             # SURVEY 8d; the time spans signs + count + totals + emit (+ the read-back of the sizes)
             mc_bytes = 4.0 * float(R) ** 3 + 12.0 * nV + 24.0 * nF
             line["roofline_mc"] = {
-                "kernels": "mc_signs+mc_count+mc_totals+mc_emit (emit launched behind count; the sizes are read back after it)", "bound": "hbm",
+                "kernels": "mc_count+mc_totals+mc_emit (sign masks come from the lattice kernel; emit launched behind count; the sizes are read back after it)", "bound": "hbm",
                 "achieved": mc_bytes / (mc_ms_avg * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": mc_bytes / (mc_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": mc_ms_avg, "algorithmic_bytes": mc_bytes,
                 "peak_source": peak_kind,

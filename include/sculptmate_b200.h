@@ -63,7 +63,10 @@ typedef struct smb_decoder_layout {
   uint32_t off_bias_final; /* 4 fp32 (padded to 16 B) */
   uint32_t off_w0_half;    /* 64 x 120 fp32: W_0/2 (plane projection for the lattice kernel) */
   uint32_t off_f32;        /* plain fp32 copy: for each layer W (out,in) then b (out) */
-  uint32_t reserved[7];
+  uint32_t off_tc_biasblk; /* (n_hidden-1) x 8192 B: per hidden layer l=1.. a [64 x 64] fp16 K-block in the same image format whose
+                              K rows 0/1 hold b_l/2 split as fp16 hi + lo (rest zero): the bias enters the accumulator through one
+                              extra K=16 MMA against a constant (1,1,0,..) activation block instead of 64 FADDs per sample */
+  uint32_t reserved[6];
 } smb_decoder_layout;
 
 int smb_decoder_layout_for(int n_hidden, smb_decoder_layout* out);
@@ -126,6 +129,16 @@ int smb_query_lattice_tc(const float* planes_q, const void* decoder_blob, const 
 int smb_query_lattice_f32(const float* planes_cl, const void* decoder_blob, const smb_decoder_layout* layout,
                           const smb_query_cfg* cfg, const float* axis_u, int R, int x_begin, int nx,
                           float* out_density_act, float* out_density, void* stream);
+/* smb_query_lattice_tc that also leaves the marching-cubes sign masks of the slab it evaluates in
+ * mc_workspace (a workspace of smb_mc_workspace_bytes(nx, R, R)): bit k%32 of word (i*R + j)*ceil(R/32) + k/32
+ * = ((density_act - sub) * sign > 0), the case bit of tsr/system.py:184 + isosurface.py:45-46 with
+ * sub = threshold, sign = 1.  The warp that holds 32 consecutive z-samples ballots them while they are still in
+ * registers, so the marching-cubes pass (smb_mc_count_presigned) never re-reads the 4 R^3-byte density grid to
+ * classify it. */
+int smb_query_lattice_tc_signs(const float* planes_q, const void* decoder_blob, const smb_decoder_layout* layout,
+                               const smb_query_cfg* cfg, const float* axis_u, int R, int x_begin, int nx,
+                               float* out_density_act, float* out_density, float sub, float sign,
+                               void* mc_workspace, size_t mc_workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------- marching cubes
  * Replaces MarchingCubeHelper.forward (tsr/models/isosurface.py:41-54), i.e.
@@ -150,6 +163,10 @@ size_t smb_mc_workspace_bytes(int nx, int ny, int nz);
 /* counts_dev: device smb_mc_counts written by the stream; copy it back to size the outputs. */
 int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub, float sign, int emit_last_plane,
                  void* workspace, size_t workspace_bytes, smb_mc_counts* counts_dev, void* stream);
+/* smb_mc_count for a workspace whose sign masks were already written by smb_query_lattice_tc_signs with the
+ * same (nx, ny, nz, sub, sign): count + scan only. */
+int smb_mc_count_presigned(int nx, int ny, int nz, int emit_last_plane, void* workspace, size_t workspace_bytes,
+                           smb_mc_counts* counts_dev, void* stream);
 /* Must follow smb_mc_count on the same grid/workspace.  vertex_id_offset is added to
  * every face index (running vertex count of the lower slabs); x_origin is the global
  * index of the slab's first plane.  verts (nverts,3) fp32, faces (ntris,3) int64. */

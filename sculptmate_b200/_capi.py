@@ -28,7 +28,8 @@ class DecoderLayout(ctypes.Structure):
         ("off_bias_final", c_uint32),
         ("off_w0_half", c_uint32),
         ("off_f32", c_uint32),
-        ("reserved", c_uint32 * 7),
+        ("off_tc_biasblk", c_uint32),
+        ("reserved", c_uint32 * 6),
     ]
 
 
@@ -81,6 +82,12 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     ),
+    "smb_query_lattice_tc_signs": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float,
+         c_void_p, c_size_t, c_void_p],
+    ),
+    "smb_mc_count_presigned": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "smb_query_lattice_f32": (
         c_int,
         [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -64,6 +64,9 @@ extern "C" int smb_decoder_layout_for(int n_hidden, smb_decoder_layout* out) {
   off += (kHid * kFeat + kHid) * 4u;
   off += (uint32_t)(n_hidden - 1) * (kHid * kHid + kHid) * 4u;
   off += (kOut * kHid + kOut) * 4u;
+  off = (off + 1023u) & ~1023u;
+  out->off_tc_biasblk = off;
+  off += (uint32_t)(n_hidden - 1) * 8192u;
   out->total_bytes = align16(off);
   return SMB_OK;
 }
@@ -85,6 +88,16 @@ extern "C" int smb_decoder_pack_host(const float* const* W, const float* const* 
     unsigned char* img = blob + L->off_tc_hidden + (size_t)(l - 1) * 8192;
     for (int n = 0; n < kHid; ++n)
       for (int k = 0; k < kHid; ++k) put_half(img, sw128_offset(n, k), 0.5f * W[l][n * kHid + k]);
+  }
+  // bias K-blocks of the hidden layers: b_l/2 = hi + lo in fp16 at K rows 0 and 1
+  for (int l = 1; l < n_hidden; ++l) {
+    unsigned char* img = blob + L->off_tc_biasblk + (size_t)(l - 1) * 8192;
+    for (int n = 0; n < kHid; ++n) {
+      const float b = 0.5f * B[l][n];
+      const __half hi = __float2half_rn(b);
+      put_half(img, sw128_offset(n, 0), __half2float(hi));
+      put_half(img, sw128_offset(n, 1), b - __half2float(hi));
+    }
   }
   {  // head: rows 0..3 = W_L (not halved: no SiLU after it), rows 4..15 zero
     unsigned char* img = blob + L->off_tc_final;
@@ -186,7 +199,10 @@ struct smb_extractor {
   smb_mc_counts* slab_counts_pin = nullptr; // kSlabs
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slab_done[kSlabs] = {};
-  int n_slabs = 2;  // measured on B200 at 256^3: 2-3 slabs 4.42 ms, 1 (off) 4.71 ms, >= 4 slower and noisier (per-slab launch + host event cost)
+  int n_slabs = 3;  // equal slabs, measured on B200 at 256^3: 2-3 slabs 4.42 ms, 1 (off) 4.71 ms, >= 4 slower and noisier (per-slab launch + host event cost)
+  // slab k holds a share ~ slab_ratio^k of the cell layers: only the LAST slab's copy is exposed, and the copy of
+  // slab k (PCIe, ~1/3 of its compute time) still hides behind the compute of the smaller slab k+1
+  double slab_ratio = 0.45;
 };
 
 #define EX_CUDA(call)                        \
@@ -239,6 +255,10 @@ extern "C" int smb_extractor_create(const float* const* W, const float* const* B
   if (const char* e = getenv("SMB_PIPE_SLABS")) {  // tuning knob: 0/1 disables the slab pipeline
     const int v = atoi(e);
     ex->n_slabs = v < 0 ? 0 : (v > smb_extractor::kSlabs ? smb_extractor::kSlabs : v);
+  }
+  if (const char* e = getenv("SMB_PIPE_RATIO")) {  // tuning knob: 1 = equal slabs
+    const double v = atof(e);
+    if (v > 0.05 && v <= 1.0) ex->slab_ratio = v;
   }
   *out = ex;
   return SMB_OK;
@@ -315,15 +335,33 @@ static int extract_pipelined(smb_extractor* ex, int R, float threshold, int64_t*
   const double r = (double)ex->cfg.radius;
   const int flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE;
   const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
-  const int cells = R - 1, base = cells / S, extra = cells % S;
+  // geometric slab sizes (at least 8 cell layers each), first slab largest
+  const int cells = R - 1;
+  int bounds[smb_extractor::kSlabs + 1];
+  {
+    double wsum = 0.0, w = 1.0;
+    for (int k = 0; k < S; ++k, w *= ex->slab_ratio) wsum += w;
+    double acc = 0.0;
+    w = 1.0;
+    bounds[0] = 0;
+    for (int k = 0; k < S; ++k, w *= ex->slab_ratio) {
+      acc += w;
+      int b = (int)(cells * (acc / wsum) + 0.5);
+      if (b < bounds[k] + 8) b = bounds[k] + 8;
+      if (b > cells - 8 * (S - 1 - k)) b = cells - 8 * (S - 1 - k);
+      bounds[k + 1] = b;
+    }
+    bounds[S] = cells;
+  }
   int a = 0;
   for (int k = 0; k < S; ++k) {
-    const int b = a + base + (k < extra ? 1 : 0);
+    const int b = bounds[k + 1];
     const int nx = b - a + 1, last = k == S - 1;
-    int rc = smb_query_lattice_tc(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, a, nx, ex->density, nullptr, st);
+    int rc = smb_query_lattice_tc_signs(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, a, nx, ex->density, nullptr,
+                                        threshold, 1.0f, ex->mc_ws, ex->mc_ws_bytes, st);
     if (rc != SMB_OK) return rc;
     smb_mc_counts* cnt = reinterpret_cast<smb_mc_counts*>(ex->slab_counts_dev + 4 * k);
-    rc = smb_mc_count(ex->density, nx, R, R, threshold, 1.0f, last, ex->mc_ws, ex->mc_ws_bytes, cnt, st);
+    rc = smb_mc_count_presigned(nx, R, R, last, ex->mc_ws, ex->mc_ws_bytes, cnt, st);
     if (rc != SMB_OK) return rc;
     EX_CUDA(cudaMemcpyAsync(&ex->slab_counts_pin[k], cnt, sizeof(smb_mc_counts), cudaMemcpyDeviceToHost, st));
     rc = smb_mc_emit_gather(ex->density, nx, R, R, threshold, 1.0f, a, last, flags, vdiv, vmul, vadd, ex->mc_ws, ex->slab_counts_dev, k,
@@ -373,11 +411,12 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
     *faces_host = ex->faces_pin;
     return SMB_OK;
   }
-  rc = smb_query_lattice_tc(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, 0, R, ex->density,
-                            nullptr, st);
+  // system.py:184  helper(-(density - threshold))  ->  level = density - threshold, iso 0; the case bits are
+  // balloted by the lattice kernel
+  rc = smb_query_lattice_tc_signs(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, 0, R, ex->density,
+                                  nullptr, threshold, 1.0f, ex->mc_ws, ex->mc_ws_bytes, st);
   if (rc != SMB_OK) return rc;
-  // system.py:184  helper(-(density - threshold))  ->  level = density - threshold, iso 0
-  rc = smb_mc_count(ex->density, R, R, R, threshold, 1.0f, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
+  rc = smb_mc_count_presigned(R, R, R, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
   if (rc != SMB_OK) return rc;
   // isosurface.py:52-53 (flip, /(R-1)) and system.py:185-189 (scale to +-radius)
   const double r = (double)ex->cfg.radius;

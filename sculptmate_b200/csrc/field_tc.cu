@@ -386,10 +386,11 @@ static int launch_tc(const TcParams& p, int sms, cudaStream_t st) {
 
 using namespace smb;
 
-extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_blob,
-                                    const smb_decoder_layout* layout, const smb_query_cfg* cfg,
-                                    const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
-                                    float* out_density, void* stream) {
+static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob,
+                                 const smb_decoder_layout* layout, const smb_query_cfg* cfg,
+                                 const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
+                                 float* out_density, bool want_signs, float sub, float sign, void* mc_workspace,
+                                 size_t mc_workspace_bytes, void* stream) {
   if (!planes_q || !decoder_blob || !layout || !cfg || !axis_u || !out_density_act) return SMB_ERR_BAD_ARG;
   if (R < 2 || nx < 0 || x_begin < 0 || x_begin + nx > R) return SMB_ERR_BAD_ARG;
   if (nx == 0) return SMB_OK;
@@ -417,6 +418,7 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
   TcParams p{};
   p.planes_q = planes_q;
   p.tc_weights = static_cast<const unsigned char*>(decoder_blob) + layout->off_tc_hidden;
+  p.tc_biasblk = static_cast<const unsigned char*>(decoder_blob) + layout->off_tc_biasblk;
   p.bias0_half = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_bias_half);
   p.axis_u = axis_u;
   p.R = R;
@@ -436,16 +438,28 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
     p.dbg = e ? atoi(e) : 0;
     e = getenv("SMB_TC_WAITNS");
     p.wait_ns = e ? atoi(e) : 2000;
+    e = getenv("SMB_TC_TA_STAGGER");
+    p.stagger_clk = e ? atoi(e) : 0;
+    e = getenv("SMB_TC_TA_TOKENS");
+    p.xu_tokens = e ? atoi(e) : 0;
   }
   // as many consumer warpgroups (2 slots each) as shared memory allows
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  if (want_signs) {
+    if (!mc_workspace || smb_mc_workspace_bytes(nx, R, R) > mc_workspace_bytes) return SMB_ERR_WORKSPACE;
+    p.sign_out = static_cast<uint32_t*>(mc_workspace);  // the sign masks are the first region of an MC workspace
+    p.sign_sub = sub;
+    p.sign_mul = sign;
+    p.sign_wz = (R + 31) / 32;
+  }
   // default: activations-in-TMEM kernel (field_tc_ta.cu); SMB_TC_VARIANT=smem selects this file's
   // shared-memory-A kernel (kept for comparison and as the home of the timeline instrumentation)
   {
     const char* v = getenv("SMB_TC_VARIANT");
     if (!p.dbg && !(v && v[0] == 's')) return launch_tc_ta(p, sms, st);
   }
+  p.sign_out = nullptr;  // the shared-memory-A kernel does not ballot: stand-alone sign pass below
   if (p.dbg) {  // SMB_TC_TRACE=1: developer timeline instrumentation (tools/trace_lattice.py)
     rc = launch_tc<3, true>(p, sms, st);
   } else {
@@ -453,7 +467,26 @@ extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_b
     if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<2, false>(p, sms, st);
     if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<1, false>(p, sms, st);
   }
+  if (rc == SMB_OK && want_signs) rc = launch_mc_signs(out_density_act, nx, R, R, sub, sign, mc_workspace, mc_workspace_bytes, st);
   return rc;
+}
+
+extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_blob,
+                                    const smb_decoder_layout* layout, const smb_query_cfg* cfg,
+                                    const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
+                                    float* out_density, void* stream) {
+  return query_lattice_tc_impl(planes_q, decoder_blob, layout, cfg, axis_u, R, x_begin, nx, out_density_act, out_density, false, 0.f,
+                               1.f, nullptr, 0, stream);
+}
+
+extern "C" int smb_query_lattice_tc_signs(const float* planes_q, const void* decoder_blob,
+                                          const smb_decoder_layout* layout, const smb_query_cfg* cfg,
+                                          const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
+                                          float* out_density, float sub, float sign, void* mc_workspace,
+                                          size_t mc_workspace_bytes, void* stream) {
+  if (!mc_workspace) return SMB_ERR_BAD_ARG;
+  return query_lattice_tc_impl(planes_q, decoder_blob, layout, cfg, axis_u, R, x_begin, nx, out_density_act, out_density, true, sub,
+                               sign, mc_workspace, mc_workspace_bytes, stream);
 }
 
 // developer instrumentation: copies the clock64 trace of the last SMB_TC_TRACE=1 launch

@@ -19,6 +19,7 @@ constexpr int kSlotsPerWG = 2;
 struct TcParams {
   const float* planes_q;  // (3,H,W,64) fp32
   const unsigned char* tc_weights;  // blob + off_tc_hidden: hidden images, head image, biases (contiguous)
+  const unsigned char* tc_biasblk;  // blob + off_tc_biasblk: (n_hidden-1) bias K-block images
   const float* bias0_half;          // b0/2 (64)
   const float* axis_u;
   int R, x_begin, nx, H, W, align_corners, n_hidden;
@@ -28,6 +29,11 @@ struct TcParams {
   float* out_act;
   float* out_raw;
   int wait_ns;  // suspend-time hint of the consumer mbarrier waits (0: plain try_wait polling)
+  uint32_t* sign_out;  // optional: marching-cubes sign masks of the slab (word = line * sign_wz + k/32)
+  float sign_sub, sign_mul;
+  int sign_wz;
+  int stagger_clk;  // field_tc_ta: warpgroup g starts its first tile g*stagger_clk clocks late (breaks the SFU convoy)
+  int xu_tokens;    // field_tc_ta: > 0 = at most this many warps per SM sub-partition inside an activation stretch
   int dbg;  // 1: developer timeline instrumentation (SMB_TC_TRACE); 0 in production
 };
 
@@ -71,5 +77,8 @@ __device__ __forceinline__ TileGeom tile_geom(long long t, int tiles_per_line, c
 
 // field_tc_ta.cu: the activations-in-TMEM variant
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st);
+// mcubes.cu: sign masks of a density slab (the stand-alone pass the fused path replaces) / where they live
+int launch_mc_signs(const float* grid, int nx, int ny, int nz, float sub, float sign, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st);
 
 }  // namespace smb

@@ -13,6 +13,15 @@
 //     columns); a warpgroup's MMA latency is covered by the other three.
 //   * 4 producer warps (one per warpgroup) build the layer-0 tables (T, c) one tile ahead, as in
 //     field_tc.cu (measured at 256^3: 1 producer 4.69 ms, 2: 2.90 ms, 4: 2.85 ms).
+//   * kBiasMMA: the bias of a hidden layer enters the accumulator through a fifth K=16 MMA -- a
+//     constant activation block (1, 1, 0, ...) in TMEM against a weight block whose K rows 0/1 hold
+//     b_l/2 as fp16 hi + lo -- instead of 16 LDS.128 + 64 FADD per sample and layer in the epilogue.
+//   * kPoly: kPoly of every 16 activations take their tanh from an FMA-pipe polynomial (silu_poly
+//     below, tools/fit_tanh_poly.py) -- the software-exponential trick of FlashAttention-4 applied to
+//     SiLU: SFU demand drops by kPoly/16 at the price of 10 more instructions per such activation.
+//   Both are OFF by default: measured on B200 they are slower (see launch_tc_ta and DESIGN.md 4/K1 --
+//   the kernel is bound by the latency each warp exposes between its SFU ops, not by SFU throughput,
+//   so added instructions cost more than the SFU slots they free).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -21,7 +30,31 @@
 
 namespace smb {
 
-constexpr int kTaColsPerWG = 96;  // 64 accumulator + 32 activation columns
+constexpr int kTaColsPerWG = 128;  // 64 accumulator + 32 activation + 8 constant (bias) columns, padded
+
+// silu(2h) = h + |h| tanh(|h|) with tanh(|h|) ~= hc q(hc^2), hc = min(|h|, 4): degree-8 polynomial in hc^2,
+// max abs error of tanh 1.0e-3 (MUFU.TANH: 5e-4; the result is rounded to fp16 = 5e-4 relative anyway).
+// 1 FMNMX + 2 FMUL + 9 FFMA, no MUFU.  Coefficients: `python tools/fit_tanh_poly.py 4.0 8`.
+__device__ __forceinline__ float silu_poly(float h) {
+  const float a = fabsf(h);
+  const float hc = fminf(a, 4.0f);
+  const float u = hc * hc;
+  float q = 7.428608762e-09f;
+  q = fmaf(q, u, -5.504116545e-07f);
+  q = fmaf(q, u, 1.724979285e-05f);
+  q = fmaf(q, u, -2.989478161e-04f);
+  q = fmaf(q, u, 3.156803466e-03f);
+  q = fmaf(q, u, -2.129765012e-02f);
+  q = fmaf(q, u, 9.570061363e-02f);
+  q = fmaf(q, u, -3.115132217e-01f);
+  q = fmaf(q, u, 9.962177177e-01f);
+  return fmaf(a, hc * q, h);
+}
+// activation i of a 16-column chunk: kPoly of the 16 go to the FMA pipe
+template <int kPoly>
+__device__ __forceinline__ float silu_mix(float h, int i) {
+  return (((i * kPoly) & 15) < kPoly) ? silu_poly(h) : silu_from_half_arg(h);
+}
 
 // D[tmem] (+)= A[tmem] * B[smem]^T
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -42,7 +75,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __host__ __device__ inline int ta_table_bytes(int trows) { return ((trows * kTPitch * 4 + kHid * 4 + 127) / 128) * 128; }
 
-template <int kTaWG, int kTaProducers>
+template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly>
 __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc_ta_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nh = p.n_hidden;
@@ -51,11 +84,14 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   unsigned char* sWf = sW + (nh - 1) * kWBytes;
   const float* sBias = reinterpret_cast<const float*>(sWf + kWFinalBytes);
   const float* sBiasF = sBias + nh * kHid;
-  unsigned char* tables = smem + ((wbytes + 1023) / 1024) * 1024;
+  unsigned char* sBB = smem + ((wbytes + 1023) / 1024) * 1024;  // bias K-blocks (kBiasMMA)
+  const int bbbytes = kBiasMMA ? (nh - 1) * kWBytes : 0;
+  unsigned char* tables = sBB + bbbytes;
   const int tbytes = ta_table_bytes(p.trows);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tables + kTaWG * tbytes);
   // bars[0] = weights; per warpgroup g: [1+3g] t_full, [2+3g] t_empty, [3+3g] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * kTaWG);
+  int* xu_sem = reinterpret_cast<int*>(tmem_slot + 4);  // [4]: permits per SM sub-partition (p.xu_tokens > 0)
 
   const int tid_cta = threadIdx.x;
   const int wid = tid_cta >> 5;
@@ -69,6 +105,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
       mbar_init(smem_u32(&bars[3 + 3 * g]), 1);  // acc_full: tcgen05.commit
     }
     mbar_fence_init();
+    for (int q = 0; q < 4; ++q) xu_sem[q] = p.xu_tokens;
   }
   if (wid == 0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
@@ -77,13 +114,14 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t bar_w = smem_u32(&bars[0]);
   if (tid_cta == 0) {
-    mbar_expect_tx(bar_w, (uint32_t)wbytes);
+    mbar_expect_tx(bar_w, (uint32_t)(wbytes + bbbytes));
     int off = 0;
     while (off < wbytes) {
       const int n = min(8192, wbytes - off);
       bulk_g2s(smem_u32(sW + off), p.tc_weights + off, (uint32_t)n, bar_w);
       off += n;
     }
+    for (off = 0; off < bbbytes; off += kWBytes) bulk_g2s(smem_u32(sBB + off), p.tc_biasblk + off, (uint32_t)kWBytes, bar_w);
   }
 
   const int tiles_per_line = (p.R + kTileM - 1) / kTileM;
@@ -165,6 +203,34 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     const uint32_t bar_acc = smem_u32(&bars[3 + 3 * wg]);
     uint32_t par_t = 0, par_acc = 0;
 
+    // The four warps of an SM sub-partition (one per warpgroup) run identical steps, share its SFU
+    // equally and therefore finish together and wait for their MMAs together: a convoy that leaves
+    // the SFU idle for a whole MMA round trip per step.  Two ways to break it: a one-off start offset
+    // per warpgroup (stagger_clk), or a semaphore that lets only xu_tokens warps of a sub-partition
+    // into an activation stretch at a time (the others wait while their MMA would be waiting anyway).
+    const bool use_tok = p.xu_tokens > 0;
+    auto xu_acquire = [&]() {
+      if (!use_tok) return;
+      if (lane == 0) {
+        uint32_t ns = 32;
+        while (atomicSub(&xu_sem[q], 1) <= 0) {
+          atomicAdd(&xu_sem[q], 1);
+          __nanosleep(ns);
+          if (ns < 256) ns <<= 1;
+        }
+      }
+      __syncwarp();
+    };
+    auto xu_release = [&]() {
+      if (!use_tok) return;
+      __syncwarp();
+      if (lane == 0) atomicAdd(&xu_sem[q], 1);
+    };
+
+    if (kBiasMMA) {  // constant activation block: k = 64, 65 -> 1.0 (bias hi, lo rows), k = 66..79 -> 0
+      const uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(d_tmem + 96 + lane_off, one);
+    }
     mbar_wait(bar_w, 0);
 
     // hand the finished activation columns to the tensor core: layer L = 1..nh
@@ -180,6 +246,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
 #pragma unroll
         for (int kc = 0; kc < kHid / 16; ++kc)  // K = 16 per instruction = 8 packed columns of A, +32 B of B
           umma_f16_ts(d_tmem, a_tmem + 8 * kc, b_desc + 2 * kc, idesc, kc > 0 ? 1u : 0u);
+        if (kBiasMMA && !head) umma_f16_ts(d_tmem, d_tmem + 96, umma_desc_k_sw128(smem_u32(sBB + (L - 1) * kWBytes)), idesc, 1u);
         umma_commit(bar_acc);
       }
     };
@@ -199,6 +266,11 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         r0 = min(max(r0, 0), p.trows - 2);
         mbar_wait_sleep(smem_u32(&bars[1 + 3 * wg]), par_t, (uint32_t)p.wait_ns);
         par_t ^= 1u;
+        if (n == 0 && p.stagger_clk > 0 && wg > 0) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < (long long)wg * p.stagger_clk) {}
+        }
+        xu_acquire();
         const float4* t0p = reinterpret_cast<const float4*>(sT + r0 * kTPitch);
         const float4* t1p = reinterpret_cast<const float4*>(sT + (r0 + 1) * kTPitch);
         const float4* cc = reinterpret_cast<const float4*>(sC);
@@ -212,13 +284,14 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
             const float h1 = cv.y + w0 * a.y + w1 * b.y;
             const float h2 = cv.z + w0 * a.z + w1 * b.z;
             const float h3 = cv.w + w0 * a.w + w1 * b.w;
-            pk[2 * g4 + 0] = pack_half2(silu_from_half_arg(h0), silu_from_half_arg(h1));
-            pk[2 * g4 + 1] = pack_half2(silu_from_half_arg(h2), silu_from_half_arg(h3));
+            pk[2 * g4 + 0] = pack_half2(silu_mix<kPoly>(h0, 4 * g4 + 0), silu_mix<kPoly>(h1, 4 * g4 + 1));
+            pk[2 * g4 + 1] = pack_half2(silu_mix<kPoly>(h2, 4 * g4 + 2), silu_mix<kPoly>(h3, 4 * g4 + 3));
           }
           tmem_st8(a_tmem + lane_off + 8 * c, pk);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[2 + 3 * wg]));  // t_empty
+        xu_release();
         issue_layer(1);
       }
       for (int l = 1; l <= nh; ++l) {
@@ -226,50 +299,66 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         par_acc ^= 1u;
         tc_fence_after();
         if (l < nh) {
+          xu_acquire();
           const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
           uint32_t r[2][16];
           float4 bb[2][4];
           tmem_ld16(d_tmem + lane_off, r[0]);
+          if (!kBiasMMA) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) bb[0][i] = bl[i];
+            for (int i = 0; i < 4; ++i) bb[0][i] = bl[i];
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             tmem_ld_wait();
             if (c + 1 < 4) {
               tmem_ld16(d_tmem + lane_off + (c + 1) * 16, r[(c + 1) & 1]);
+              if (!kBiasMMA) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = bl[(c + 1) * 4 + i];
+                for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = bl[(c + 1) * 4 + i];
+              }
             }
             const uint32_t* rc = r[c & 1];
-            const float4* bc = bb[c & 1];
             float h[16];
+            if (kBiasMMA) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              h[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + bc[i].x;
-              h[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + bc[i].y;
-              h[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + bc[i].z;
-              h[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + bc[i].w;
+              for (int i = 0; i < 16; ++i) h[i] = __uint_as_float(rc[i]);
+            } else {
+              const float4* bc = bb[c & 1];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                h[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + bc[i].x;
+                h[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + bc[i].y;
+                h[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + bc[i].z;
+                h[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + bc[i].w;
+              }
             }
-            float tt[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tt[i] = tanh_approx(h[i]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) h[i] = fmaf(h[i], tt[i], h[i]);
+            for (int i = 0; i < 16; ++i) h[i] = silu_mix<kPoly>(h[i], i);
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h[2 * i], h[2 * i + 1]);
             tmem_st8(a_tmem + lane_off + 8 * c, pk);
           }
+          xu_release();
           issue_layer(l + 1);
         } else {
           uint32_t r[4];
           tmem_ld4(d_tmem + lane_off, r);
           tmem_ld_wait();
           const float d = __uint_as_float(r[0]) + sBiasF[0];
+          const float act = expf(__fadd_rn(d, p.density_bias));
           if (m < tg.nvalid) {
             const long long o = tg.line * p.R + tg.k0 + m;
             if (p.out_raw) p.out_raw[o] = d;
-            p.out_act[o] = expf(__fadd_rn(d, p.density_bias));
+            p.out_act[o] = act;
+          }
+          if (p.sign_out) {
+            // marching-cubes case bits of this warp's 32 consecutive z-samples = one sign-mask word
+            // (same fp32 expression as mc_signs in mcubes.cu, on the value that was just stored)
+            const bool bit = m < tg.nvalid && __fmul_rn(__fsub_rn(act, p.sign_sub), p.sign_mul) > 0.0f;
+            const uint32_t mask = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0 && q * 32 < tg.nvalid) p.sign_out[tg.line * p.sign_wz + (tg.k0 >> 5) + q] = mask;
           }
         }
       }
@@ -281,29 +370,34 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   if (wid == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int kTaWG, int kTaProducers>
+template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly>
 static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   const int wbytes = tc_weight_bytes(p.n_hidden);
-  const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 16;
+  const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (kBiasMMA ? (size_t)(p.n_hidden - 1) * kWBytes : 0) +
+                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32;
   if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
-  cudaError_t e = cudaFuncSetAttribute(lattice_tc_ta_kernel<kTaWG, kTaProducers>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = lattice_tc_ta_kernel<kTaWG, kTaProducers, kBiasMMA, kPoly>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SMB_ERR_CUDA;
   const long long ntiles = (long long)p.nx * p.R * ((p.R + kTileM - 1) / kTileM);
   long long grid = (ntiles + kTaWG - 1) / kTaWG;
   if (grid > sms) grid = sms;
-  lattice_tc_ta_kernel<kTaWG, kTaProducers><<<(unsigned)grid, kTaWG * 128 + kTaProducers * 32, smem, st>>>(p);
+  kern<<<(unsigned)grid, kTaWG * 128 + kTaProducers * 32, smem, st>>>(p);
   return smb_check(cudaGetLastError());
 }
 
+// Default: bias in the epilogue, every tanh on the SFU, no stagger, no tokens -- the fastest measured
+// (2.86 ms at 256^3).  The other variants are kept as developer switches because their measurements are
+// what DESIGN.md 4/K1 argues from (tools/sweep_lattice.py): SMB_TC_TA_BIAS=1 (bias through a fifth
+// K=16 MMA: 2.89 ms), SMB_TC_TA_POLY=4 (4 of 16 tanh on the FMA pipe: 3.22 ms; with the bias MMA
+// 3.36 ms), SMB_TC_TA_STAGGER=<clk> (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms).
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
-  const char* v = getenv("SMB_TC_TA_WG");
-  const int wg = v ? atoi(v) : 4;
-  v = getenv("SMB_TC_TA_PROD");
-  const int pr = v ? atoi(v) : 4;
-  if (wg == 3) return launch_tc_ta_n<3, 2>(p, sms, st);
-  if (pr == 1) return launch_tc_ta_n<4, 1>(p, sms, st);
-  if (pr == 4) return launch_tc_ta_n<4, 4>(p, sms, st);
-  return launch_tc_ta_n<4, 2>(p, sms, st);
+  const char* v = getenv("SMB_TC_TA_BIAS");
+  const bool bias = v ? atoi(v) != 0 : false;
+  v = getenv("SMB_TC_TA_POLY");
+  const int poly = v ? atoi(v) : 0;
+  if (bias) return poly ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
+  return poly ? launch_tc_ta_n<4, 4, false, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
 }
 
 }  // namespace smb

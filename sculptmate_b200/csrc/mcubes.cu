@@ -615,26 +615,48 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
           // z-edge 8+2di+dj (dk=0)
           const uint32_t emask = s_emask[cs];
           const int jw = sj * d.wz + sw;
+          // The four (di,dj) rows of the cell: the owners dk = 0 and dk = 1 of a row live in the same word
+          // (bit, bit+1) unless bit == 31.  The record loads of two rows (one x-plane) are issued together and
+          // unconditionally (an active cell has all four rows): two trips to L2 per cell instead of one per
+          // owner (eight); all four rows at once would spill at the 64 registers that give 4 CTAs per SM.
 #pragma unroll
-          for (int o = 0; o < 8; ++o) {
-            const int di = o >> 2, dj = (o >> 1) & 1, dk = o & 1;
-            uint32_t ebits = 0;
-            if (di == 0) ebits |= 1u << (2 * dj + dk);
-            if (dj == 0) ebits |= 1u << (4 + 2 * di + dk);
-            if (dk == 0) ebits |= 1u << (8 + 2 * di + dj);
-            if (emask & ebits) {
-              const int b2 = bit + dk;
-              const int wo = b2 >> 5, bb = b2 & 31;
-              const int jw2 = jw + dj * d.wz + wo;
+          for (int di = 0; di < 2; ++di) {
+            uint2 rlo[2], rcb[2];  // (a, b) prefixes of the word / bases of its chunk
+            uint4 rhi[2];          // (mx, my, mz, act)
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+              const int jw2 = jw + dj * d.wz;
               const long long w2 = (long long)(si + di) * d.pw + jw2;
-              const uint4 lo = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]));
-              const uint4 hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
-              const uint4 cb = __ldg(reinterpret_cast<const uint4*>(&p.cbase[(long long)(si + di) * d.cpp + jw2 / kChunkWords]));
-              const uint32_t below = (1u << bb) - 1u;
-              const uint32_t idyz = cb.x + lo.x + __popc(hi.y & below) + __popc(hi.z & below);
-              if (di == 0) s_eid[2 * dj + dk][threadIdx.x] = cb.y + lo.y + __popc(hi.x & below);
-              if (dj == 0) s_eid[4 + 2 * di + dk][threadIdx.x] = idyz;
-              if (dk == 0) s_eid[8 + 2 * di + dj][threadIdx.x] = idyz + ((hi.y >> bb) & 1u);
+              rlo[dj] = __ldg(reinterpret_cast<const uint2*>(&p.rec[w2]));
+              rhi[dj] = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
+              rcb[dj] = __ldg(reinterpret_cast<const uint2*>(&p.cbase[(long long)(si + di) * d.cpp + jw2 / kChunkWords]));
+            }
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+#pragma unroll
+              for (int dk = 0; dk < 2; ++dk) {
+                uint32_t ebits = 0u;  // x-edge needs di == 0, y-edge dj == 0, z-edge dk == 0
+                if (di == 0) ebits |= 1u << (2 * dj + dk);
+                if (dj == 0) ebits |= 1u << (4 + 2 * di + dk);
+                if (dk == 0) ebits |= 1u << (8 + 2 * di + dj);
+                if (!(emask & ebits)) continue;
+                uint2 lo = rlo[dj], cb = rcb[dj];
+                uint4 hi = rhi[dj];
+                int bb = bit + dk;
+                if (bb == 32) {  // the owner is sample 0 of the next word of the row (rare)
+                  const int jw2 = jw + dj * d.wz + 1;
+                  const long long w2 = (long long)(si + di) * d.pw + jw2;
+                  lo = __ldg(reinterpret_cast<const uint2*>(&p.rec[w2]));
+                  hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
+                  cb = __ldg(reinterpret_cast<const uint2*>(&p.cbase[(long long)(si + di) * d.cpp + jw2 / kChunkWords]));
+                  bb = 0;
+                }
+                const uint32_t below = (1u << bb) - 1u;
+                const uint32_t idyz = cb.x + lo.x + __popc(hi.y & below) + __popc(hi.z & below);
+                if (di == 0) s_eid[2 * dj + dk][threadIdx.x] = cb.y + lo.y + __popc(hi.x & below);
+                if (dj == 0) s_eid[4 + 2 * di + dk][threadIdx.x] = idyz;
+                if (dk == 0) s_eid[8 + 2 * di + dj][threadIdx.x] = idyz + ((hi.y >> bb) & 1u);
+              }
             }
           }
           const long long slot0 = f_off + st0 + (inc - ntri);
@@ -701,6 +723,27 @@ extern "C" size_t smb_mc_workspace_bytes(int nx, int ny, int nz) {
   return carve(nullptr, d).bytes;
 }
 
+static int launch_count(const McDims& d, const McWorkspace& w, int emit_last_plane, smb_mc_counts* counts_dev, cudaStream_t st) {
+  mc_count<<<(unsigned)d.nchunks, 256, 0, st>>>(w.pos, d, w.rec, w.ctot);
+  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev);
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+
+namespace smb {
+int launch_mc_signs(const float* grid, int nx, int ny, int nz, float sub, float sign, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
+  if (!grid || !workspace || nx <= 0 || ny <= 0 || nz <= 0) return SMB_ERR_BAD_ARG;
+  McDims d = make_dims(nx, ny, nz);
+  McWorkspace w = carve(workspace, d);
+  if (w.bytes > workspace_bytes) return SMB_ERR_WORKSPACE;
+  // up to 8 CTAs of 8 warps per SM, each warp 8 words per iteration
+  long long sg = (d.nwords + 63) / 64;
+  if (sg > (long long)sm_count() * 8) sg = (long long)sm_count() * 8;
+  mc_signs<<<(unsigned)sg, 256, 0, st>>>(grid, d, sub, sign, w.pos);
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+}  // namespace smb
+
 extern "C" int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub, float sign, int emit_last_plane,
                             void* workspace, size_t workspace_bytes, smb_mc_counts* counts_dev, void* stream) {
   if (!grid || !workspace || !counts_dev || nx <= 0 || ny <= 0 || nz <= 0) return SMB_ERR_BAD_ARG;
@@ -709,14 +752,19 @@ extern "C" int smb_mc_count(const float* grid, int nx, int ny, int nz, float sub
   if (w.bytes > workspace_bytes) return SMB_ERR_WORKSPACE;
   if (d.nchunks > 0x7fffffffLL) return SMB_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int sms = sm_count();
-  // K1: up to 8 CTAs of 8 warps per SM, each warp 8 words per iteration
-  long long sg = (d.nwords + 63) / 64;
-  if (sg > (long long)sms * 8) sg = (long long)sms * 8;
-  mc_signs<<<(unsigned)sg, 256, 0, st>>>(grid, d, sub, sign, w.pos);
-  mc_count<<<(unsigned)d.nchunks, 256, 0, st>>>(w.pos, d, w.rec, w.ctot);
-  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev);
-  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+  const int rc = launch_mc_signs(grid, nx, ny, nz, sub, sign, workspace, workspace_bytes, st);
+  if (rc != SMB_OK) return rc;
+  return launch_count(d, w, emit_last_plane, counts_dev, st);
+}
+
+extern "C" int smb_mc_count_presigned(int nx, int ny, int nz, int emit_last_plane, void* workspace, size_t workspace_bytes,
+                                      smb_mc_counts* counts_dev, void* stream) {
+  if (!workspace || !counts_dev || nx <= 0 || ny <= 0 || nz <= 0) return SMB_ERR_BAD_ARG;
+  McDims d = make_dims(nx, ny, nz);
+  McWorkspace w = carve(workspace, d);
+  if (w.bytes > workspace_bytes) return SMB_ERR_WORKSPACE;
+  if (d.nchunks > 0x7fffffffLL) return SMB_ERR_BAD_ARG;
+  return launch_count(d, w, emit_last_plane, counts_dev, (cudaStream_t)stream);
 }
 
 static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,

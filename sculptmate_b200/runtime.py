@@ -205,8 +205,13 @@ def query_lattice(
     precision: str = "tc",
     want_raw: bool = False,
     out: Optional[torch.Tensor] = None,
+    mc_signs: Optional[Tuple[float, float]] = None,
 ):
-    """density_act on x-planes [x_begin, x_begin+nx) of the R^3 lattice -> (nx,R,R) fp32."""
+    """density_act on x-planes [x_begin, x_begin+nx) of the R^3 lattice -> (nx,R,R) fp32.
+
+    ``mc_signs=(sub, sign)`` (tensor-core path only): the kernel also writes the marching-cubes sign
+    masks of ``(density_act - sub) * sign > 0`` into the cached MC workspace of this slab shape, so that
+    ``mc_extract(..., presigned=True)`` on the returned grid skips the classification pass."""
     R = int(resolution)
     nx = R - x_begin if nx is None else int(nx)
     _require_cuda(axis_u, "axis_u")
@@ -217,13 +222,23 @@ def query_lattice(
     cfg = _cfg(radius, density_bias, planes.Hp, planes.Wp, False)
     lib = _capi.load()
     with torch.cuda.device(dev):
-        if precision == "tc":
+        if precision == "tc" and mc_signs is not None:
+            ws, _, _ = _mc_cache.get(dev, (nx, R, R))
+            rc = lib.smb_query_lattice_tc_signs(
+                planes.planes_q.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
+                axis_u.data_ptr(), R, int(x_begin), nx, out.data_ptr(), _ptr(raw), float(mc_signs[0]), float(mc_signs[1]),
+                ws.data_ptr(), ws.numel(), _stream_ptr(dev),
+            )
+            check(rc, "smb_query_lattice_tc_signs")
+        elif precision == "tc":
             rc = lib.smb_query_lattice_tc(
                 planes.planes_q.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
                 axis_u.data_ptr(), R, int(x_begin), nx, out.data_ptr(), _ptr(raw), _stream_ptr(dev),
             )
             check(rc, "smb_query_lattice_tc")
         elif precision == "fp32":
+            if mc_signs is not None:
+                raise ValueError("mc_signs needs precision='tc'")
             rc = lib.smb_query_lattice_f32(
                 planes.planes_cl.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
                 axis_u.data_ptr(), R, int(x_begin), nx, out.data_ptr(), _ptr(raw), _stream_ptr(dev),
@@ -269,7 +284,15 @@ class McPending:
     nverts_numbered: int
 
 
-def mc_count(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, emit_last_plane: bool = True) -> McPending:
+def _launch_count(lib, grid, nx, ny, nz, sub, sign, emit_last_plane, ws, counts_dev, st, presigned: bool) -> None:
+    if presigned:  # the sign masks in ws were written by query_lattice(mc_signs=(sub, sign)) for this grid
+        check(lib.smb_mc_count_presigned(nx, ny, nz, int(emit_last_plane), ws.data_ptr(), ws.numel(), counts_dev.data_ptr(), st), "smb_mc_count_presigned")
+    else:
+        check(lib.smb_mc_count(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), int(emit_last_plane), ws.data_ptr(), ws.numel(),
+                               counts_dev.data_ptr(), st), "smb_mc_count")
+
+
+def mc_count(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, emit_last_plane: bool = True, presigned: bool = False) -> McPending:
     """Classify + scan; returns the counts (one host sync to read them)."""
     _require_cuda(grid, "grid")
     if grid.dim() != 3 or grid.dtype != torch.float32 or not grid.is_contiguous():
@@ -278,13 +301,7 @@ def mc_count(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, emit_last_
     dev = grid.device
     ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
     with torch.cuda.device(dev):
-        check(
-            _capi.load().smb_mc_count(
-                grid.data_ptr(), nx, ny, nz, float(sub), float(sign), int(emit_last_plane), ws.data_ptr(),
-                ws.numel(), counts_dev.data_ptr(), _stream_ptr(dev),
-            ),
-            "smb_mc_count",
-        )
+        _launch_count(_capi.load(), grid, nx, ny, nz, sub, sign, emit_last_plane, ws, counts_dev, _stream_ptr(dev), presigned)
         counts_pin.copy_(counts_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
     return McPending(grid, float(sub), float(sign), bool(emit_last_plane), int(counts_pin[0]), int(counts_pin[1]), int(counts_pin[2]))
@@ -325,7 +342,8 @@ _mc_caps: Dict[Tuple, Tuple[int, int]] = {}
 
 
 def mc_extract(
-    grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, flags: int = 0, vdiv: float = 1.0, vmul: float = 1.0, vadd: float = 0.0
+    grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, flags: int = 0, vdiv: float = 1.0, vmul: float = 1.0, vadd: float = 0.0,
+    presigned: bool = False,
 ) -> Tuple[torch.Tensor, torch.Tensor, McPending]:
     """count + emit for a whole grid with no host round trip between them: emit is launched right
     behind count into buffers sized from the previous mesh of this shape (+25 %), the counts are
@@ -339,7 +357,7 @@ def mc_extract(
     key = (str(dev), (nx, ny, nz))
     cap = _mc_caps.get(key)
     if cap is None:
-        pend = mc_count(grid, sub=sub, sign=sign, emit_last_plane=True)
+        pend = mc_count(grid, sub=sub, sign=sign, emit_last_plane=True, presigned=presigned)
         verts, faces = mc_emit(pend, flags=flags, vdiv=vdiv, vmul=vmul, vadd=vadd)
     else:
         ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
@@ -348,7 +366,7 @@ def mc_extract(
         faces = torch.empty((cap[1], 3), dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             st = _stream_ptr(dev)
-            check(lib.smb_mc_count(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), 1, ws.data_ptr(), ws.numel(), counts_dev.data_ptr(), st), "smb_mc_count")
+            _launch_count(lib, grid, nx, ny, nz, sub, sign, True, ws, counts_dev, st, presigned)
             check(
                 lib.smb_mc_emit_bounded(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), 0, 1, int(flags), float(vdiv), float(vmul),
                                         float(vadd), 0, ws.data_ptr(), verts.data_ptr(), cap[0], faces.data_ptr(), cap[1], st),

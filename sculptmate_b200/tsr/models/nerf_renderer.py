@@ -96,14 +96,17 @@ class TriplaneNeRFRenderer(BaseModule):
         nx: Optional[int] = None,
         precision: str = "tc",
         out: Optional[torch.Tensor] = None,
+        mc_signs=None,
     ) -> torch.Tensor:
         """density_act of query_triplane on the MarchingCubeHelper lattice, planes
-        [x_begin, x_begin+nx) -> (nx,R,R); positions are generated in-kernel."""
+        [x_begin, x_begin+nx) -> (nx,R,R); positions are generated in-kernel.
+        ``mc_signs=(sub, sign)``: also leave the marching-cubes sign masks in the MC workspace
+        (see ``runtime.query_lattice``)."""
         self._check_supported()
         pack, scene = self._planes(decoder, triplane)
         if axis_u is None:
             axis_u = runtime.lattice_axis(resolution, self.cfg.radius, device=triplane.device)
         return runtime.query_lattice(
             scene, pack, axis_u, resolution, self.cfg.radius, self.cfg.density_bias,
-            x_begin=x_begin, nx=nx, precision=precision, out=out,
+            x_begin=x_begin, nx=nx, precision=precision, out=out, mc_signs=mc_signs,
         )

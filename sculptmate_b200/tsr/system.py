@@ -91,14 +91,17 @@ class TSR(BaseModule):
         self.set_marching_cubes_resolution(resolution)
         R = resolution
         radius = self.renderer.cfg.radius
+        # helper(-(density - threshold)) then level = -input  ==  val = density - threshold; the tensor-core
+        # lattice kernel ballots the case bits while the densities are in registers (no classification pass)
+        fused = precision == "tc"
         with torch.no_grad():
             density = self.renderer.query_lattice(
-                self.decoder, scene_code, R, axis_u=self._axis(R, scene_code.device), precision=precision
+                self.decoder, scene_code, R, axis_u=self._axis(R, scene_code.device), precision=precision,
+                mc_signs=(float(threshold), 1.0) if fused else None,
             )
-        # helper(-(density - threshold)) then level = -input  ==  val = density - threshold
         v_pos, t_pos_idx, pend = runtime.mc_extract(
             density, sub=float(threshold), sign=1.0, flags=MC_FLIP | MC_DIV | MC_AFFINE,
-            vdiv=float(R - 1.0), vmul=float(radius - (-radius)), vadd=float(-radius),
+            vdiv=float(R - 1.0), vmul=float(radius - (-radius)), vadd=float(-radius), presigned=fused,
         )
         if pend.nverts == 0 or pend.ntris == 0:
             runtime.raise_for_empty_surface(density, float(threshold), 1.0)

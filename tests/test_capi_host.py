@@ -80,6 +80,19 @@ def test_decoder_pack_layout_and_values(lib, golden):
         off = lay.off_tc_l0 + (k // 64) * 8192 + _sw128(n, k % 64)
         got = b[off : off + 2].view(np.float16)[0]
         assert got == (np.float16(np.float32(0.5) * ws[0][n, k]) if k < 120 else np.float16(0))
+    # bias K-blocks: K rows 0/1 = fp16 hi/lo of b_l/2, everything else zero
+    assert lay.off_tc_biasblk % 1024 == 0 and lay.off_tc_biasblk + 8 * 8192 <= lay.total_bytes
+    for l in range(1, 9):
+        img = b[lay.off_tc_biasblk + (l - 1) * 8192 : lay.off_tc_biasblk + l * 8192]
+        total = 0.0
+        for n in range(64):
+            hi = img[_sw128(n, 0) : _sw128(n, 0) + 2].view(np.float16)[0]
+            lo = img[_sw128(n, 1) : _sw128(n, 1) + 2].view(np.float16)[0]
+            half_b = np.float32(0.5) * bs[l][n]
+            assert hi == np.float16(half_b)
+            assert abs(np.float32(hi) + np.float32(lo) - half_b) <= max(2.0 ** -21 * abs(half_b), 2.0 ** -25)  # lo may be an fp16 subnormal
+            total += abs(float(hi)) + abs(float(lo))
+        assert np.abs(img.view(np.float16).astype(np.float64)).sum() == pytest.approx(total)
     bh = b[lay.off_bias_half : lay.off_bias_half + 9 * 64 * 4].view(np.float32).reshape(9, 64)
     np.testing.assert_array_equal(bh, np.stack([0.5 * x for x in bs[:9]]))
     np.testing.assert_array_equal(b[lay.off_bias_final : lay.off_bias_final + 16].view(np.float32), bs[9])

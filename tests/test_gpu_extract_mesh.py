@@ -62,6 +62,36 @@ def test_mesh_bit_exact_vs_oracle_on_shared_density(golden, R):
     np.testing.assert_array_equal(f.cpu().numpy(), f_ref)
 
 
+@pytest.mark.parametrize("R", [17, 33, 100, 130, 160])
+def test_fused_sign_masks_equal_the_classification_pass(golden, R):
+    """The lattice kernel ballots the marching-cubes case bits while the densities are in registers
+    (smb_query_lattice_tc_signs); the masks and the mesh must equal what the stand-alone pass over the
+    stored grid gives, also when R is not a multiple of 32 / 128 (ragged words and tiles)."""
+    from oracle import mc_oracle
+    from sculptmate_b200 import runtime
+
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    dens0 = m.renderer.query_lattice(m.decoder, tp, R)
+    thr = float(dens0.median())
+    nwords = R * R * ((R + 31) // 32)
+    ws = runtime._mc_cache.get(dens0.device, (R, R, R))[0]
+    dens = m.renderer.query_lattice(m.decoder, tp, R, mc_signs=(thr, 1.0))
+    torch.cuda.synchronize()
+    fused = ws[: 4 * nwords].clone().view(torch.int32)
+    assert torch.equal(dens, dens0)
+    v1, f1, _ = runtime.mc_extract(dens, sub=thr, sign=1.0, flags=7, vdiv=float(R - 1.0), vmul=2 * RADIUS, vadd=-RADIUS, presigned=True)
+    ws.zero_()
+    v2, f2, _ = runtime.mc_extract(dens, sub=thr, sign=1.0, flags=7, vdiv=float(R - 1.0), vmul=2 * RADIUS, vadd=-RADIUS)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, ws[: 4 * nwords].view(torch.int32))
+    assert torch.equal(v1, v2) and torch.equal(f1, f2)
+    v_ref, f_ref, _ = mc_oracle.marching_cubes_slab(dens.cpu().numpy(), sub=np.float32(thr), flags=7, vdiv=float(R - 1.0), vmul=2 * RADIUS, vadd=-RADIUS)
+    np.testing.assert_array_equal(v1.cpu().numpy(), v_ref)
+    np.testing.assert_array_equal(f1.cpu().numpy(), f_ref)
+
+
 def test_threshold_errors_like_reference(golden):
     g = golden("extract_mesh.npz")
     m = _model(g)
