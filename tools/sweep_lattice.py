@@ -41,7 +41,10 @@ print(f"R={R} iters={iters} wscale={wscale}; fp32 logits: min {float(ref_raw.min
 configs = [(0, 0, 0, 0), (1, 0, 0, 0), (0, 4, 0, 0), (1, 4, 0, 0), (0, 0, 650, 0), (0, 0, 0, 1), (0, 0, 0, 2), (0, 0, 0, 3), (1, 4, 0, 2)]
 if os.environ.get("SWEEP_CONFIGS"):
     configs = [tuple(int(x) for x in c.split(",")) for c in os.environ["SWEEP_CONFIGS"].split(";")]
-for bias, poly, stag, tok in configs:
+for cfg in configs:
+    bias, poly, stag, tok = cfg[:4]
+    pipe = cfg[4] if len(cfg) > 4 else 0
+    os.environ["SMB_TC_TA_PIPE"] = str(pipe)
     os.environ["SMB_TC_TA_BIAS"] = str(bias)
     os.environ["SMB_TC_TA_POLY"] = str(poly)
     os.environ["SMB_TC_TA_STAGGER"] = str(stag)
@@ -62,4 +65,4 @@ for bias, poly, stag, tok in configs:
         if i >= 3:
             ts.append(a.elapsed_time(b))
     ms = float(np.median(ts))
-    print(f"bias_mma={bias} poly={poly}/16 stagger={stag} tokens={tok}: {ms:.3f} ms (min {min(ts):.3f}) {81408 * R**3 / ms / 1e9:.1f} TFLOP/s | logit err max {e_raw:.2e} rms {e_rms:.2e} | density_act max rel {e_rel:.2e}", flush=True)
+    print(f"bias_mma={bias} poly={poly}/16 stagger={stag} tokens={tok} pipe={pipe}: {ms:.3f} ms (min {min(ts):.3f}) {81408 * R**3 / ms / 1e9:.1f} TFLOP/s | logit err max {e_raw:.2e} rms {e_rms:.2e} | density_act max rel {e_rel:.2e}", flush=True)
