@@ -301,6 +301,17 @@ int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges
                   void* stream);
 int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t n_vertices, float* out, void* stream);
 
+/* ------------------------------------------------------------ mesh hand-off
+ * What the reference's sink TSR.import_obj_blender (tsr/system.py:127-168) needs from the mesh, produced on the
+ * device so the sink can use Blender's bulk foreach_set instead of its per-loop Python assignment (:143-146):
+ *   smb_mesh_loop_colors: loop_colors (3*ntris, 4) fp32, row 3*f + c = (vertex_colors[faces[f][c]], alpha) --
+ *     from_pydata numbers polygon loops 3*f + c; alpha = 1 is the column system.py:133-135 appends.
+ *     bad_index_flag (optional device int, caller zeroes it) is set when a face index is outside [0, nverts).
+ *   smb_mesh_faces_i32: faces narrowed to int32 (MeshLoop.vertex_index is a 32-bit int). */
+int smb_mesh_loop_colors(const float* vertex_colors, const int64_t* faces, int64_t nverts, int64_t ntris, float alpha,
+                         float* loop_colors, int* bad_index_flag, void* stream);
+int smb_mesh_faces_i32(const int64_t* faces, int64_t ntris, int32_t* faces_i32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

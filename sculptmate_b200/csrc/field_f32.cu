@@ -31,25 +31,49 @@ __global__ void planes_to_channels_last(const float* __restrict__ src, float* __
 }
 
 // planes_q[p][h][w][n] = sum_c (W0/2)[n][p*Cp + c] * plane[p][c][h][w]   (fp32)
-__global__ void project_planes(const float* __restrict__ src, const float* __restrict__ w0_half,
-                               float* __restrict__ dst, int H, int W) {
-  __shared__ float sW[kHid * kCp];  // this plane's (64 x 40) slice of W0/2
+// One CTA = 64 consecutive texels of one plane: the (40 x 64) source tile is staged in shared memory with
+// coalesced 256-byte rows, the plane's (64 x 40) weight slice transposed to [c][n]; thread (g, t) accumulates
+// the 16 outputs n = 16g .. 16g+15 of texel t (source reads conflict-free, weight reads warp-uniform
+// broadcasts) in the reference's summation order c = 0 .. 39 and writes them as four 16-byte stores.
+constexpr int kProjTexels = 64;
+__global__ void __launch_bounds__(256) project_planes(const float* __restrict__ src, const float* __restrict__ w0_half,
+                                                      float* __restrict__ dst, int H, int W) {
+  __shared__ float sW[kCp][kHid];
+  __shared__ float sS[kCp][kProjTexels];
   const int p = blockIdx.y;
+  const int HW = H * W;
+  const int hw0 = blockIdx.x * kProjTexels;
   for (int t = threadIdx.x; t < kHid * kCp; t += blockDim.x) {
-    int n = t / kCp, c = t % kCp;
-    sW[t] = w0_half[n * kFeat + p * kCp + c];
+    const int n = t / kCp, c = t - n * kCp;
+    sW[c][n] = w0_half[n * kFeat + p * kCp + c];
+  }
+  for (int t = threadIdx.x; t < kCp * kProjTexels; t += blockDim.x) {
+    const int c = t / kProjTexels, x = t - c * kProjTexels;
+    sS[c][x] = hw0 + x < HW ? src[((long long)p * kCp + c) * HW + hw0 + x] : 0.0f;
   }
   __syncthreads();
-  const int HW = H * W;
-  const int n = threadIdx.x & (kHid - 1);
-  const int sub = threadIdx.x >> 6;  // texels per block iteration = blockDim/64
-  const int per = blockDim.x >> 6;
-  for (int hw = blockIdx.x * per + sub; hw < HW; hw += gridDim.x * per) {
-    const float* s = src + (long long)p * kCp * HW + hw;
-    float acc = 0.0f;
+  const int x = threadIdx.x & (kProjTexels - 1);
+  const int g = threadIdx.x >> 6;  // 0..3: outputs 16g .. 16g+15
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
 #pragma unroll 8
-    for (int c = 0; c < kCp; ++c) acc = fmaf(sW[n * kCp + c], s[(long long)c * HW], acc);
-    dst[((long long)p * HW + hw) * kHid + n] = acc;
+  for (int c = 0; c < kCp; ++c) {
+    const float v = sS[c][x];
+    const float4* w4 = reinterpret_cast<const float4*>(&sW[c][16 * g]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = w4[j];
+      acc[4 * j + 0] = fmaf(w.x, v, acc[4 * j + 0]);
+      acc[4 * j + 1] = fmaf(w.y, v, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(w.z, v, acc[4 * j + 2]);
+      acc[4 * j + 3] = fmaf(w.w, v, acc[4 * j + 3]);
+    }
+  }
+  if (hw0 + x < HW) {
+    float4* o = reinterpret_cast<float4*>(dst + ((long long)p * HW + hw0 + x) * kHid + 16 * g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
   }
 }
 
@@ -253,10 +277,7 @@ extern "C" int smb_scene_prepare(const float* triplane, int Hp, int Wp, const vo
   if (planes_q) {
     if (!decoder_blob || !layout) return SMB_ERR_BAD_ARG;
     const float* w0h = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_w0_half);
-    int per = 256 / kHid;
-    int gx = (Hp * Wp + per - 1) / per;
-    if (gx > 1024) gx = 1024;
-    project_planes<<<dim3(gx, 3), 256, 0, st>>>(triplane, w0h, planes_q, Hp, Wp);
+    project_planes<<<dim3((Hp * Wp + kProjTexels - 1) / kProjTexels, 3), 256, 0, st>>>(triplane, w0h, planes_q, Hp, Wp);
     if (cudaGetLastError() != cudaSuccess) return SMB_ERR_CUDA;
   }
   return SMB_OK;

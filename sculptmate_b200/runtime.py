@@ -343,7 +343,7 @@ _mc_caps: Dict[Tuple, Tuple[int, int]] = {}
 
 def mc_extract(
     grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, flags: int = 0, vdiv: float = 1.0, vmul: float = 1.0, vadd: float = 0.0,
-    presigned: bool = False,
+    presigned: bool = False, on_launched=None,
 ) -> Tuple[torch.Tensor, torch.Tensor, McPending]:
     """count + emit for a whole grid with no host round trip between them: emit is launched right
     behind count into buffers sized from the previous mesh of this shape (+25 %), the counts are
@@ -359,6 +359,8 @@ def mc_extract(
     if cap is None:
         pend = mc_count(grid, sub=sub, sign=sign, emit_last_plane=True, presigned=presigned)
         verts, faces = mc_emit(pend, flags=flags, vdiv=vdiv, vmul=vmul, vadd=vadd)
+        if on_launched is not None:
+            on_launched()
     else:
         ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
         lib = _capi.load()
@@ -372,6 +374,8 @@ def mc_extract(
                                         float(vadd), 0, ws.data_ptr(), verts.data_ptr(), cap[0], faces.data_ptr(), cap[1], st),
                 "smb_mc_emit_bounded",
             )
+            if on_launched is not None:  # e.g. a CUDA event: the kernels are queued, the host has not synchronised yet
+                on_launched()
             counts_pin.copy_(counts_dev, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
         pend = McPending(grid, float(sub), float(sign), True, int(counts_pin[0]), int(counts_pin[1]), int(counts_pin[2]))
