@@ -25,6 +25,7 @@ Differences from the reference, all internal:
 """
 from __future__ import annotations
 
+import inspect
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Tuple
 
@@ -33,6 +34,7 @@ import torch
 
 from .. import runtime
 from .._capi import MC_AFFINE, MC_DIV, MC_FLIP
+from . import blender_io
 from .models.isosurface import MarchingCubeHelper
 from .models.nerf_renderer import TriplaneNeRFRenderer
 from .models.network_utils import NeRFMLP
@@ -68,12 +70,12 @@ class TSR(BaseModule):
             return
         self.isosurface_helper = MarchingCubeHelper(resolution)
 
-    def import_obj_blender(self, verts, faces, vertex_colors=None, name="NewMesh"):
+    def import_obj_blender(self, verts, faces, vertex_colors=None, name="NewMesh", **extra):
         """Sink with the reference's signature.  Inside Blender, assign the reference's own
         ``TSR.import_obj_blender`` to ``mesh_sink``; elsewhere meshes are collected in
         ``self.meshes``."""
         if self.mesh_sink is not None:
-            return self.mesh_sink(verts, faces, vertex_colors, name=name)
+            return self.mesh_sink(verts, faces, vertex_colors, name=name, **extra)
         self.meshes.append((verts, faces, vertex_colors, name))
 
     def _axis(self, resolution: int, device: torch.device) -> torch.Tensor:
@@ -111,11 +113,24 @@ class TSR(BaseModule):
         for scene_code in scene_codes:
             v_pos, t_pos_idx = self.extract_mesh_tensors(scene_code, resolution, threshold)
             color = None
+            extra = {}
             if enable_texture:
                 with torch.no_grad():
                     color = self.renderer.query_triplane(self.decoder, v_pos, scene_code, precision="tc")["color"]
+                if self._sink_takes_loop_colors():
+                    # the per-loop RGBA array the reference builds element by element (system.py:133-146),
+                    # gathered on the GPU for sinks that foreach_set it (tsr/blender_io.py)
+                    extra["loop_colors"] = blender_io.loop_colors(color, t_pos_idx).cpu().numpy()
                 color = color.cpu().numpy()
-            self.import_obj_blender(v_pos.cpu().numpy(), t_pos_idx.cpu().numpy(), color, name=mesh_name)
+            self.import_obj_blender(v_pos.cpu().numpy(), t_pos_idx.cpu().numpy(), color, name=mesh_name, **extra)
+
+    def _sink_takes_loop_colors(self) -> bool:
+        if self.mesh_sink is None:
+            return False
+        try:
+            return "loop_colors" in inspect.signature(self.mesh_sink).parameters
+        except (TypeError, ValueError):
+            return False
 
     # the reference-shaped slow path, kept for parity tests of the wrapper semantics:
     # grid_vertices -> scale_tensor -> query_triplane -> helper(-(density - threshold))
