@@ -223,6 +223,14 @@ int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int res
                           const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                           int64_t* ntris);
 
+/* The same with enable_texture=True (system.py:190-200): also returns the vertex colours
+ * colors_host (nverts,3) fp32 = query_triplane(decoder, v_pos, scene_code)["color"] (sigmoid of the three
+ * feature outputs; tensor-core points kernel) and, when loop_colors_host != NULL, the (3*ntris,4) RGBA-per-loop
+ * array the Blender sink assigns (smb_mesh_loop_colors, alpha = 1).  Buffers owned by the handle. */
+int smb_extract_mesh_host_textured(smb_extractor* ex, const float* triplane_host, int resolution, float threshold,
+                                   const float** verts_host, const int64_t** faces_host, const float** colors_host,
+                                   const float** loop_colors_host, int64_t* nverts, int64_t* ntris);
+
 /* ------------------------------------------- field query on tensor cores, any positions
  * One kernel for both decoders of the path: bilinear gathers from the channels-last planes feed an MLP
  * whose every layer is a tcgen05 UMMA (fp16 operands, fp32 accumulate), activations kept on-chip.

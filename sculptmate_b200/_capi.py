@@ -123,6 +123,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],
     ),
+    "smb_extract_mesh_host_textured": (
+        c_int,
+        [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(POINTER(c_float)),
+         POINTER(POINTER(c_float)), POINTER(c_int64), POINTER(c_int64)],
+    ),
     "smb_mlp_tc_layout_for": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(MlpTcLayout)]),
     "smb_mlp_tc_pack_host": (c_int, [_FLOATPP, _FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(MlpTcLayout), c_void_p]),
     "smb_scene_prepare_half": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -199,6 +199,15 @@ struct smb_extractor {
   smb_mc_counts* slab_counts_pin = nullptr; // kSlabs
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slab_done[kSlabs] = {};
+  // colour query at the mesh vertices (enable_texture): tensor-core points kernel
+  smb_mlp_tc_layout pts_layout;
+  void* pts_blob_dev = nullptr;
+  float* planes_cl = nullptr;
+  float* colors_dev = nullptr;
+  float* loop_colors_dev = nullptr;
+  float* colors_pin = nullptr;
+  float* loop_colors_pin = nullptr;
+  size_t colors_cap = 0, loop_colors_cap = 0;
   int n_slabs = 3;  // equal slabs, measured on B200 at 256^3: 2-3 slabs 4.42 ms, 1 (off) 4.71 ms, >= 4 slower and noisier (per-slab launch + host event cost)
   // slab k holds a share ~ slab_ratio^k of the cell layers: only the LAST slab's copy is exposed, and the copy of
   // slab k (PCIe, ~1/3 of its compute time) still hides behind the compute of the smaller slab k+1
@@ -227,6 +236,21 @@ extern "C" int smb_extractor_create(const float* const* W, const float* const* B
     delete ex;
     return rc;
   }
+  {  // NeRFMLP as a tensor-core MLP for arbitrary positions (the colour query, system.py:191-198)
+    std::vector<int> k_in(n_hidden + 1, kHid), n_out(n_hidden + 1, kHid);
+    k_in[0] = kFeat;
+    n_out[n_hidden] = kOut;
+    rc = smb_mlp_tc_layout_for(n_hidden + 1, k_in.data(), n_out.data(), &ex->pts_layout);
+    std::vector<unsigned char> pblob(rc == SMB_OK ? ex->pts_layout.total_bytes : 0);
+    if (rc == SMB_OK) rc = smb_mlp_tc_pack_host(W, B, k_in.data(), n_out.data(), &ex->pts_layout, pblob.data());
+    if (rc == SMB_OK && (cudaMalloc(&ex->pts_blob_dev, pblob.size()) != cudaSuccess ||
+                         cudaMemcpy(ex->pts_blob_dev, pblob.data(), pblob.size(), cudaMemcpyHostToDevice) != cudaSuccess))
+      rc = SMB_ERR_CUDA;
+    if (rc != SMB_OK) {
+      smb_extractor_destroy(ex);
+      return rc;
+    }
+  }
   ex->cfg.radius = radius;
   ex->cfg.density_bias = density_bias;
   ex->cfg.align_corners = 0;
@@ -237,6 +261,7 @@ extern "C" int smb_extractor_create(const float* const* W, const float* const* B
             cudaMalloc(&ex->blob_dev, blob.size()) == cudaSuccess &&
             cudaMalloc(&ex->triplane_dev, tp_bytes) == cudaSuccess &&
             cudaMalloc(&ex->planes_q, (size_t)3 * Hp * Wp * kHid * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&ex->planes_cl, tp_bytes) == cudaSuccess &&
             cudaMalloc(&ex->counts_dev, sizeof(smb_mc_counts)) == cudaSuccess &&
             cudaMalloc(&ex->minmax_dev, 2 * sizeof(float)) == cudaSuccess &&
             cudaMallocHost(&ex->triplane_pin, tp_bytes) == cudaSuccess &&
@@ -283,6 +308,12 @@ extern "C" void smb_extractor_destroy(smb_extractor* ex) {
   cudaFreeHost(ex->minmax_pin);
   cudaFree(ex->slab_counts_dev);
   cudaFreeHost(ex->slab_counts_pin);
+  cudaFree(ex->pts_blob_dev);
+  cudaFree(ex->planes_cl);
+  cudaFree(ex->colors_dev);
+  cudaFree(ex->loop_colors_dev);
+  cudaFreeHost(ex->colors_pin);
+  cudaFreeHost(ex->loop_colors_pin);
   for (int k = 0; k < smb_extractor::kSlabs; ++k)
     if (ex->slab_done[k]) cudaEventDestroy(ex->slab_done[k]);
   if (ex->copy_stream) cudaStreamDestroy(ex->copy_stream);
@@ -480,6 +511,55 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
   *faces_host = ex->faces_pin;
   *nverts = V;
   *ntris = F;
+  return SMB_OK;
+}
+
+// enable_texture=True (system.py:190-200): mesh as above, then the colour query at the vertices on the tensor
+// cores (positions = the vertices already in (-radius, radius), still on the device) and, optionally, the
+// per-loop RGBA gather the Blender sink assigns.
+extern "C" int smb_extract_mesh_host_textured(smb_extractor* ex, const float* triplane_host, int R, float threshold,
+                                              const float** verts_host, const int64_t** faces_host,
+                                              const float** colors_host, const float** loop_colors_host, int64_t* nverts,
+                                              int64_t* ntris) {
+  if (!colors_host) return SMB_ERR_BAD_ARG;
+  int rc = smb_extract_mesh_host(ex, triplane_host, R, threshold, verts_host, faces_host, nverts, ntris);
+  if (rc != SMB_OK) return rc;
+  const int64_t V = *nverts, F = *ntris;
+  cudaStream_t st = ex->stream;
+  if ((size_t)V > ex->colors_cap) {
+    cudaFree(ex->colors_dev);
+    cudaFreeHost(ex->colors_pin);
+    ex->colors_dev = ex->colors_pin = nullptr;
+    ex->colors_cap = 0;
+    const size_t cap = (size_t)V * 5 / 4;
+    EX_CUDA(cudaMalloc(&ex->colors_dev, sizeof(float) * 3 * cap));
+    EX_CUDA(cudaMallocHost(&ex->colors_pin, sizeof(float) * 3 * cap));
+    ex->colors_cap = cap;
+  }
+  rc = smb_scene_prepare(ex->triplane_dev, ex->cfg.Hp, ex->cfg.Wp, nullptr, nullptr, ex->planes_cl, nullptr, st);
+  if (rc != SMB_OK) return rc;
+  rc = smb_query_points_tc(ex->planes_cl, 0, ex->cfg.Hp, ex->cfg.Wp, 0, ex->pts_blob_dev, &ex->pts_layout, ex->cfg.radius,
+                           ex->cfg.density_bias, 1, ex->verts_dev, V, nullptr, nullptr, nullptr, ex->colors_dev, st);
+  if (rc != SMB_OK) return rc;
+  EX_CUDA(cudaMemcpyAsync(ex->colors_pin, ex->colors_dev, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+  if (loop_colors_host) {
+    if ((size_t)F > ex->loop_colors_cap) {
+      cudaFree(ex->loop_colors_dev);
+      cudaFreeHost(ex->loop_colors_pin);
+      ex->loop_colors_dev = ex->loop_colors_pin = nullptr;
+      ex->loop_colors_cap = 0;
+      const size_t cap = (size_t)F * 5 / 4;
+      EX_CUDA(cudaMalloc(&ex->loop_colors_dev, sizeof(float) * 12 * cap));
+      EX_CUDA(cudaMallocHost(&ex->loop_colors_pin, sizeof(float) * 12 * cap));
+      ex->loop_colors_cap = cap;
+    }
+    rc = smb_mesh_loop_colors(ex->colors_dev, ex->faces_dev, V, F, 1.0f, ex->loop_colors_dev, nullptr, st);
+    if (rc != SMB_OK) return rc;
+    EX_CUDA(cudaMemcpyAsync(ex->loop_colors_pin, ex->loop_colors_dev, sizeof(float) * 12 * F, cudaMemcpyDeviceToHost, st));
+  }
+  EX_CUDA(cudaStreamSynchronize(st));
+  *colors_host = ex->colors_pin;
+  if (loop_colors_host) *loop_colors_host = ex->loop_colors_pin;
   return SMB_OK;
 }
 

@@ -10,7 +10,7 @@
 //                  8 independent loads in flight per lane) and reduces it 32:1 to sign
 //                  bit masks with warp ballots.  Everything downstream works on the
 //                  masks (R^3/8 bytes, L2 resident).
-//   K2 mc_count  : one thread per word, one CTA per chunk of 2048 words of a plane:
+//   K2 mc_count  : one thread per word, one CTA per chunk of 1024 words of a plane:
 //                  crossing masks by XOR of neighbouring sign masks, owned-vertex and
 //                  triangle counts (popc / case table), CTA-wide exclusive scan; writes
 //                  a 16-byte record per word + the chunk totals.
@@ -38,8 +38,8 @@
 
 namespace smb {
 
-constexpr int kChunkWords = 2048;  // words per count CTA (256 threads x 8)
-constexpr int kWordsPerThread = 8;
+constexpr int kChunkWords = 1024;  // words per count CTA (256 threads x 4): 512 CTAs at 256^3 (2048 = 256 CTAs left the 148 SMs 1.7 waves)
+constexpr int kWordsPerThread = 4;
 
 struct McDims {
   int nx, ny, nz, wz;   // wz = words per z-row
@@ -230,10 +230,10 @@ __device__ __forceinline__ uint32_t cell_case(const WordMasks& k, int lane) {
 }
 
 // ------------------------------------------------------- K2 count + scan
-// blockIdx.x = i*cpp + c : chunk c of plane i.  Thread t owns the 8 consecutive words
-// c*2048 + 8t .. +7 of the plane (blocked, so the scan order is the canonical order).
+// blockIdx.x = i*cpp + c : chunk c of plane i.  Thread t owns kWordsPerThread consecutive words
+// c*kChunkWords + kWordsPerThread*t ... of the plane (blocked, so the scan order is the canonical order).
 // The three counters are packed into one 64-bit lane (21/21/22 bits: a chunk holds at
-// most 2048*64 in-plane vertices, 2048*32 x-edge vertices, 2048*160 triangles).
+// most kChunkWords*64 in-plane vertices, kChunkWords*32 x-edge vertices, kChunkWords*160 triangles).
 __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos, McDims d, WordRec* __restrict__ rec,
                                                 ChunkRec* __restrict__ ctot) {
   __shared__ unsigned char s_ntri[256];

@@ -169,6 +169,50 @@ def test_capi_host_extractor_matches_python_path(golden):
         lib.smb_extractor_destroy(ex)
 
 
+def test_capi_host_extractor_textured(golden):
+    """enable_texture through the C ABI: vertex colours = the Python drop-in's colour query at the same vertices,
+    loop colours = their per-loop gather with alpha 1 (what import_obj_blender assigns, system.py:133-146)."""
+    from sculptmate_b200 import _capi, runtime
+
+    lib = _capi.load()
+    g = golden("extract_mesh.npz")
+    ws, bs = golden_decoder(g)
+    fpp = ctypes.POINTER(ctypes.c_float)
+    ws_c = [np.ascontiguousarray(w) for w in ws]
+    bs_c = [np.ascontiguousarray(b) for b in bs]
+    W = (fpp * 10)(*[w.ctypes.data_as(fpp) for w in ws_c])
+    B = (fpp * 10)(*[b.ctypes.data_as(fpp) for b in bs_c])
+    ex = ctypes.c_void_p()
+    assert lib.smb_extractor_create(W, B, 9, RADIUS, -1.0, 16, 16, ctypes.byref(ex)) == 0
+    try:
+        tp = np.ascontiguousarray(g["triplane"])
+        R, thr = 48, float(g["threshold"])
+        axis = np.ascontiguousarray(runtime.lattice_axis(R, RADIUS).numpy())
+        assert lib.smb_extractor_set_axis(ex, R, axis.ctypes.data_as(fpp)) == 0
+        m = _model(g)
+        tpd = torch.from_numpy(tp).cuda()
+        v2, f2 = m.extract_mesh_tensors(tpd, R, thr)
+        c2 = m.renderer.query_triplane(m.decoder, v2, tpd, precision="tc")["color"].cpu().numpy()
+        for want_loops in (False, True, True):  # 1st call single pass, later ones the slab pipeline
+            vp, fp_, cp, lp = fpp(), ctypes.POINTER(ctypes.c_int64)(), fpp(), fpp()
+            nv, nt = ctypes.c_int64(), ctypes.c_int64()
+            rc = lib.smb_extract_mesh_host_textured(ex, tp.ctypes.data_as(fpp), R, thr, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(cp),
+                                                    ctypes.byref(lp) if want_loops else None, ctypes.byref(nv), ctypes.byref(nt))
+            assert rc == 0
+            v = np.ctypeslib.as_array(vp, shape=(nv.value, 3)).copy()
+            f = np.ctypeslib.as_array(fp_, shape=(nt.value, 3)).copy()
+            c = np.ctypeslib.as_array(cp, shape=(nv.value, 3)).copy()
+            assert np.array_equal(f, f2.cpu().numpy()) and np.array_equal(v, v2.cpu().numpy())
+            np.testing.assert_array_equal(c, c2)
+            assert c.min() >= 0.0 and c.max() <= 1.0
+            if want_loops:
+                lc = np.ctypeslib.as_array(lp, shape=(3 * nt.value, 4)).copy()
+                np.testing.assert_array_equal(lc[:, :3], c[f.reshape(-1)])
+                assert np.all(lc[:, 3] == 1.0)
+    finally:
+        lib.smb_extractor_destroy(ex)
+
+
 def test_full_size_256_mesh_properties(golden):
     """256^3 (BASELINE configs[1]): closedness away from the boundary is not guaranteed for a
     field that crosses the lattice border, so check size-independent properties: determinism,
