@@ -309,6 +309,19 @@ int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges
                   void* stream);
 int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t n_vertices, float* out, void* stream);
 
+/* ------------------------------------------------------------ volume rendering
+ * The two elementwise stages of TriplaneNeRFRenderer._forward (tsr/models/nerf_renderer.py:93-152) around the field
+ * query (smb_query_points_tc / smb_query_points_f32 at the positions produced here):
+ *   smb_ray_sample_positions: positions (n_rays, n_samples, 3) = rays_o + z * rays_d with
+ *     z = t_near * (1 - t_mid[s]) + t_far * t_mid[s] (:110-117), in the reference's fp32 operation order;
+ *     t_near / t_far (n_rays) from rays_intersect_bbox (tsr/utils.py:115-149), t_mid (n_samples) the bin centres (:108-109).
+ *   smb_ray_composite: alpha = 1 - exp(-deltas[s] * density_act), weights = alpha * cumprod(1 - alpha + 1e-10)
+ *     (exclusive), comp_rgb (n_rays,3) = sum_s w c + (1 - sum_s w) (white background, :125-150); opacity optional. */
+int smb_ray_sample_positions(const float* rays_o, const float* rays_d, const float* t_near, const float* t_far,
+                             const float* t_mid, int64_t n_rays, int n_samples, float* positions, void* stream);
+int smb_ray_composite(const float* density_act, const float* color, const float* deltas, int64_t n_rays, int n_samples,
+                      float* comp_rgb, float* opacity, void* stream);
+
 /* ------------------------------------------------------------ mesh hand-off
  * What the reference's sink TSR.import_obj_blender (tsr/system.py:127-168) needs from the mesh, produced on the
  * device so the sink can use Blender's bulk foreach_set instead of its per-loop Python assignment (:143-146):

@@ -20,6 +20,8 @@ What each function restates (paths relative to /root/reference):
                               (plane p samples (x,y),(x,z),(y,z); concat plane-major)
   nerf_mlp                    TripoSR/tsr/models/network_utils.py:49-79,116-124
   query_triplane              TripoSR/tsr/models/nerf_renderer.py:41-91
+  rays_intersect_bbox         TripoSR/tsr/utils.py:115-149
+  render_rays                 TripoSR/tsr/models/nerf_renderer.py:93-152 (sample positions, alpha compositing)
   sf3d_query_triplane         StableFast/sf3d/system.py:170-198
   material_mlp_head           StableFast/sf3d/models/network.py:158-178,191-208
 """
@@ -182,6 +184,48 @@ def grid_density(
 
 
 # ------------------------------------------------------------------- SF3D ---
+def rays_intersect_bbox(rays_o: np.ndarray, rays_d: np.ndarray, radius: float, near: float = 0.0, valid_thresh: float = 0.01):
+    """utils.py:115-149 in fp32: slab test against the box tightened by (1 - 1e-3)."""
+    o = rays_o.reshape(-1, 3).astype(np.float32)
+    d = rays_d.reshape(-1, 3).astype(np.float32)
+    d = np.where(np.abs(d) < np.float32(1e-6), np.float32(1e-6), d)
+    hi = np.float32(np.float32(1.0 - 1.0e-3) * np.float32(radius))
+    lo = np.float32(np.float32(1.0 - 1.0e-3) * np.float32(-radius))
+    a = ((hi - o) / d).astype(np.float32)
+    b = ((lo - o) / d).astype(np.float32)
+    t_near = np.maximum(np.minimum(a, b).max(axis=-1), np.float32(near))
+    t_far = np.maximum(a, b).min(axis=-1)
+    valid = (t_far - t_near) > np.float32(valid_thresh)
+    t_near = np.where(valid, t_near, np.float32(0)).astype(np.float32)
+    t_far = np.where(valid, t_far, np.float32(0)).astype(np.float32)
+    return t_near, t_far, valid
+
+
+def render_rays(triplane: np.ndarray, rays_o: np.ndarray, rays_d: np.ndarray, weights, biases, radius: float = 0.87,
+                density_bias: float = -1.0, num_samples: int = 128) -> np.ndarray:
+    """nerf_renderer.py:93-152 for rays that all hit the box (the only case the reference supports)."""
+    shape = rays_o.shape[:-1]
+    o = rays_o.reshape(-1, 3).astype(np.float32)
+    d = rays_d.reshape(-1, 3).astype(np.float32)
+    t_near, t_far, valid = rays_intersect_bbox(o, d, radius)
+    assert valid.all(), "the reference's _forward needs every ray to hit the box"
+    t_vals = np.linspace(0.0, 1.0, num_samples + 1).astype(np.float32)
+    t_mid = ((t_vals[:-1] + t_vals[1:]) / np.float32(2.0)).astype(np.float32)
+    z = (t_near[:, None] * (np.float32(1) - t_mid[None]) + t_far[:, None] * t_mid[None]).astype(np.float32)
+    xyz = (o[:, None, :] + z[..., None] * d[:, None, :]).astype(np.float32)
+    out = query_triplane(xyz.reshape(-1, 3), triplane, weights, biases, radius=radius, density_bias=density_bias)
+    sigma = out["density_act"].reshape(-1, num_samples)
+    color = out["color"].reshape(-1, num_samples, 3)
+    deltas = (t_vals[1:] - t_vals[:-1]).astype(np.float32)
+    alpha = (np.float32(1) - np.exp(-deltas[None] * sigma)).astype(np.float32)
+    trans = np.cumprod((np.float32(1) - alpha[:, :-1] + np.float32(1e-10)).astype(np.float32), axis=-1, dtype=np.float32)
+    accum = np.concatenate([np.ones_like(alpha[:, :1]), trans], axis=-1)
+    w = (alpha * accum).astype(np.float32)
+    rgb = (w[..., None] * color).sum(axis=-2, dtype=np.float32)
+    opacity = w.sum(axis=-1, dtype=np.float32)
+    return (rgb + (np.float32(1) - opacity)[:, None]).astype(np.float32).reshape(*shape, 3)
+
+
 def sf3d_query_triplane(positions: np.ndarray, triplane: np.ndarray, radius: float = 0.87) -> np.ndarray:
     """sf3d/system.py:170-198 for one un-batched triplane: (N,3) -> (N, 3*Cp)."""
     pos = scale_tensor(positions.reshape(-1, 3), (-radius, radius), (-1, 1))

@@ -17,6 +17,26 @@ import torch.nn.functional as F
 ValidScale = Union[Tuple[float, float], torch.FloatTensor]
 
 
+def rays_intersect_bbox(rays_o: torch.Tensor, rays_d: torch.Tensor, radius, near: float = 0.0, valid_thresh: float = 0.01):
+    """Slab test of rays against the (slightly tightened) +-radius box: the reference's utils.py:115-149 with the
+    same torch ops in the same order (so t_near / t_far are bit-identical on the same device):
+    returns ``t_near``, ``t_far`` (``*shape, 1``) and ``rays_valid`` (``*shape``)."""
+    shape = rays_o.shape[:-1]
+    o, d = rays_o.view(-1, 3), rays_d.view(-1, 3)
+    d_safe = torch.where(d.abs() < 1e-6, torch.full_like(d, 1e-6), d)  # never divide by ~0
+    if type(radius) in [int, float]:
+        radius = torch.FloatTensor([[-radius, radius]] * 3).to(o.device)
+    radius = (1.0 - 1.0e-3) * radius  # the hit points must lie inside the box
+    hit_hi = (radius[..., 1] - o) / d_safe
+    hit_lo = (radius[..., 0] - o) / d_safe
+    t_near = torch.minimum(hit_hi, hit_lo).amax(dim=-1).clamp_min(near)
+    t_far = torch.maximum(hit_hi, hit_lo).amin(dim=-1)
+    valid = t_far - t_near > valid_thresh
+    t_near[torch.where(~valid)] = 0.0
+    t_far[torch.where(~valid)] = 0.0
+    return t_near.view(*shape, 1), t_far.view(*shape, 1), valid.view(*shape)
+
+
 def scale_tensor(dat: torch.FloatTensor, inp_scale: ValidScale, tgt_scale: ValidScale):
     """Affine remap, same operation order as utils.py:222-231."""
     if inp_scale is None:
