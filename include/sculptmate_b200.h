@@ -219,6 +219,9 @@ void smb_extractor_destroy(smb_extractor* ex);
  * reference's own ops produce (isosurface.py:30-32 -> system.py:177-181 -> nerf_renderer.py:52-54),
  * making the C path bit-identical to the Python drop-in.  Copied; valid until R changes. */
 int smb_extractor_set_axis(smb_extractor* ex, int resolution, const float* axis_u_host);
+/* The handle's pinned staging buffer for the scene code (3*40*Hp*Wp floats).  A host that writes the triplane
+ * there and passes the same pointer as triplane_host skips the pageable->pinned copy (about 0.1 ms for 2 MB). */
+int smb_extractor_pinned_input(smb_extractor* ex, float** triplane_pinned);
 int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int resolution, float threshold,
                           const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                           int64_t* ntris);

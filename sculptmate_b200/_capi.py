@@ -125,6 +125,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],
     ),
+    "smb_extractor_pinned_input": (c_int, [c_void_p, POINTER(POINTER(c_float))]),
     "smb_extract_mesh_host_textured": (
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(POINTER(c_float)),

@@ -321,6 +321,12 @@ extern "C" void smb_extractor_destroy(smb_extractor* ex) {
   delete ex;
 }
 
+extern "C" int smb_extractor_pinned_input(smb_extractor* ex, float** triplane_pinned) {
+  if (!ex || !triplane_pinned) return SMB_ERR_BAD_ARG;
+  *triplane_pinned = ex->triplane_pin;
+  return SMB_OK;
+}
+
 static int ensure_resolution(smb_extractor* ex, int R) {
   // per-resolution workspaces are cached like the reference caches its helper
   // (system.py:118-124 set_marching_cubes_resolution)
@@ -431,7 +437,7 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
   if (rc != SMB_OK) return rc;
   cudaStream_t st = ex->stream;
   const size_t tp_bytes = (size_t)3 * kCp * ex->cfg.Hp * ex->cfg.Wp * sizeof(float);
-  memcpy(ex->triplane_pin, triplane_host, tp_bytes);
+  if (triplane_host != ex->triplane_pin) memcpy(ex->triplane_pin, triplane_host, tp_bytes);  // else: written in place
   EX_CUDA(cudaMemcpyAsync(ex->triplane_dev, ex->triplane_pin, tp_bytes, cudaMemcpyHostToDevice, st));
   rc = smb_scene_prepare(ex->triplane_dev, ex->cfg.Hp, ex->cfg.Wp, ex->blob_dev, &ex->layout, nullptr, ex->planes_q, st);
   if (rc != SMB_OK) return rc;

@@ -30,7 +30,8 @@
 
 namespace smb {
 
-constexpr int kTaColsPerWG = 128;  // 64 accumulator + 32 activation + 8 constant (bias) columns, padded
+// TMEM columns per warpgroup: 64 accumulator + 32 activation (+ 8 constant bias columns, padded to 128, with kBiasMMA)
+__host__ __device__ constexpr int ta_cols_per_wg(bool bias_mma) { return bias_mma ? 128 : 96; }
 
 // silu(2h) = h + |h| tanh(|h|) with tanh(|h|) ~= hc q(hc^2), hc = min(|h|, 4): degree-8 polynomial in hc^2,
 // max abs error of tanh 1.0e-3 (MUFU.TANH: 5e-4; the result is rounded to fp16 = 5e-4 relative anyway).
@@ -132,7 +133,11 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   const long long ntiles = (long long)p.nx * p.R * tiles_per_line;
   const long long HW = (long long)p.H * p.W;
 
+  // kRegShift (5 warpgroups): the CTA is launched at 80 registers per thread (768 threads); the producer
+  // warpgroup gives registers back and the consumers take them (the increase is served from the registers the CTA itself gave back: 128 x (80 - 40) = 640 x (88 - 80))
+  constexpr bool kRegShift = kTaWG * 128 + kTaProducers * 32 > 640;
   if (wid >= kTaWG * 4) {
+    if (kRegShift) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // =================================================================== producer
     const int pi = wid - kTaWG * 4;
     const float* Q0 = p.planes_q;
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
       if (!any) break;
     }
   } else {
+    if (kRegShift) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // =================================================================== consumer
     const int wg = wid >> 2;
     const int q = wid & 3;
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     const int tid_wg = tid_cta & 127;
     const float* sT = reinterpret_cast<const float*>(tables + wg * tbytes);
     const float* sC = sT + p.trows * kTPitch;
-    const uint32_t d_tmem = tmem_base + (uint32_t)(wg * kTaColsPerWG);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(wg * ta_cols_per_wg(kBiasMMA));
     const uint32_t a_tmem = d_tmem + 64;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t idesc_hidden = umma_idesc_f16_f32(128, 64);
@@ -390,8 +396,10 @@ static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   return smb_check(cudaGetLastError());
 }
 
-// Default: bias in the epilogue, every tanh on the SFU, no stagger, no tokens -- the fastest measured
-// (2.86 ms at 256^3).  The other variants are kept as developer switches because their measurements are
+// Default: FIVE consumer warpgroups (all of tensor memory: 5 x 96 = 480 columns; 768 threads, the producer
+// warpgroup hands 40 of its 80 registers to the consumers with setmaxnreg so that they run at 88), bias in the
+// epilogue, every tanh on the SFU, no stagger, no tokens: 2.88 ms at 256^3 against 2.93 ms with four warpgroups on
+// the same GPU (SMB_TC_TA_WG=4).  The other variants are kept as developer switches because their measurements are
 // what DESIGN.md 4/K1 argues from (tools/sweep_lattice.py): SMB_TC_TA_BIAS=1 (bias through a fifth
 // K=16 MMA: 2.89 ms), SMB_TC_TA_POLY=4 (4 of 16 tanh on the FMA pipe: 3.22 ms; with the bias MMA
 // 3.36 ms), SMB_TC_TA_STAGGER=<clk> (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms).
@@ -400,6 +408,9 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
   const bool bias = v ? atoi(v) != 0 : false;
   v = getenv("SMB_TC_TA_POLY");
   const int poly = v ? atoi(v) : 0;
+  v = getenv("SMB_TC_TA_WG");
+  const int wgs = v ? atoi(v) : 5;
+  if (wgs == 5 && !bias && !poly) return launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
   if (bias) return poly ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
   return poly ? launch_tc_ta_n<4, 4, false, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
 }

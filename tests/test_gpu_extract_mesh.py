@@ -193,7 +193,16 @@ def test_capi_host_extractor_textured(golden):
         tpd = torch.from_numpy(tp).cuda()
         v2, f2 = m.extract_mesh_tensors(tpd, R, thr)
         c2 = m.renderer.query_triplane(m.decoder, v2, tpd, precision="tc")["color"].cpu().numpy()
-        for want_loops in (False, True, True):  # 1st call single pass, later ones the slab pipeline
+        # the triplane may be written straight into the handle's pinned staging buffer (no pageable->pinned copy)
+        pin = fpp()
+        assert lib.smb_extractor_pinned_input(ex, ctypes.byref(pin)) == 0
+        np.copyto(np.ctypeslib.as_array(pin, shape=tp.shape), tp)
+        vp, fp_ = fpp(), ctypes.POINTER(ctypes.c_int64)()
+        nv, nt = ctypes.c_int64(), ctypes.c_int64()
+        assert lib.smb_extract_mesh_host(ex, pin, R, thr, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt)) == 0
+        assert np.array_equal(np.ctypeslib.as_array(fp_, shape=(nt.value, 3)), f2.cpu().numpy())
+        assert np.array_equal(np.ctypeslib.as_array(vp, shape=(nv.value, 3)), v2.cpu().numpy())
+        for want_loops in (False, True, True):  # single pass or slab pipeline, with and without loop colours
             vp, fp_, cp, lp = fpp(), ctypes.POINTER(ctypes.c_int64)(), fpp(), fpp()
             nv, nt = ctypes.c_int64(), ctypes.c_int64()
             rc = lib.smb_extract_mesh_host_textured(ex, tp.ctypes.data_as(fpp), R, thr, ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(cp),
