@@ -287,7 +287,10 @@ def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precis
     lib = _capi.load()
     tsr.set_marching_cubes_resolution(R)
     with torch.no_grad():
-        slab = tsr.renderer.query_lattice(tsr.decoder, scene_code, R, axis_u=tsr._axis(R, dev), x_begin=a, nx=nx, precision=precision)
+        # the tensor-core lattice kernel also ballots the marching-cubes sign masks of the slab into the workspace
+        fused = precision == "tc"
+        slab = tsr.renderer.query_lattice(tsr.decoder, scene_code, R, axis_u=tsr._axis(R, dev), x_begin=a, nx=nx, precision=precision,
+                                          mc_signs=(float(threshold), 1.0) if fused else None)
     ws, _, _ = runtime._mc_cache.get(dev, (nx, R, R))
     r = tsr.renderer.cfg.radius
     flags = MC_FLIP | MC_DIV | MC_AFFINE
@@ -300,8 +303,11 @@ def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precis
 
     with torch.cuda.device(dev):
         st = runtime._stream_ptr(dev)
-        _capi.check(lib.smb_mc_count(slab.data_ptr(), nx, R, R, float(threshold), 1.0, int(last), ws.data_ptr(), ws.numel(),
-                                     pg.counts_dev.data_ptr(), st), "smb_mc_count")
+        if fused:
+            _capi.check(lib.smb_mc_count_presigned(nx, R, R, int(last), ws.data_ptr(), ws.numel(), pg.counts_dev.data_ptr(), st), "smb_mc_count_presigned")
+        else:
+            _capi.check(lib.smb_mc_count(slab.data_ptr(), nx, R, R, float(threshold), 1.0, int(last), ws.data_ptr(), ws.numel(),
+                                         pg.counts_dev.data_ptr(), st), "smb_mc_count")
         dist.all_gather_into_tensor(pg.all_counts_dev, pg.counts_dev, group=group)
         totals = None
         if pg.vcap == 0:  # first call: learn the sizes, then map buffers with 25 % head room
