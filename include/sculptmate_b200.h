@@ -325,6 +325,21 @@ int smb_ray_sample_positions(const float* rays_o, const float* rays_d, const flo
 int smb_ray_composite(const float* density_act, const float* color, const float* deltas, int64_t n_rays, int n_samples,
                       float* comp_rgb, float* opacity, void* stream);
 
+/* ------------------------------------------------------------ texture baking (SF3D)
+ * TextureBaker.rasterize / interpolate (StableFast/sf3d/texture_baker/baker.py:12-118).  The reference calls
+ * rasterize_cpu / interpolate_cpu inside a Windows-only DLL without source; the Python functions of the same name
+ * beside it (texture_baker/common.py:104-142,214-230) are the algorithm restated here:
+ *   smb_bake_rasterize: rast (res,res,4) fp32; texel (y,x) is the point (x/res, 1 - y/res); (u, v, w, triangle index)
+ *     of the triangle of the UV atlas that contains it (barycentrics in fp32 as common.py:104-121), else (0,0,0,-1).
+ *     Texels covered by several triangles (shared edges) take the lowest index (the reference: first BVH hit).
+ *     uv (nverts,2) fp32, faces (nfaces,3) int32 (baker.py:44), workspace of smb_bake_workspace_bytes(res).
+ *   smb_bake_interpolate: out (res,res,channels) = attr[i0]*u + attr[i1]*v + attr[i2]*w (fp32), 0 where no triangle. */
+size_t smb_bake_workspace_bytes(int resolution);
+int smb_bake_rasterize(const float* uv, const int32_t* faces, int64_t nverts, int64_t nfaces, int resolution, float* rast,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int smb_bake_interpolate(const float* attr, int channels, const int32_t* faces, int64_t nfaces, const float* rast,
+                         int resolution, float* out, void* stream);
+
 /* ------------------------------------------------------------ mesh hand-off
  * What the reference's sink TSR.import_obj_blender (tsr/system.py:127-168) needs from the mesh, produced on the
  * device so the sink can use Blender's bulk foreach_set instead of its per-loop Python assignment (:143-146):

@@ -82,6 +82,9 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     ),
+    "smb_bake_workspace_bytes": (c_size_t, [c_int]),
+    "smb_bake_rasterize": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "smb_bake_interpolate": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "smb_ray_sample_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "smb_ray_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "smb_mesh_loop_colors": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),

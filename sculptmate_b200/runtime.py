@@ -629,6 +629,28 @@ def get_sf3d_points_pack(decoder: torch.nn.Module, device: torch.device) -> MlpT
     return hit
 
 
+def get_sf3d_head_pack(decoder: torch.nn.Module, name: str, device: torch.device) -> MlpTcPack:
+    """One MaterialMLP head with <= 3 outputs (network.py:158-178; e.g. ``features`` / ``perturb_normal``:
+    120 -> 64 x n_hidden -> 3) as a tensor-core MLP: its outputs sit in rows 1..3 of the padded last layer (the
+    kernel's ``vec`` outputs), row 0 is zero."""
+    lin = [m for m in decoder.heads[name] if isinstance(m, torch.nn.Linear)]
+    if len(lin) < 2 or lin[0].in_features != 120 or any(m.out_features != 64 for m in lin[:-1]) or lin[-1].out_features > 3:
+        raise NotImplementedError(f"head {name!r}: the CUDA path expects 120 -> 64 x n -> (<= 3 outputs), SiLU")
+    params = [q for m in lin for q in (m.weight, m.bias)]
+    key = _param_key(params, device)
+    hit = _mlp_tc_cache.get(("sf3d_head", name, id(decoder)))
+    if hit is None or hit.key != key:
+        f = lambda t: t.detach().to("cpu", torch.float32)  # noqa: E731
+        ws = [f(m.weight) for m in lin[:-1]]
+        bs = [f(m.bias) for m in lin[:-1]]
+        k = lin[-1].out_features
+        w_last, b_last = torch.zeros(4, 64), torch.zeros(4)
+        w_last[1 : 1 + k] = f(lin[-1].weight)
+        b_last[1 : 1 + k] = f(lin[-1].bias)
+        hit = _mlp_tc_cache[("sf3d_head", name, id(decoder))] = _pack_mlp_tc([*ws, w_last], [*bs, b_last], device, key)
+    return hit
+
+
 def query_points_tc(
     planes: ScenePlanes, pack: MlpTcPack, positions: torch.Tensor, radius: float, out0_bias: float,
     align_corners: bool, sigmoid_vec: bool, want: Sequence[str] = ("out0_act",),

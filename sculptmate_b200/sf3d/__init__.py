@@ -7,3 +7,4 @@ from .models.mesh import Mesh  # noqa: F401
 from .models.network import HeadSpec, MaterialMLP  # noqa: F401
 from .system import SF3D  # noqa: F401
 from .tets import kuhn_tet_grid, save_tet_grid  # noqa: F401
+from .texture_baker import TextureBaker  # noqa: F401

@@ -19,6 +19,7 @@ from ..tsr.utils import BaseModule, scale_tensor
 from .models.isosurface import MarchingTetrahedraHelper
 from .models.mesh import Mesh
 from .models.network import MaterialMLP
+from .models.network import get_activation as network_activation
 
 # StableFast/checkpoints/config.yaml:45-65 (the two heads of the mesh path)
 DEFAULT_DECODER_CFG = dict(
@@ -62,6 +63,37 @@ class SF3D(BaseModule):
             res = runtime.sf3d_query(planes, None, 0.0, self.cfg.radius, positions=positions[b], want=("features",))
             outs.append(res["features"])
         return torch.stack(outs, dim=0)  # the reference keeps the batch dim it adds (system.py:175-179,196)
+
+    def query_and_decode(self, positions: torch.Tensor, triplane: torch.Tensor, include=None, exclude=None, precision: str = None):
+        """``decoder(query_triplane(positions, triplane)[0], include=..., exclude=...)`` as fused kernels -- the texel-space
+        query of the texture bake, sf3d/system.py:375-378 (``exclude=["density", "vertex_offset"]``: heads ``features``,
+        ``perturb_normal``).  positions (N,3) in (-radius, radius); returns the same dict of activated head outputs.
+        With ``precision="tc"`` (default: ``cfg.precision``) every head with <= 3 outputs runs gather + MLP on the tensor
+        cores (fp16 operands, fp32 accumulate), one pass per head; anything else goes through the fp32 feature kernel and
+        the head's torch modules, as does ``precision="fp32"``."""
+        if include is not None and exclude is not None:
+            raise ValueError("Cannot specify both include and exclude.")
+        heads = [h for h in self.decoder.cfg.heads if (include is None or h.name in include) and (exclude is None or h.name not in exclude)]
+        precision = precision or self.cfg.precision
+        dev = triplane.device
+        out, rest = {}, []
+        if precision == "tc":
+            planes = runtime.prepare_planes_half(triplane)
+            for h in heads:
+                try:
+                    pack = runtime.get_sf3d_head_pack(self.decoder, h.name, dev)
+                except NotImplementedError:
+                    rest.append(h.name)
+                    continue
+                raw = runtime.query_points_tc(planes, pack, positions, self.cfg.radius, 0.0, align_corners=True, sigmoid_vec=False,
+                                              want=("vec",))["vec"][:, : h.out_channels]
+                out[h.name] = network_activation(h.output_activation)(raw + h.out_bias)
+        else:
+            rest = [h.name for h in heads]
+        if rest:
+            feats = self.query_triplane(positions, triplane)[0]
+            out.update(self.decoder(feats, include=rest))
+        return {h.name: out[h.name] for h in heads}
 
     def _positions(self, device: torch.device) -> torch.Tensor:
         if self._grid_positions is None or self._grid_positions.device != device:

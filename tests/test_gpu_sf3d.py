@@ -144,3 +144,49 @@ def test_tensor_core_query_vs_fp32_and_mesh(golden, tets_dir):
     np.testing.assert_array_equal(mesh.t_pos_idx.cpu().numpy(), f)
     v = (v * np.float32(2 * RADIUS) + np.float32(-RADIUS)).astype(np.float32)
     np.testing.assert_array_equal(mesh.v_pos.cpu().numpy(), v)
+
+
+def test_texel_query_heads_on_tensor_cores(tets_dir):
+    """Texel-space query of the texture bake (sf3d/system.py:375-378): query_triplane at the baked positions +
+    decoder(exclude=[density, vertex_offset]) -> heads ``features`` (sigmoid) and ``perturb_normal`` (normalised),
+    fused per head on the tensor cores, against the CPU oracle (oracle/field_oracle.py, pinned to the reference)."""
+    from oracle import field_oracle as fo
+    from sculptmate_b200.sf3d import SF3D
+
+    heads = [  # StableFast/checkpoints/config.yaml:49-65
+        dict(name="density", out_channels=1, out_bias=-1.0, n_hidden_layers=2, output_activation="trunc_exp"),
+        dict(name="features", out_channels=3, n_hidden_layers=3, output_activation="sigmoid"),
+        dict(name="perturb_normal", out_channels=3, n_hidden_layers=3, output_activation="normalize_channel_last"),
+        dict(name="vertex_offset", out_channels=3, n_hidden_layers=2),
+    ]
+    torch.manual_seed(5)
+    m = SF3D(dict(isosurface_resolution=10, radius=RADIUS, tets_path=os.path.join(tets_dir, "tets10.npz"),
+                  decoder=dict(in_channels=120, n_neurons=64, activation="silu", heads=heads))).cuda()
+    g = torch.Generator().manual_seed(6)
+    tp = (0.5 * torch.randn(3, 40, 48, 48, generator=g)).cuda()
+    pos = ((torch.rand(3001, 3, generator=g) * 2 - 1) * RADIUS).cuda()
+    sd = {k: v.detach().cpu().numpy() for k, v in m.decoder.state_dict().items()}
+    feats = fo.sf3d_query_triplane(pos.cpu().numpy(), tp.cpu().numpy(), RADIUS)
+
+    def ref(name, n_lin, act):
+        ws = [sd[f"heads.{name}.{2 * i}.weight"] for i in range(n_lin)]
+        bs = [sd[f"heads.{name}.{2 * i}.bias"] for i in range(n_lin)]
+        return fo.material_mlp_head(feats, ws, bs, 0.0, act)
+
+    r_feat = ref("features", 4, "sigmoid")
+    r_nrm = ref("perturb_normal", 4, None)
+    r_nrm = r_nrm / np.maximum(np.linalg.norm(r_nrm, axis=-1, keepdims=True), 1e-12)
+    for precision, tol in (("fp32", 2e-5), ("tc", 5e-3)):
+        with torch.no_grad():
+            out = m.query_and_decode(pos, tp, exclude=["density", "vertex_offset"], precision=precision)
+        assert list(out) == ["features", "perturb_normal"]
+        assert out["features"].shape == (3001, 3) and out["perturb_normal"].shape == (3001, 3)
+        assert np.abs(out["features"].cpu().numpy() - r_feat).max() < tol
+        assert np.abs(out["perturb_normal"].cpu().numpy() - r_nrm).max() < 4 * tol  # unit vectors of small raw outputs
+    # a 1-output head through the same per-head path, and include=
+    with torch.no_grad():
+        d = m.query_and_decode(pos, tp, include=["density"], precision="tc")["density"]
+    r_d = fo.material_mlp_head(feats, [sd[f"heads.density.{2 * i}.weight"] for i in range(3)], [sd[f"heads.density.{2 * i}.bias"] for i in range(3)], -1.0, "exp")
+    assert np.abs(d.cpu().numpy() / r_d - 1).max() < 5e-3
+    with pytest.raises(ValueError):
+        m.query_and_decode(pos, tp, include=["density"], exclude=["features"])
