@@ -457,7 +457,7 @@ static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob
   // shared-memory-A kernel (kept for comparison and as the home of the timeline instrumentation)
   {
     const char* v = getenv("SMB_TC_VARIANT");
-    if (!p.dbg && !(v && v[0] == 's')) return launch_tc_ta(p, sms, st);
+    if ((!p.dbg || p.dbg == 2) && !(v && v[0] == 's')) return launch_tc_ta(p, sms, st);
   }
   p.sign_out = nullptr;  // the shared-memory-A kernel does not ballot: stand-alone sign pass below
   if (p.dbg) {  // SMB_TC_TRACE=1: developer timeline instrumentation (tools/trace_lattice.py)
@@ -490,6 +490,8 @@ extern "C" int smb_query_lattice_tc_signs(const float* planes_q, const void* dec
 }
 
 // developer instrumentation: copies the clock64 trace of the last SMB_TC_TRACE=1 launch
+extern "C" int smb_debug_read_trace_ta(long long* host, int n) { return smb::read_trace_ta(host, n); }
+
 extern "C" int smb_debug_read_trace(long long* host, int n) {
   if (!host || n <= 0 || n > 4 * 512 * 4) return SMB_ERR_BAD_ARG;
   return smb_check(cudaMemcpyFromSymbol(host, smb::g_trace, sizeof(long long) * n));

@@ -77,6 +77,7 @@ __device__ __forceinline__ TileGeom tile_geom(long long t, int tiles_per_line, c
 
 // field_tc_ta.cu: the activations-in-TMEM variant
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st);
+int read_trace_ta(long long* host, int n);  // SMB_TC_TRACE=2 timeline of the last launch
 // mcubes.cu: sign masks of a density slab (the stand-alone pass the fused path replaces) / where they live
 int launch_mc_signs(const float* grid, int nx, int ny, int nz, float sub, float sign, void* workspace, size_t workspace_bytes,
                     cudaStream_t st);

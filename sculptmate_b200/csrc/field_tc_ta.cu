@@ -80,7 +80,67 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __host__ __device__ inline int ta_table_bytes(int trows) { return ((trows * kTPitch * 4 + kHid * 4 + 127) / 128) * 128; }
 
-template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly>
+// Layer-0 table of tile t (z rows of the (.,z) planes at this line's x / y taps, and the constant vector of the
+// (x,y) plane + bias): one producer warp; the caller owns the hand-off barriers.
+struct TableGeom {
+  TileGeom tg;
+  Tap2 txw, tyw, tyh;
+};
+__device__ __forceinline__ TableGeom table_geom(const TcParams& p, long long t, int tiles_per_line) {
+  TableGeom g;
+  g.tg = tile_geom(t, tiles_per_line, p);
+  const float ux = p.axis_u[p.x_begin + g.tg.i];
+  const float uy = p.axis_u[g.tg.j];
+  g.txw = make_tap(ux, p.W, p.align_corners);
+  g.tyw = make_tap(uy, p.W, p.align_corners);
+  g.tyh = make_tap(uy, p.H, p.align_corners);
+  return g;
+}
+__device__ __forceinline__ void build_table(const TcParams& p, const TableGeom& G, float* sT, int lane) {
+  const long long HW = (long long)p.H * p.W;
+  const float* Q0 = p.planes_q;
+  const float* Q1 = Q0 + HW * kHid;
+  const float* Q2 = Q1 + HW * kHid;
+  float* sC = sT + p.trows * kTPitch;
+  const TileGeom& tg = G.tg;
+  const Tap2 &txw = G.txw, &tyw = G.tyw, &tyh = G.tyh;
+  {
+    const float2 q00 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i0 * p.W + txw.i0) * kHid) + lane);
+    const float2 q01 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i0 * p.W + txw.i1) * kHid) + lane);
+    const float2 q10 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i1 * p.W + txw.i0) * kHid) + lane);
+    const float2 q11 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i1 * p.W + txw.i1) * kHid) + lane);
+    const float2 b0 = __ldg(reinterpret_cast<const float2*>(p.bias0_half) + lane);
+    float2 c;
+    c.x = b0.x + (tyh.w0 * (txw.w0 * q00.x + txw.w1 * q01.x) + tyh.w1 * (txw.w0 * q10.x + txw.w1 * q11.x));
+    c.y = b0.y + (tyh.w0 * (txw.w0 * q00.y + txw.w1 * q01.y) + tyh.w1 * (txw.w0 * q10.y + txw.w1 * q11.y));
+    reinterpret_cast<float2*>(sC)[lane] = c;
+  }
+  {
+    const int n4 = lane & 15;
+#pragma unroll 4
+    for (int r = lane >> 4; r < tg.nrow; r += 2) {
+      const int h = tg.hlo + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (h >= 0 && h < p.H) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i0) * kHid) + n4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i1) * kHid) + n4);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i0) * kHid) + n4);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i1) * kHid) + n4);
+        v.x = txw.w0 * a.x + txw.w1 * b.x + tyw.w0 * c.x + tyw.w1 * d.x;
+        v.y = txw.w0 * a.y + txw.w1 * b.y + tyw.w0 * c.y + tyw.w1 * d.y;
+        v.z = txw.w0 * a.z + txw.w1 * b.z + tyw.w0 * c.z + tyw.w1 * d.z;
+        v.w = txw.w0 * a.w + txw.w1 * b.w + tyw.w0 * c.w + tyw.w1 * d.w;
+      }
+      *reinterpret_cast<float4*>(sT + r * kTPitch + 4 * n4) = v;
+    }
+  }
+}
+
+// developer instrumentation (kTrace, SMB_TC_TRACE=2): clock64 stamps of block 0, every consumer warp, first kTraceSteps layer steps
+constexpr int kTraceSteps = 160;
+__device__ long long g_trace_ta[5 * 4 * kTraceSteps * 4];
+
+template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly, bool kTrace = false>
 __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc_ta_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nh = p.n_hidden;
@@ -140,9 +200,6 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     if (kRegShift) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // =================================================================== producer
     const int pi = wid - kTaWG * 4;
-    const float* Q0 = p.planes_q;
-    const float* Q1 = Q0 + HW * kHid;
-    const float* Q2 = Q1 + HW * kHid;
     uint32_t par_empty = 0xff;  // bit g: parity to wait on; a fresh barrier passes a wait on parity 1
     for (long long n = 0;; ++n) {
       bool any = false;
@@ -152,45 +209,10 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         if (t >= ntiles) continue;
         any = true;
         float* sT = reinterpret_cast<float*>(tables + g * tbytes);
-        float* sC = sT + p.trows * kTPitch;
-        const TileGeom tg = tile_geom(t, tiles_per_line, p);
-        const float ux = p.axis_u[p.x_begin + tg.i];
-        const float uy = p.axis_u[tg.j];
-        const Tap2 txw = make_tap(ux, p.W, p.align_corners);
-        const Tap2 tyw = make_tap(uy, p.W, p.align_corners);
-        const Tap2 tyh = make_tap(uy, p.H, p.align_corners);
+        const TableGeom G = table_geom(p, t, tiles_per_line);
         mbar_wait_sleep(smem_u32(&bars[2 + 3 * g]), (par_empty >> g) & 1u, 20000u);
         par_empty ^= 1u << g;
-        {
-          const float2 q00 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i0 * p.W + txw.i0) * kHid) + lane);
-          const float2 q01 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i0 * p.W + txw.i1) * kHid) + lane);
-          const float2 q10 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i1 * p.W + txw.i0) * kHid) + lane);
-          const float2 q11 = __ldg(reinterpret_cast<const float2*>(Q0 + ((long long)tyh.i1 * p.W + txw.i1) * kHid) + lane);
-          const float2 b0 = __ldg(reinterpret_cast<const float2*>(p.bias0_half) + lane);
-          float2 c;
-          c.x = b0.x + (tyh.w0 * (txw.w0 * q00.x + txw.w1 * q01.x) + tyh.w1 * (txw.w0 * q10.x + txw.w1 * q11.x));
-          c.y = b0.y + (tyh.w0 * (txw.w0 * q00.y + txw.w1 * q01.y) + tyh.w1 * (txw.w0 * q10.y + txw.w1 * q11.y));
-          reinterpret_cast<float2*>(sC)[lane] = c;
-        }
-        {
-          const int n4 = lane & 15;
-#pragma unroll 4
-          for (int r = lane >> 4; r < tg.nrow; r += 2) {
-            const int h = tg.hlo + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (h >= 0 && h < p.H) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i0) * kHid) + n4);
-              const float4 b = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i1) * kHid) + n4);
-              const float4 c = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i0) * kHid) + n4);
-              const float4 d = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i1) * kHid) + n4);
-              v.x = txw.w0 * a.x + txw.w1 * b.x + tyw.w0 * c.x + tyw.w1 * d.x;
-              v.y = txw.w0 * a.y + txw.w1 * b.y + tyw.w0 * c.y + tyw.w1 * d.y;
-              v.z = txw.w0 * a.z + txw.w1 * b.z + tyw.w0 * c.z + tyw.w1 * d.z;
-              v.w = txw.w0 * a.w + txw.w1 * b.w + tyw.w0 * c.w + tyw.w1 * d.w;
-            }
-            *reinterpret_cast<float4*>(sT + r * kTPitch + 4 * n4) = v;
-          }
-        }
+        build_table(p, G, sT, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[1 + 3 * g]));  // t_full
       }
@@ -212,6 +234,18 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     const uint32_t idesc_head = umma_idesc_f16_f32(128, 16);
     const uint32_t bar_acc = smem_u32(&bars[3 + 3 * wg]);
     uint32_t par_t = 0, par_acc = 0;
+    int tr_n = 0;  // kTrace: layer steps recorded so far
+    long long tr0 = 0, tr1 = 0, tr2 = 0;
+    auto tr_put = [&](long long a, long long b, long long c, long long d) {
+      if (kTrace && blockIdx.x == 0 && lane == 0 && tr_n < kTraceSteps) {
+        long long* o = g_trace_ta + (((long long)(wg * 4 + q) * kTraceSteps) + tr_n) * 4;
+        o[0] = a;  // step begins (about to wait for the accumulator / the table)
+        o[1] = b;  // accumulator (table) ready
+        o[2] = c;  // activations computed and stored to TMEM (tcgen05.st issued)
+        o[3] = d;  // past tcgen05.wait::st + named barrier (the MMA of the next layer has been issued by thread 0)
+        ++tr_n;
+      }
+    };
 
     // The four warps of an SM sub-partition (one per warpgroup) run identical steps, share its SFU
     // equally and therefore finish together and wait for their MMAs together: a convoy that leaves
@@ -274,8 +308,10 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         const float w0 = __fsub_rn(1.0f, w1);
         int r0 = (int)hf - tg.hlo;
         r0 = min(max(r0, 0), p.trows - 2);
+        if (kTrace) tr0 = clock64();
         mbar_wait_sleep(smem_u32(&bars[1 + 3 * wg]), par_t, (uint32_t)p.wait_ns);
         par_t ^= 1u;
+        if (kTrace) tr1 = clock64();
         if (n == 0 && p.stagger_clk > 0 && wg > 0) {
           const long long t0 = clock64();
           while (clock64() - t0 < (long long)wg * p.stagger_clk) {}
@@ -302,12 +338,16 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[2 + 3 * wg]));  // t_empty
         xu_release();
+        if (kTrace) tr2 = clock64();
         issue_layer(1);
+        if (kTrace) tr_put(tr0, tr1, tr2, clock64());
       }
       for (int l = 1; l <= nh; ++l) {
+        if (kTrace) tr0 = clock64();
         mbar_wait_sleep(bar_acc, par_acc, (uint32_t)p.wait_ns);
         par_acc ^= 1u;
         tc_fence_after();
+        if (kTrace) tr1 = clock64();
         if (l < nh) {
           xu_acquire();
           const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
@@ -351,7 +391,9 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
             tmem_st8(a_tmem + lane_off + 8 * c, pk);
           }
           xu_release();
+          if (kTrace) tr2 = clock64();
           issue_layer(l + 1);
+          if (kTrace) tr_put(tr0, tr1, tr2, clock64());
         } else {
           uint32_t r[4];
           tmem_ld4(d_tmem + lane_off, r);
@@ -370,6 +412,10 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
             const uint32_t mask = __ballot_sync(0xffffffffu, bit);
             if (lane == 0 && q * 32 < tg.nvalid) p.sign_out[tg.line * p.sign_wz + (tg.k0 >> 5) + q] = mask;
           }
+          if (kTrace) {
+            const long long t = clock64();
+            tr_put(tr0, tr1, t, t);
+          }
         }
       }
     }
@@ -380,13 +426,14 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   if (wid == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly>
+
+template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly, bool kTrace = false>
 static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   const int wbytes = tc_weight_bytes(p.n_hidden);
   const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (kBiasMMA ? (size_t)(p.n_hidden - 1) * kWBytes : 0) +
                       (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32;
   if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
-  auto kern = lattice_tc_ta_kernel<kTaWG, kTaProducers, kBiasMMA, kPoly>;
+  auto kern = lattice_tc_ta_kernel<kTaWG, kTaProducers, kBiasMMA, kPoly, kTrace>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SMB_ERR_CUDA;
   const long long ntiles = (long long)p.nx * p.R * ((p.R + kTileM - 1) / kTileM);
@@ -410,9 +457,15 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
   const int poly = v ? atoi(v) : 0;
   v = getenv("SMB_TC_TA_WG");
   const int wgs = v ? atoi(v) : 5;
+  if (p.dbg == 2) return wgs == 5 ? launch_tc_ta_n<5, 4, false, 0, true>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0, true>(p, sms, st);
   if (wgs == 5 && !bias && !poly) return launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
   if (bias) return poly ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
   return poly ? launch_tc_ta_n<4, 4, false, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
+}
+
+int read_trace_ta(long long* host, int n) {
+  if (!host || n <= 0 || n > 5 * 4 * kTraceSteps * 4) return SMB_ERR_BAD_ARG;
+  return smb_check(cudaMemcpyFromSymbol(host, g_trace_ta, sizeof(long long) * n));
 }
 
 }  // namespace smb
