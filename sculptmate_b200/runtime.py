@@ -7,6 +7,7 @@ and raises otherwise -- there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -90,19 +91,20 @@ def decoder_params(decoder: torch.nn.Module) -> Tuple[List[torch.Tensor], List[t
     return [m.weight for m in lin], [m.bias for m in lin]
 
 
-_pack_cache: Dict[int, DecoderPack] = {}
+# keyed weakly by the decoder module: an entry dies with its decoder (no growth, no stale hit on a recycled id())
+_pack_cache: "weakref.WeakKeyDictionary[torch.nn.Module, DecoderPack]" = weakref.WeakKeyDictionary()
 
 
 def get_decoder_pack(decoder: torch.nn.Module, device: torch.device) -> DecoderPack:
     """Device blob for `decoder`, rebuilt when any parameter changes (ptr/version) or moves."""
     ws, bs = decoder_params(decoder)
     key = tuple((p.data_ptr(), p._version, str(p.device)) for p in (*ws, *bs)) + (str(device),)
-    cached = _pack_cache.get(id(decoder))
+    cached = _pack_cache.get(decoder)
     if cached is not None and cached.key == key:
         return cached
     blob, lay = pack_decoder_host(ws, bs)
     pack = DecoderPack(blob=blob.to(device), layout=lay, key=key)
-    _pack_cache[id(decoder)] = pack
+    _pack_cache[decoder] = pack
     return pack
 
 
@@ -588,7 +590,21 @@ def _pack_mlp_tc(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]
     return MlpTcPack(blob.to(device), lay, key)
 
 
-_mlp_tc_cache: Dict[Tuple, MlpTcPack] = {}
+class _ModuleCache:
+    """(tag, module) -> pack, weak in the module."""
+
+    def __init__(self) -> None:
+        self._d: "weakref.WeakKeyDictionary[torch.nn.Module, Dict[Tuple, MlpTcPack]]" = weakref.WeakKeyDictionary()
+
+    def get(self, tag: Tuple, module: torch.nn.Module) -> Optional[MlpTcPack]:
+        return self._d.get(module, {}).get(tag)
+
+    def put(self, tag: Tuple, module: torch.nn.Module, pack: MlpTcPack) -> MlpTcPack:
+        self._d.setdefault(module, {})[tag] = pack
+        return pack
+
+
+_mlp_tc_cache = _ModuleCache()
 
 
 def _param_key(params, device) -> Tuple:
@@ -599,9 +615,9 @@ def get_tsr_points_pack(decoder: torch.nn.Module, device: torch.device) -> MlpTc
     """NeRFMLP (network_utils.py:48-79) as a tensor-core MLP for arbitrary positions."""
     ws, bs = decoder_params(decoder)
     key = _param_key((*ws, *bs), device)
-    hit = _mlp_tc_cache.get(("tsr", id(decoder)))
+    hit = _mlp_tc_cache.get(("tsr",), decoder)
     if hit is None or hit.key != key:
-        hit = _mlp_tc_cache[("tsr", id(decoder))] = _pack_mlp_tc(ws, bs, device, key)
+        hit = _mlp_tc_cache.put(("tsr",), decoder, _pack_mlp_tc(ws, bs, device, key))
     return hit
 
 
@@ -614,7 +630,7 @@ def get_sf3d_points_pack(decoder: torch.nn.Module, device: torch.device) -> MlpT
         raise NotImplementedError("the CUDA path expects 2 hidden layers per head (config.yaml:50-65)")
     params = [q for m in (*d, *o) for q in (m.weight, m.bias)]
     key = _param_key(params, device)
-    hit = _mlp_tc_cache.get(("sf3d", id(decoder)))
+    hit = _mlp_tc_cache.get(("sf3d",), decoder)
     if hit is None or hit.key != key:
         f = lambda t: t.detach().to("cpu", torch.float32)  # noqa: E731
         w0 = torch.cat([f(d[0].weight), f(o[0].weight)], 0)
@@ -625,7 +641,7 @@ def get_sf3d_points_pack(decoder: torch.nn.Module, device: torch.device) -> MlpT
         w2[0, :64] = f(d[2].weight)[0]
         w2[1:, 64:] = f(o[2].weight)
         b2 = torch.cat([f(d[2].bias), f(o[2].bias)], 0)
-        hit = _mlp_tc_cache[("sf3d", id(decoder))] = _pack_mlp_tc([w0, w1, w2], [b0, b1, b2], device, key)
+        hit = _mlp_tc_cache.put(("sf3d",), decoder, _pack_mlp_tc([w0, w1, w2], [b0, b1, b2], device, key))
     return hit
 
 
@@ -638,7 +654,7 @@ def get_sf3d_head_pack(decoder: torch.nn.Module, name: str, device: torch.device
         raise NotImplementedError(f"head {name!r}: the CUDA path expects 120 -> 64 x n -> (<= 3 outputs), SiLU")
     params = [q for m in lin for q in (m.weight, m.bias)]
     key = _param_key(params, device)
-    hit = _mlp_tc_cache.get(("sf3d_head", name, id(decoder)))
+    hit = _mlp_tc_cache.get(("sf3d_head", name), decoder)
     if hit is None or hit.key != key:
         f = lambda t: t.detach().to("cpu", torch.float32)  # noqa: E731
         ws = [f(m.weight) for m in lin[:-1]]
@@ -647,7 +663,7 @@ def get_sf3d_head_pack(decoder: torch.nn.Module, name: str, device: torch.device
         w_last, b_last = torch.zeros(4, 64), torch.zeros(4)
         w_last[1 : 1 + k] = f(lin[-1].weight)
         b_last[1 : 1 + k] = f(lin[-1].bias)
-        hit = _mlp_tc_cache[("sf3d_head", name, id(decoder))] = _pack_mlp_tc([*ws, w_last], [*bs, b_last], device, key)
+        hit = _mlp_tc_cache.put(("sf3d_head", name), decoder, _pack_mlp_tc([*ws, w_last], [*bs, b_last], device, key))
     return hit
 
 
