@@ -61,3 +61,48 @@ def test_marching_tets_restatement_vs_live_reference(tmp_path):
     v, f = so.marching_tets(*kuhn_tet_grid(n)[:1], sdf.numpy(), kuhn_tet_grid(n)[1])
     np.testing.assert_array_equal(f, mesh.t_pos_idx.numpy())
     np.testing.assert_array_equal(v, mesh.v_pos.numpy())
+
+
+@pytest.mark.parametrize("seed,res", [(11, 24), (12, 33), (13, 40)])
+def test_bake_restatement_vs_live_reference_python_functions(seed, res):
+    """oracle/bake_oracle.py against the reference's rasterize_cpu / interpolate_cpu (texture_baker/common.py) on fresh
+    random atlases: same mask and -- wherever the same triangle is chosen -- bit-identical barycentrics and attributes."""
+    from oracle import bake_oracle as bo
+    from oracle.make_golden_bake import atlas, load_common
+
+    tb = load_common()
+    uv, faces, attr = atlas(seed, n=6)
+    with np.errstate(all="ignore"):
+        ref_rast = tb.rasterize_cpu(uv, faces, res).astype(np.float32)
+        ref_int = tb.interpolate_cpu(attr, faces, ref_rast).astype(np.float32)
+    rast = bo.rasterize(uv, faces, res)
+    np.testing.assert_array_equal(rast[..., 3] >= 0, ref_rast[..., 3] >= 0)
+    same = rast[..., 3] == ref_rast[..., 3]
+    assert same.mean() > 0.995  # only texels exactly on a shared edge may pick the other triangle (BVH order vs lowest index)
+    np.testing.assert_array_equal(rast[same], ref_rast[same])
+    out = bo.interpolate(attr, faces, rast)
+    np.testing.assert_array_equal(out[same], ref_int[same])
+    assert np.abs(out - ref_int).max() < 1e-5
+
+
+def test_render_restatement_vs_live_reference():
+    """oracle/field_oracle.py::render_rays against the reference's TriplaneNeRFRenderer.forward on fresh rays."""
+    from oracle import field_oracle as fo
+    from oracle.make_golden_render import make_rays
+
+    ref_shim.load_triposr()
+    dec = ref_shim.make_reference_decoder(9)
+    with torch.no_grad():
+        dec.layers[18].weight[0] *= 30.0
+        dec.layers[18].bias[0] -= 2.0
+    rend = ref_shim.make_reference_renderer(4096)
+    rend.eval()
+    torch.manual_seed(4)
+    tp = 0.5 * torch.randn(3, 40, 12, 12)
+    rays_o, rays_d = make_rays(64, 33)
+    with torch.no_grad():
+        want = rend(dec, tp, rays_o, rays_d).numpy()
+    ws, bs = fo.decoder_params_from_state_dict({k: v.numpy() for k, v in dec.state_dict().items()})
+    got = fo.render_rays(tp.numpy(), rays_o.numpy(), rays_d.numpy(), ws, bs, radius=RADIUS, num_samples=int(rend.cfg.num_samples_per_ray))
+    assert np.abs(got - want).max() < 5e-6
+    assert want.min() < 0.9  # not all background
