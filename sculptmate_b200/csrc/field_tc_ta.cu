@@ -458,7 +458,10 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
   v = getenv("SMB_TC_TA_WG");
   const int wgs = v ? atoi(v) : 5;
   if (p.dbg == 2) return wgs == 5 ? launch_tc_ta_n<5, 4, false, 0, true>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0, true>(p, sms, st);
-  if (wgs == 5 && !bias && !poly) return launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
+  if (wgs == 5 && !bias && !poly) {
+    const int rc = launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
+    if (rc != SMB_ERR_BAD_ARG) return rc;  // five table buffers did not fit in shared memory: four warpgroups below
+  }
   if (bias) return poly ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
   return poly ? launch_tc_ta_n<4, 4, false, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
 }
