@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see sculptmate_b200/lib/build.log")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB_PATH, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     with open(stamp, "w") as f:
         f.write(fp)
     return LIB_PATH
