@@ -106,3 +106,27 @@ def test_render_restatement_vs_live_reference():
     got = fo.render_rays(tp.numpy(), rays_o.numpy(), rays_d.numpy(), ws, bs, radius=RADIUS, num_samples=int(rend.cfg.num_samples_per_ray))
     assert np.abs(got - want).max() < 5e-6
     assert want.min() < 0.9  # not all background
+
+
+def test_rays_intersect_bbox_mirror_vs_live_reference():
+    """sculptmate_b200.tsr.utils.rays_intersect_bbox against the reference's (tsr/utils.py:115-149) on random rays that hit,
+    graze and miss the box, incl. zero direction components: bit-identical t_near / t_far / validity."""
+    from sculptmate_b200.tsr.utils import rays_intersect_bbox
+
+    ref = ref_shim.load_triposr()
+    g = torch.Generator().manual_seed(8)
+    o = torch.randn(4000, 3, generator=g) * 1.5
+    d = torch.randn(4000, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    d[:50, 0] = 0.0
+    d[50:100, 1:] = 0.0
+    want = ref.utils.rays_intersect_bbox(o.clone(), d.clone(), RADIUS)
+    got = rays_intersect_bbox(o.clone(), d.clone(), RADIUS)
+    assert 0.1 < float(want[2].float().mean()) < 0.9
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a, b)
+    # batched shapes
+    got2 = rays_intersect_bbox(o.view(40, 100, 3), d.view(40, 100, 3), RADIUS)
+    want2 = ref.utils.rays_intersect_bbox(o.view(40, 100, 3), d.view(40, 100, 3), RADIUS)
+    for a, b in zip(got2, want2):
+        assert a.shape == b.shape and torch.equal(a, b)
