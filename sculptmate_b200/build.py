@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsculptmate_b200.so")
-SOURCES = ["capi.cu", "field_f32.cu", "field_tc.cu", "mcubes.cu", "sf3d.cu", "field_pts_tc.cu", "field_tc_ta.cu", "mesh_io.cu", "render.cu", "bake.cu"]
+SOURCES = ["capi.cu", "field_f32.cu", "field_tc.cu", "mcubes.cu", "sf3d.cu", "field_pts_tc.cu", "field_tc_ta.cu", "field_tc_pair.cu", "mesh_io.cu", "render.cu", "bake.cu"]
 HEADERS = ["field_common.cuh", "field_tc_common.cuh", "ptx_sm100.cuh", "mc_tables.h", os.path.join("..", "..", "include", "sculptmate_b200.h")]
 
 NVCC_FLAGS = [

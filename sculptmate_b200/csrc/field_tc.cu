@@ -457,6 +457,11 @@ static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob
   // shared-memory-A kernel (kept for comparison and as the home of the timeline instrumentation)
   {
     const char* v = getenv("SMB_TC_VARIANT");
+    if ((!p.dbg || p.dbg == 3) && v && v[0] == 'p') {  // SMB_TC_VARIANT=pair: round-2 experiment (field_tc_pair.cu), not faster yet
+      const char* e = getenv("SMB_TC_POLY");
+      const int rc2 = launch_tc_pair(p, sms, e ? atoi(e) : 0, st);
+      if (rc2 != SMB_ERR_BAD_ARG) return rc2;  // eight table buffers did not fit in shared memory: kernel below
+    }
     if ((!p.dbg || p.dbg == 2) && !(v && v[0] == 's')) return launch_tc_ta(p, sms, st);
   }
   p.sign_out = nullptr;  // the shared-memory-A kernel does not ballot: stand-alone sign pass below
@@ -490,6 +495,10 @@ extern "C" int smb_query_lattice_tc_signs(const float* planes_q, const void* dec
 }
 
 // developer instrumentation: copies the clock64 trace of the last SMB_TC_TRACE=1 launch
+namespace smb { int pair_debug_dump(); int pair_prof_read(unsigned int* host, int n); int pair_evt_read(unsigned int* host, int n); }
+extern "C" int smb_debug_pair_evt(unsigned int* host, int n) { return smb::pair_evt_read(host, n); }
+extern "C" int smb_debug_pair_prof(unsigned int* host, int n) { return smb::pair_prof_read(host, n); }
+extern "C" int smb_debug_pair_dump(void) { return smb::pair_debug_dump(); }
 extern "C" int smb_debug_read_trace_ta(long long* host, int n) { return smb::read_trace_ta(host, n); }
 
 extern "C" int smb_debug_read_trace(long long* host, int n) {

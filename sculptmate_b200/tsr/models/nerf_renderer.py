@@ -15,6 +15,7 @@ from dataclasses import dataclass
 from typing import Dict, Optional
 
 import ctypes
+import weakref
 
 import torch
 
@@ -41,6 +42,9 @@ class TriplaneNeRFRenderer(BaseModule):
         self.chunk_size = 0
         # "fp32": CUDA-core kernel, reference precision (default); "tc": tcgen05 kernel, fp16 operands
         self.point_precision = "fp32"
+        # prepared planes of the LAST triplane seen, valid only for that very tensor object (weak reference) at the
+        # same _version: an address-based key would alias the next scene code the caching allocator hands the freed block
+        self._scene_ref = None
         self._scene_key = None
         self._scene: Optional[runtime.ScenePlanes] = None
 
@@ -60,10 +64,12 @@ class TriplaneNeRFRenderer(BaseModule):
 
     def _planes(self, decoder: torch.nn.Module, triplane: torch.Tensor):
         pack = runtime.get_decoder_pack(decoder, triplane.device)
-        key = (triplane.data_ptr(), triplane._version, tuple(triplane.shape), pack.key)
-        if self._scene_key != key:
+        key = (triplane._version, triplane.data_ptr(), tuple(triplane.shape), pack.key)
+        same = self._scene_ref is not None and self._scene_ref() is triplane and self._scene_key == key
+        if not same:
             self._scene = runtime.prepare_scene(triplane, pack)
             self._scene_key = key
+            self._scene_ref = weakref.ref(triplane)
         return pack, self._scene
 
     def query_triplane(
