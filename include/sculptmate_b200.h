@@ -36,7 +36,8 @@ typedef enum smb_status {
   SMB_ERR_WORKSPACE = -3,   /* workspace too small */
   SMB_ERR_ARCH = -4,        /* device is not sm_100 */
   SMB_ERR_LEVEL_RANGE = -5, /* iso level outside the data range (skimage: ValueError) */
-  SMB_ERR_NO_SURFACE = -6   /* no triangle produced (skimage: RuntimeError) */
+  SMB_ERR_NO_SURFACE = -6,  /* no triangle produced (skimage: RuntimeError) */
+  SMB_ERR_CAPACITY = -7     /* caller-provided output buffers too small; the needed sizes were returned */
 } smb_status;
 
 const char* smb_status_string(int status);
@@ -151,6 +152,8 @@ int smb_query_lattice_tc_signs(const float* planes_q, const void* decoder_blob, 
 #define SMB_MC_FLIP 1    /* faces[:, [1,0,2]]            isosurface.py:52 */
 #define SMB_MC_DIV 2     /* verts / vdiv (IEEE fp32)     isosurface.py:53 */
 #define SMB_MC_AFFINE 4  /* verts * vmul + vadd          system.py:185-189 */
+#define SMB_MC_FACES_I32 8 /* `faces` is (F,3) int32 instead of int64: the index width Blender's loop arrays use
+                           * (system.py:127-131 hands the array to bpy); same values, half the bytes on PCIe / NVLink */
 
 typedef struct smb_mc_counts {
   int64_t nverts;          /* vertices this slab stores */
@@ -225,6 +228,20 @@ int smb_extractor_pinned_input(smb_extractor* ex, float** triplane_pinned);
 int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_host, int resolution, float threshold,
                           const float** verts_host, const int64_t** faces_host, int64_t* nverts,
                           int64_t* ntris);
+
+/* Deliver the faces of smb_extract_mesh_host[_textured] as (F,3) int32 instead of int64 (the returned pointer then
+ * addresses int32 data): the index width Blender's loop arrays use, and a third less PCIe traffic per mesh. */
+int smb_extractor_set_faces_i32(smb_extractor* ex, int enable);
+
+/* Device-resident variant = what TSR.extract_mesh does between "scene code on the GPU" and "v_pos / t_pos_idx on the
+ * GPU" (tsr/system.py:173-189): triplane_dev (3,40,Hp,Wp) fp32 in HBM, mesh written to the CALLER's buffers
+ * verts_out (verts_capacity,3) fp32 / faces_out (faces_capacity,3) int64 (int32 with face_flags = SMB_MC_FACES_I32).
+ * All kernels are queued on `stream` by this one call, then the sizes are read (one stream synchronisation).
+ * Returns SMB_ERR_CAPACITY with *nverts / *ntris set when a buffer is too small: allocate and call again with
+ * emit_only = 1 (density and records are kept).  density_out (optional, (R,R,R) fp32) receives density_act. */
+int smb_extract_mesh_device(smb_extractor* ex, const float* triplane_dev, int resolution, float threshold, int face_flags,
+                            float* verts_out, int64_t verts_capacity, void* faces_out, int64_t faces_capacity,
+                            float* density_out, int emit_only, void* stream, int64_t* nverts, int64_t* ntris);
 
 /* The same with enable_texture=True (system.py:190-200): also returns the vertex colours
  * colors_host (nverts,3) fp32 = query_triplane(decoder, v_pos, scene_code)["color"] (sigmoid of the three

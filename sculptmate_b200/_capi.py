@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsculptmate_b200.so")
 
 OK = 0
-ERR_CUDA, ERR_BAD_ARG, ERR_WORKSPACE, ERR_ARCH, ERR_LEVEL_RANGE, ERR_NO_SURFACE = -1, -2, -3, -4, -5, -6
-MC_FLIP, MC_DIV, MC_AFFINE = 1, 2, 4
+ERR_CUDA, ERR_BAD_ARG, ERR_WORKSPACE, ERR_ARCH, ERR_LEVEL_RANGE, ERR_NO_SURFACE, ERR_CAPACITY = -1, -2, -3, -4, -5, -6, -7
+MC_FLIP, MC_DIV, MC_AFFINE, MC_FACES_I32 = 1, 2, 4, 8
 
 
 class DecoderLayout(ctypes.Structure):
@@ -129,6 +129,11 @@ SIGNATURES = {
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(c_int64), POINTER(c_int64)],
     ),
     "smb_extractor_pinned_input": (c_int, [c_void_p, POINTER(POINTER(c_float))]),
+    "smb_extractor_set_faces_i32": (c_int, [c_void_p, c_int]),
+    "smb_extract_mesh_device": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, POINTER(c_int64), POINTER(c_int64)],
+    ),
     "smb_extract_mesh_host_textured": (
         c_int,
         [c_void_p, POINTER(c_float), c_int, c_float, POINTER(POINTER(c_float)), POINTER(POINTER(c_int64)), POINTER(POINTER(c_float)),

@@ -23,6 +23,7 @@ extern "C" const char* smb_status_string(int status) {
     case SMB_ERR_ARCH: return "device is not sm_100 (B200)";
     case SMB_ERR_LEVEL_RANGE: return "Surface level must be within volume data range.";
     case SMB_ERR_NO_SURFACE: return "No surface found at the given iso value.";
+    case SMB_ERR_CAPACITY: return "output buffers too small (sizes returned; call again with larger buffers)";
   }
   return "unknown status";
 }
@@ -135,10 +136,11 @@ extern "C" int smb_decoder_pack_host(const float* const* W, const float* const* 
 //   torch.linspace(0, 1, R)                              isosurface.py:30-32
 //   scale_tensor(., (0,1), (-radius, radius))            system.py:177-181
 //   scale_tensor(., (-radius, radius), (-1, 1))          nerf_renderer.py:52-54
-// aten's CPU linspace is vectorised (base + step*lane per SIMD vector), so its values
-// differ from this scalar form by <= 2 ulp at a few indices, depending on the host's
-// SIMD width; the Python host therefore builds axis_u with torch itself, and this
-// function serves non-Python hosts (tests/test_capi_host.py bounds the difference).
+// aten's CPU linspace evaluates  start + step*i  (i < R/2)  and  end - step*(R-1-i)  (else) with the
+// multiply-add CONTRACTED into one fused operation (one rounding; step itself is rounded to fp32): fmaf
+// below.  With separately rounded multiply and add the values differ by one ulp at many indices (this was the
+// state of round 1).  scale_tensor is four separate elementwise aten ops, each rounded on its own.
+// tests/test_capi_host.py asserts equality with torch for every R in 2..400 and the benchmark sizes.
 extern "C" int smb_lattice_axis_host(int R, float radius, float* axis_u_host) {
   if (R < 1 || !axis_u_host) return SMB_ERR_BAD_ARG;
   const double r = (double)radius;
@@ -150,11 +152,9 @@ extern "C" int smb_lattice_axis_host(int R, float radius, float* axis_u_host) {
     if (R == 1) {
       t = 0.0f;
     } else if (i < R / 2) {
-      volatile float m = step * (float)i;
-      t = 0.0f + m;
+      t = fmaf(step, (float)i, 0.0f);
     } else {
-      volatile float m = step * (float)(R - 1 - i);
-      t = 1.0f - m;
+      t = fmaf(-step, (float)(R - 1 - i), 1.0f);
     }
     volatile float v = t - a_sub;
     v = v / a_div;
@@ -208,6 +208,7 @@ struct smb_extractor {
   float* colors_pin = nullptr;
   float* loop_colors_pin = nullptr;
   size_t colors_cap = 0, loop_colors_cap = 0;
+  int faces_i32 = 0;  // host extractor delivers (F,3) int32 faces (smb_extractor_set_faces_i32)
   int n_slabs = 3;  // equal slabs, measured on B200 at 256^3: 2-3 slabs 4.42 ms, 1 (off) 4.71 ms, >= 4 slower and noisier (per-slab launch + host event cost)
   // slab k holds a share ~ slab_ratio^k of the cell layers: only the LAST slab's copy is exposed, and the copy of
   // slab k (PCIe, ~1/3 of its compute time) still hides behind the compute of the smaller slab k+1
@@ -367,10 +368,11 @@ extern "C" int smb_extractor_set_axis(smb_extractor* ex, int R, const float* axi
 // (empty surface, or the mesh outgrew the remembered capacities), < 0 on error.
 static int extract_pipelined(smb_extractor* ex, int R, float threshold, int64_t* nverts, int64_t* ntris) {
   const int S = ex->n_slabs;
+  const size_t fbytes = ex->faces_i32 ? sizeof(int32_t) : sizeof(int64_t);  // buffers are sized for int64 either way
   if (S < 2 || ex->verts_cap == 0 || ex->faces_cap == 0 || R - 1 < 8 * S) return 0;
   cudaStream_t st = ex->stream;
   const double r = (double)ex->cfg.radius;
-  const int flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE;
+  const int flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (ex->faces_i32 ? SMB_MC_FACES_I32 : 0);
   const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
   // geometric slab sizes (at least 8 cell layers each), first slab largest
   const int cells = R - 1;
@@ -417,7 +419,8 @@ static int extract_pipelined(smb_extractor* ex, int R, float threshold, int64_t*
     if (fits) {
       EX_CUDA(cudaStreamWaitEvent(ex->copy_stream, ex->slab_done[k], 0));
       if (Vk) EX_CUDA(cudaMemcpyAsync(ex->verts_pin + 3 * V, ex->verts_dev + 3 * V, sizeof(float) * 3 * Vk, cudaMemcpyDeviceToHost, ex->copy_stream));
-      if (Fk) EX_CUDA(cudaMemcpyAsync(ex->faces_pin + 3 * F, ex->faces_dev + 3 * F, sizeof(int64_t) * 3 * Fk, cudaMemcpyDeviceToHost, ex->copy_stream));
+      if (Fk) EX_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(ex->faces_pin) + fbytes * 3 * F, reinterpret_cast<char*>(ex->faces_dev) + fbytes * 3 * F,
+                                      fbytes * 3 * Fk, cudaMemcpyDeviceToHost, ex->copy_stream));
     }
     V += Vk;
     F += Fk;
@@ -457,7 +460,8 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
   if (rc != SMB_OK) return rc;
   // isosurface.py:52-53 (flip, /(R-1)) and system.py:185-189 (scale to +-radius)
   const double r = (double)ex->cfg.radius;
-  const int mc_flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE;
+  const int mc_flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (ex->faces_i32 ? SMB_MC_FACES_I32 : 0);
+  const size_t fbytes = ex->faces_i32 ? sizeof(int32_t) : sizeof(int64_t);
   const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
   // emit right behind count into the buffers kept from the previous mesh (no host round trip);
   // the sizes are read afterwards and emit is repeated only if the mesh outgrew them
@@ -506,12 +510,12 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
     ex->faces_pin_cap = (size_t)F * 5 / 4;
   }
   if (!fits) {
-    rc = smb_mc_emit(ex->density, R, R, R, threshold, 1.0f, 0, 1, mc_flags, vdiv, vmul, vadd, 0, ex->mc_ws, ex->verts_dev,
-                     ex->faces_dev, st);
+    rc = smb_mc_emit_bounded(ex->density, R, R, R, threshold, 1.0f, 0, 1, mc_flags, vdiv, vmul, vadd, 0, ex->mc_ws, ex->verts_dev,
+                             (int64_t)ex->verts_cap, ex->faces_dev, (int64_t)ex->faces_cap, st);
     if (rc != SMB_OK) return rc;
   }
   EX_CUDA(cudaMemcpyAsync(ex->verts_pin, ex->verts_dev, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
-  EX_CUDA(cudaMemcpyAsync(ex->faces_pin, ex->faces_dev, sizeof(int64_t) * 3 * F, cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaMemcpyAsync(ex->faces_pin, ex->faces_dev, fbytes * 3 * F, cudaMemcpyDeviceToHost, st));
   EX_CUDA(cudaStreamSynchronize(st));
   *verts_host = ex->verts_pin;
   *faces_host = ex->faces_pin;
@@ -566,6 +570,61 @@ extern "C" int smb_extract_mesh_host_textured(smb_extractor* ex, const float* tr
   EX_CUDA(cudaStreamSynchronize(st));
   *colors_host = ex->colors_pin;
   if (loop_colors_host) *loop_colors_host = ex->loop_colors_pin;
+  return SMB_OK;
+}
+
+extern "C" int smb_extractor_set_faces_i32(smb_extractor* ex, int enable) {
+  if (!ex) return SMB_ERR_BAD_ARG;
+  ex->faces_i32 = enable ? 1 : 0;
+  return SMB_OK;
+}
+
+// The device-resident whole path (what TSR.extract_mesh_tensors runs): triplane already in HBM, mesh left in
+// HBM in the CALLER's buffers.  One call queues prepare -> lattice (+ sign ballot) -> count -> totals -> emit on
+// `stream` back to back (no host code between the launches, so the device never waits for the host), then reads
+// the sizes.  emit_only != 0: density and word records of the previous call are still valid (same handle, same
+// R / threshold) and only the emit is repeated -- what a caller does after SMB_ERR_CAPACITY with larger buffers.
+extern "C" int smb_extract_mesh_device(smb_extractor* ex, const float* triplane_dev, int R, float threshold, int face_flags,
+                                       float* verts_out, int64_t verts_capacity, void* faces_out, int64_t faces_capacity,
+                                       float* density_out, int emit_only, void* stream, int64_t* nverts, int64_t* ntris) {
+  if (!ex || !triplane_dev || R < 2 || !nverts || !ntris || verts_capacity < 0 || faces_capacity < 0) return SMB_ERR_BAD_ARG;
+  if ((verts_capacity > 0 && !verts_out) || (faces_capacity > 0 && !faces_out)) return SMB_ERR_BAD_ARG;
+  int rc = ensure_resolution(ex, R);
+  if (rc != SMB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dens = density_out ? density_out : ex->density;
+  const double r = (double)ex->cfg.radius;
+  const int mc_flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (face_flags & SMB_MC_FACES_I32);
+  const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
+  if (!emit_only) {
+    rc = smb_scene_prepare(triplane_dev, ex->cfg.Hp, ex->cfg.Wp, ex->blob_dev, &ex->layout, nullptr, ex->planes_q, st);
+    if (rc != SMB_OK) return rc;
+    rc = smb_query_lattice_tc_signs(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, 0, R, dens, nullptr, threshold, 1.0f,
+                                    ex->mc_ws, ex->mc_ws_bytes, st);
+    if (rc != SMB_OK) return rc;
+    rc = smb_mc_count_presigned(R, R, R, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
+    if (rc != SMB_OK) return rc;
+  }
+  if (verts_capacity > 0 || faces_capacity > 0) {
+    rc = smb_mc_emit_bounded(dens, R, R, R, threshold, 1.0f, 0, 1, mc_flags, vdiv, vmul, vadd, 0, ex->mc_ws, verts_out, verts_capacity,
+                             static_cast<int64_t*>(faces_out), faces_capacity, st);
+    if (rc != SMB_OK) return rc;
+  }
+  EX_CUDA(cudaMemcpyAsync(ex->counts_pin, ex->counts_dev, sizeof(smb_mc_counts), cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaStreamSynchronize(st));
+  const int64_t V = ex->counts_pin->nverts, F = ex->counts_pin->ntris;
+  *nverts = V;
+  *ntris = F;
+  if (V == 0 || F == 0) {
+    rc = smb_grid_minmax(dens, (int64_t)R * R * R, threshold, 1.0f, ex->minmax_dev, st);
+    if (rc != SMB_OK) return rc;
+    EX_CUDA(cudaMemcpyAsync(ex->minmax_pin, ex->minmax_dev, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    EX_CUDA(cudaStreamSynchronize(st));
+    if (ex->minmax_pin[0] > 0.0f || ex->minmax_pin[1] < 0.0f) return SMB_ERR_LEVEL_RANGE;
+    return SMB_ERR_NO_SURFACE;
+  }
+  if ((face_flags & SMB_MC_FACES_I32) && V >= (int64_t)1 << 31) return SMB_ERR_BAD_ARG;
+  if (V > verts_capacity || F > faces_capacity) return SMB_ERR_CAPACITY;
   return SMB_OK;
 }
 

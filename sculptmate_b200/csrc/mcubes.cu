@@ -407,7 +407,7 @@ struct EmitParams {
   const WordRec* rec;
   const ChunkRec* cbase;
   float* verts;
-  long long* faces;
+  void* faces;  // (F,3) int64, or int32 with SMB_MC_FACES_I32
   long long vcap, fcap;  // capacity of verts / faces in vertices / triangles (writes beyond are dropped)
   // gather mode: (world,4) int64 = every rank's smb_mc_counts; this slab's output offsets are the
   // sums over the lower ranks, and verts/faces point at the destination rank's buffers (peer memory)
@@ -660,15 +660,29 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
             }
           }
           const long long slot0 = f_off + st0 + (inc - ntri);
-          long long* o = p.faces + 3 * slot0;
-          for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
-            const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + id_off;
-            const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + id_off;
-            const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + id_off;
-            const bool flip = p.flags & SMB_MC_FLIP;
-            o[3 * t + 0] = flip ? i1 : i0;
-            o[3 * t + 1] = flip ? i0 : i1;
-            o[3 * t + 2] = i2;
+          const bool flip = p.flags & SMB_MC_FLIP;
+          if (p.flags & SMB_MC_FACES_I32) {
+            // int32 indices (what Blender's loop arrays and a PCIe / NVLink wire want); ids < 2^31 is checked on the host
+            int* o = static_cast<int*>(p.faces) + 3 * slot0;
+            const int ido = (int)id_off;
+            for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
+              const int i0 = (int)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + ido;
+              const int i1 = (int)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + ido;
+              const int i2 = (int)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + ido;
+              o[3 * t + 0] = flip ? i1 : i0;
+              o[3 * t + 1] = flip ? i0 : i1;
+              o[3 * t + 2] = i2;
+            }
+          } else {
+            long long* o = static_cast<long long*>(p.faces) + 3 * slot0;
+            for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
+              const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + id_off;
+              const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + id_off;
+              const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + id_off;
+              o[3 * t + 0] = flip ? i1 : i0;
+              o[3 * t + 1] = flip ? i0 : i1;
+              o[3 * t + 2] = i2;
+            }
           }
         }
       }
@@ -790,7 +804,7 @@ static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, flo
   p.rec = w.rec;
   p.cbase = w.cbase;
   p.verts = verts;
-  p.faces = reinterpret_cast<long long*>(faces);
+  p.faces = faces;
   p.vcap = verts ? verts_capacity : 0;
   p.fcap = faces ? faces_capacity : 0;
   p.all_counts = reinterpret_cast<const long long*>(all_counts);

@@ -225,13 +225,15 @@ def query_lattice(
     lib = _capi.load()
     with torch.cuda.device(dev):
         if precision == "tc" and mc_signs is not None:
-            ws, _, _ = _mc_cache.get(dev, (nx, R, R))
+            w = _mc_cache.get(dev, (nx, R, R))
+            w.generation += 1  # records of an earlier count pass on this workspace no longer match its sign masks
             rc = lib.smb_query_lattice_tc_signs(
                 planes.planes_q.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
                 axis_u.data_ptr(), R, int(x_begin), nx, out.data_ptr(), _ptr(raw), float(mc_signs[0]), float(mc_signs[1]),
-                ws.data_ptr(), ws.numel(), _stream_ptr(dev),
+                w.ws.data_ptr(), w.ws.numel(), _stream_ptr(dev),
             )
             check(rc, "smb_query_lattice_tc_signs")
+            w.mark_signed(out, mc_signs[0], mc_signs[1])
         elif precision == "tc":
             rc = lib.smb_query_lattice_tc(
                 planes.planes_q.data_ptr(), pack.blob.data_ptr(), ctypes.byref(pack.layout), ctypes.byref(cfg),
@@ -252,24 +254,49 @@ def query_lattice(
 
 
 # ---------------------------------------------------------- marching cubes
+class McWorkspace:
+    """Scratch of one (device, slab shape): the word records / sign masks, the device and pinned count records.
+
+    ``generation`` counts the count passes run on it and ``signed_for`` remembers which density tensor the lattice
+    kernel balloted the sign masks for: a pending emit (or a ``presigned`` count) is only valid against the very
+    pass / grid it belongs to, otherwise it would read another grid's records (same shape, same cache entry)."""
+
+    def __init__(self, device: torch.device, shape: Tuple[int, int, int]) -> None:
+        nbytes = _capi.load().smb_mc_workspace_bytes(*shape)
+        self.shape = tuple(shape)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.counts_dev = torch.zeros(4, dtype=torch.int64, device=device)
+        self.counts_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.generation = 0
+        self.signed_for = None  # (weakref to the grid tensor, grid._version, sub, sign)
+
+    def mark_signed(self, grid: torch.Tensor, sub: float, sign: float) -> None:
+        self.signed_for = (weakref.ref(grid), grid._version, float(sub), float(sign))
+
+    def signed_matches(self, grid: torch.Tensor, sub: float, sign: float) -> bool:
+        sf = self.signed_for
+        return sf is not None and sf[0]() is grid and sf[1] == grid._version and sf[2] == float(sub) and sf[3] == float(sign)
+
+
 class McWorkspaceCache:
-    """Per-(device, shape) scratch + pinned counters, cached like the reference caches
-    its helper per resolution (system.py:118-124)."""
+    """Per-(device, shape) workspaces, cached like the reference caches its helper per resolution
+    (system.py:118-124).  Least-recently-used eviction; a workspace that a live ``McPending`` still references
+    stays alive through that reference."""
+
+    MAX_ENTRIES = 6
 
     def __init__(self) -> None:
-        self._ws: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+        self._ws: "Dict[Tuple, McWorkspace]" = {}
 
-    def get(self, device: torch.device, shape: Tuple[int, int, int]):
+    def get(self, device: torch.device, shape: Tuple[int, int, int]) -> McWorkspace:
         key = (str(device), tuple(shape))
-        if key not in self._ws:
-            nbytes = _capi.load().smb_mc_workspace_bytes(*shape)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            counts_dev = torch.zeros(4, dtype=torch.int64, device=device)
-            counts_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
-            if len(self._ws) > 4:
-                self._ws.clear()
-            self._ws[key] = (ws, counts_dev, counts_pin)
-        return self._ws[key]
+        w = self._ws.pop(key, None)
+        if w is None:
+            w = McWorkspace(device, shape)
+            while len(self._ws) >= self.MAX_ENTRIES:
+                self._ws.pop(next(iter(self._ws)))
+        self._ws[key] = w  # most recently used last
+        return w
 
 
 _mc_cache = McWorkspaceCache()
@@ -284,29 +311,47 @@ class McPending:
     nverts: int
     ntris: int
     nverts_numbered: int
+    wsp: Optional[McWorkspace] = None  # the workspace that holds this pass' records
+    generation: int = -1
+
+    def stale(self) -> bool:
+        return self.wsp is None or self.wsp.generation != self.generation
 
 
-def _launch_count(lib, grid, nx, ny, nz, sub, sign, emit_last_plane, ws, counts_dev, st, presigned: bool) -> None:
-    if presigned:  # the sign masks in ws were written by query_lattice(mc_signs=(sub, sign)) for this grid
+def _launch_count(lib, grid, nx, ny, nz, sub, sign, emit_last_plane, w: McWorkspace, st, presigned: bool) -> None:
+    ws, counts_dev = w.ws, w.counts_dev
+    w.generation += 1
+    if presigned and w.signed_matches(grid, sub, sign):
+        # the sign masks in ws were written by query_lattice(mc_signs=(sub, sign)) for this very grid
         check(lib.smb_mc_count_presigned(nx, ny, nz, int(emit_last_plane), ws.data_ptr(), ws.numel(), counts_dev.data_ptr(), st), "smb_mc_count_presigned")
     else:
+        w.signed_for = None  # the stand-alone sign pass overwrites the masks
         check(lib.smb_mc_count(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), int(emit_last_plane), ws.data_ptr(), ws.numel(),
                                counts_dev.data_ptr(), st), "smb_mc_count")
 
 
-def mc_count(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, emit_last_plane: bool = True, presigned: bool = False) -> McPending:
-    """Classify + scan; returns the counts (one host sync to read them)."""
+def _check_grid(grid: torch.Tensor) -> None:
     _require_cuda(grid, "grid")
     if grid.dim() != 3 or grid.dtype != torch.float32 or not grid.is_contiguous():
         raise ValueError("grid must be a contiguous (nx,ny,nz) float32 tensor")
+
+
+def mc_count(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0, emit_last_plane: bool = True, presigned: bool = False) -> McPending:
+    """Classify + scan; returns the counts (one host sync to read them)."""
+    _check_grid(grid)
     nx, ny, nz = grid.shape
     dev = grid.device
-    ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
+    w = _mc_cache.get(dev, (nx, ny, nz))
     with torch.cuda.device(dev):
-        _launch_count(_capi.load(), grid, nx, ny, nz, sub, sign, emit_last_plane, ws, counts_dev, _stream_ptr(dev), presigned)
-        counts_pin.copy_(counts_dev, non_blocking=True)
+        _launch_count(_capi.load(), grid, nx, ny, nz, sub, sign, emit_last_plane, w, _stream_ptr(dev), presigned)
+        w.counts_pin.copy_(w.counts_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-    return McPending(grid, float(sub), float(sign), bool(emit_last_plane), int(counts_pin[0]), int(counts_pin[1]), int(counts_pin[2]))
+    c = w.counts_pin
+    return McPending(grid, float(sub), float(sign), bool(emit_last_plane), int(c[0]), int(c[1]), int(c[2]), w, w.generation)
+
+
+def _faces_dtype(flags: int) -> torch.dtype:
+    return torch.int32 if flags & _capi.MC_FACES_I32 else torch.int64
 
 
 def mc_emit(
@@ -323,19 +368,29 @@ def mc_emit(
     grid = pending.grid
     nx, ny, nz = grid.shape
     dev = grid.device
-    ws, _, _ = _mc_cache.get(dev, (nx, ny, nz))
+    if pending.stale():
+        # another count pass has reused the workspace since (same shape): redo this grid's pass, do not read foreign records
+        redo = mc_count(grid, pending.sub, pending.sign, pending.emit_last_plane)
+        if (redo.nverts, redo.ntris) != (pending.nverts, pending.ntris):
+            raise RuntimeError("the density grid changed between mc_count and mc_emit")
+        pending.wsp, pending.generation = redo.wsp, redo.generation
+    fdt = _faces_dtype(flags)
     verts = verts_out if verts_out is not None else torch.empty((pending.nverts, 3), dtype=torch.float32, device=dev)
-    faces = faces_out if faces_out is not None else torch.empty((pending.ntris, 3), dtype=torch.int64, device=dev)
+    faces = faces_out if faces_out is not None else torch.empty((pending.ntris, 3), dtype=fdt, device=dev)
+    if faces.dtype != fdt:
+        raise ValueError(f"faces_out must be {fdt} for these flags")
+    if fdt == torch.int32 and vertex_id_offset + pending.nverts_numbered >= 2**31:
+        raise ValueError("vertex ids do not fit int32; drop MC_FACES_I32")
     if pending.nverts == 0 and pending.ntris == 0:
         return verts, faces
     with torch.cuda.device(dev):
         check(
-            _capi.load().smb_mc_emit(
+            _capi.load().smb_mc_emit_bounded(
                 grid.data_ptr(), nx, ny, nz, pending.sub, pending.sign, int(x_origin), int(pending.emit_last_plane),
-                int(flags), float(vdiv), float(vmul), float(vadd), int(vertex_id_offset), ws.data_ptr(),
-                verts.data_ptr(), faces.data_ptr(), _stream_ptr(dev),
+                int(flags), float(vdiv), float(vmul), float(vadd), int(vertex_id_offset), pending.wsp.ws.data_ptr(),
+                verts.data_ptr(), int(verts.shape[0]), faces.data_ptr(), int(faces.shape[0]), _stream_ptr(dev),
             ),
-            "smb_mc_emit",
+            "smb_mc_emit_bounded",
         )
     return verts, faces
 
@@ -350,37 +405,38 @@ def mc_extract(
     """count + emit for a whole grid with no host round trip between them: emit is launched right
     behind count into buffers sized from the previous mesh of this shape (+25 %), the counts are
     read afterwards and the outputs are views of exactly (V,3) / (F,3).  Falls back to the
-    two-phase path on the first call for a shape and on overflow."""
-    _require_cuda(grid, "grid")
-    if grid.dim() != 3 or grid.dtype != torch.float32 or not grid.is_contiguous():
-        raise ValueError("grid must be a contiguous (nx,ny,nz) float32 tensor")
+    two-phase path on the first call for a shape and on overflow.  ``presigned`` is honoured only when the
+    workspace's sign masks were balloted for this very grid (``query_lattice(mc_signs=...)``)."""
+    _check_grid(grid)
     nx, ny, nz = grid.shape
     dev = grid.device
     key = (str(dev), (nx, ny, nz))
     cap = _mc_caps.get(key)
+    fdt = _faces_dtype(flags)
     if cap is None:
         pend = mc_count(grid, sub=sub, sign=sign, emit_last_plane=True, presigned=presigned)
         verts, faces = mc_emit(pend, flags=flags, vdiv=vdiv, vmul=vmul, vadd=vadd)
         if on_launched is not None:
             on_launched()
     else:
-        ws, counts_dev, counts_pin = _mc_cache.get(dev, (nx, ny, nz))
+        w = _mc_cache.get(dev, (nx, ny, nz))
         lib = _capi.load()
         verts = torch.empty((cap[0], 3), dtype=torch.float32, device=dev)
-        faces = torch.empty((cap[1], 3), dtype=torch.int64, device=dev)
+        faces = torch.empty((cap[1], 3), dtype=fdt, device=dev)
         with torch.cuda.device(dev):
             st = _stream_ptr(dev)
-            _launch_count(lib, grid, nx, ny, nz, sub, sign, True, ws, counts_dev, st, presigned)
+            _launch_count(lib, grid, nx, ny, nz, sub, sign, True, w, st, presigned)
             check(
                 lib.smb_mc_emit_bounded(grid.data_ptr(), nx, ny, nz, float(sub), float(sign), 0, 1, int(flags), float(vdiv), float(vmul),
-                                        float(vadd), 0, ws.data_ptr(), verts.data_ptr(), cap[0], faces.data_ptr(), cap[1], st),
+                                        float(vadd), 0, w.ws.data_ptr(), verts.data_ptr(), cap[0], faces.data_ptr(), cap[1], st),
                 "smb_mc_emit_bounded",
             )
             if on_launched is not None:  # e.g. a CUDA event: the kernels are queued, the host has not synchronised yet
                 on_launched()
-            counts_pin.copy_(counts_dev, non_blocking=True)
+            w.counts_pin.copy_(w.counts_dev, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-        pend = McPending(grid, float(sub), float(sign), True, int(counts_pin[0]), int(counts_pin[1]), int(counts_pin[2]))
+        c = w.counts_pin
+        pend = McPending(grid, float(sub), float(sign), True, int(c[0]), int(c[1]), int(c[2]), w, w.generation)
         if pend.nverts <= cap[0] and pend.ntris <= cap[1]:
             verts, faces = verts[: pend.nverts], faces[: pend.ntris]
         else:  # the surface grew past the remembered capacity: emit again at the exact size
@@ -391,6 +447,103 @@ def mc_extract(
         for k in list(_mc_caps)[:-8]:
             del _mc_caps[k]
     return verts, faces, pend
+
+
+# ------------------------------------------------------ whole path, one C call
+class MeshExtractor:
+    """``smb_extractor`` handle for one decoder on one device: the device-resident whole path of
+    TSR.extract_mesh (tsr/system.py:173-189) as ONE C call per scene code (``smb_extract_mesh_device``) --
+    prepare, lattice query with the sign ballot, count, totals and emit are queued back to back by the library,
+    so no Python runs between the launches.  Output tensors are allocated here per call (the caller owns them);
+    their capacity is remembered per resolution from the previous mesh (+25 %), and an overflow repeats only
+    the emit."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], radius: float, density_bias: float,
+                 Hp: int, Wp: int, device: torch.device) -> None:
+        lib = _capi.load()
+        ws = [w.detach().to(device="cpu", dtype=torch.float32).contiguous() for w in weights]
+        bs = [b.detach().to(device="cpu", dtype=torch.float32).contiguous() for b in biases]
+        fpp = ctypes.POINTER(ctypes.c_float)
+        W = (fpp * len(ws))(*[ctypes.cast(w.data_ptr(), fpp) for w in ws])
+        B = (fpp * len(bs))(*[ctypes.cast(b.data_ptr(), fpp) for b in bs])
+        self.device = device
+        self.radius = float(radius)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.smb_extractor_create(W, B, len(ws) - 1, float(radius), float(density_bias), int(Hp), int(Wp), ctypes.byref(self._h)), "smb_extractor_create")
+        self._axis_set = set()
+        self._caps: Dict[int, Tuple[int, int]] = {}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            try:
+                _capi.load().smb_extractor_destroy(self._h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+            self._h = None
+
+    __del__ = close
+
+    def extract(self, triplane: torch.Tensor, resolution: int, threshold: float, faces_dtype: torch.dtype = torch.int64,
+                axis_u: Optional[torch.Tensor] = None, want_density: bool = False):
+        """-> (v_pos (V,3) fp32 in (-radius, radius), t_pos_idx (F,3) ``faces_dtype``[, density_act (R,R,R)]) on the device.
+        Raises ValueError / RuntimeError like skimage for an iso level outside the data range / an empty surface."""
+        _require_cuda(triplane, "triplane")
+        if faces_dtype not in (torch.int64, torch.int32):
+            raise ValueError("faces_dtype must be torch.int64 (the reference's LongTensor) or torch.int32")
+        lib = _capi.load()
+        dev = triplane.device
+        R = int(resolution)
+        tp = triplane.detach().to(torch.float32).contiguous()
+        fpp = ctypes.POINTER(ctypes.c_float)
+        with torch.cuda.device(dev):
+            if axis_u is not None and R not in self._axis_set:
+                # coordinates built with the reference's own torch ops (smb_lattice_axis_host restates them bit for bit;
+                # passing them keeps that true on a host whose aten rounds differently)
+                a = axis_u.detach().to("cpu", torch.float32).contiguous()
+                check(lib.smb_extractor_set_axis(self._h, R, ctypes.cast(a.data_ptr(), fpp)), "smb_extractor_set_axis")
+                self._axis_set = {R}
+            vcap, fcap = self._caps.get(R, (0, 0))
+            flags = _capi.MC_FACES_I32 if faces_dtype == torch.int32 else 0
+            dens = torch.empty((R, R, R), dtype=torch.float32, device=dev) if want_density else None
+            nv, nt = ctypes.c_int64(), ctypes.c_int64()
+            emit_only = 0
+            while True:
+                verts = torch.empty((vcap, 3), dtype=torch.float32, device=dev)
+                faces = torch.empty((fcap, 3), dtype=faces_dtype, device=dev)
+                rc = lib.smb_extract_mesh_device(self._h, tp.data_ptr(), R, float(threshold), flags, _ptr(verts) if vcap else None, vcap,
+                                                 _ptr(faces) if fcap else None, fcap, _ptr(dens), emit_only, _stream_ptr(dev),
+                                                 ctypes.byref(nv), ctypes.byref(nt))
+                if rc != _capi.ERR_CAPACITY:
+                    break
+                vcap, fcap, emit_only = max(vcap, nv.value * 5 // 4 + 1024), max(fcap, nt.value * 5 // 4 + 1024), 1
+        if rc == _capi.ERR_LEVEL_RANGE:
+            raise ValueError("Surface level must be within volume data range.")
+        if rc == _capi.ERR_NO_SURFACE:
+            raise RuntimeError("No surface found at the given iso value.")
+        check(rc, "smb_extract_mesh_device")
+        self._caps[R] = (max(vcap, nv.value * 5 // 4 + 1024), max(fcap, nt.value * 5 // 4 + 1024))
+        if len(self._caps) > 4:
+            self._caps.pop(next(iter(self._caps)))
+        out = (verts[: nv.value], faces[: nt.value])
+        return out + (dens,) if want_density else out
+
+
+_extractor_cache: "weakref.WeakKeyDictionary[torch.nn.Module, Dict[Tuple, MeshExtractor]]" = weakref.WeakKeyDictionary()
+
+
+def get_mesh_extractor(decoder: torch.nn.Module, radius: float, density_bias: float, Hp: int, Wp: int, device: torch.device) -> MeshExtractor:
+    """One MeshExtractor per (decoder parameters, plane size, device), rebuilt when a parameter changes."""
+    ws, bs = decoder_params(decoder)
+    key = _param_key((*ws, *bs), device) + (float(radius), float(density_bias), int(Hp), int(Wp))
+    slot = _extractor_cache.setdefault(decoder, {})
+    ex = slot.get("ex")
+    if ex is None or slot.get("key") != key:
+        if ex is not None:
+            ex.close()
+        ex = MeshExtractor(ws, bs, radius, density_bias, Hp, Wp, device)
+        slot["ex"], slot["key"] = ex, key
+    return ex
 
 
 def mc_cases(grid: torch.Tensor, sub: float = 0.0, sign: float = 1.0) -> torch.Tensor:

@@ -33,7 +33,7 @@ import numpy as np
 import torch
 
 from .. import runtime
-from .._capi import MC_AFFINE, MC_DIV, MC_FLIP
+from .._capi import MC_AFFINE, MC_DIV, MC_FACES_I32, MC_FLIP
 from . import blender_io
 from .models.isosurface import MarchingCubeHelper
 from .models.nerf_renderer import TriplaneNeRFRenderer
@@ -63,6 +63,8 @@ class TSR(BaseModule):
         # where extract_mesh delivers each mesh; the reference calls bpy here
         self.mesh_sink: Optional[Callable] = None
         self.meshes: List[Tuple[np.ndarray, np.ndarray, Optional[np.ndarray], str]] = []
+        # index dtype of the faces handed to the sink: int64 like the reference's LongTensor, or int32 (Blender's width)
+        self.face_index_dtype = torch.int64
 
     # ------------------------------------------------------------------ API
     def set_marching_cubes_resolution(self, resolution: int):
@@ -87,42 +89,70 @@ class TSR(BaseModule):
         return self._axis_cache[key]
 
     def extract_mesh_tensors(
-        self, scene_code: torch.Tensor, resolution: int, threshold: float, precision: str = "tc"
+        self, scene_code: torch.Tensor, resolution: int, threshold: float, precision: str = "tc",
+        faces_dtype: torch.dtype = torch.int64,
     ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """One scene code -> (v_pos (V,3) fp32 in (-radius,radius), t_pos_idx (F,3) int64), on device."""
+        """One scene code -> (v_pos (V,3) fp32 in (-radius,radius), t_pos_idx (F,3) int64), on device.
+
+        ``precision="tc"`` (default): the whole path is ONE call into the C library (``smb_extract_mesh_device``:
+        prepare -> tcgen05 lattice kernel that also ballots the cube-case bits -> count -> totals -> emit queued back
+        to back), so no Python runs between the launches.  ``"fp32"``: reference-precision CUDA-core lattice kernel +
+        the stand-alone classification pass (parity anchor).  ``faces_dtype=torch.int32`` delivers the same indices
+        at the width Blender's loop arrays use."""
+        runtime._require_cuda(scene_code, "scene_code")
         self.set_marching_cubes_resolution(resolution)
         R = resolution
         radius = self.renderer.cfg.radius
-        # helper(-(density - threshold)) then level = -input  ==  val = density - threshold; the tensor-core
-        # lattice kernel ballots the case bits while the densities are in registers (no classification pass)
-        fused = precision == "tc"
+        if precision == "tc":
+            self.renderer._check_supported()
+            ex = runtime.get_mesh_extractor(
+                self.decoder, radius, self.renderer.cfg.density_bias, int(scene_code.shape[-2]), int(scene_code.shape[-1]), scene_code.device
+            )
+            with torch.no_grad():
+                return ex.extract(scene_code, R, float(threshold), faces_dtype=faces_dtype, axis_u=self._axis(R, scene_code.device))
+        # helper(-(density - threshold)) then level = -input  ==  val = density - threshold
         with torch.no_grad():
             density = self.renderer.query_lattice(
                 self.decoder, scene_code, R, axis_u=self._axis(R, scene_code.device), precision=precision,
-                mc_signs=(float(threshold), 1.0) if fused else None,
             )
+        flags = MC_FLIP | MC_DIV | MC_AFFINE | (MC_FACES_I32 if faces_dtype == torch.int32 else 0)
         v_pos, t_pos_idx, pend = runtime.mc_extract(
-            density, sub=float(threshold), sign=1.0, flags=MC_FLIP | MC_DIV | MC_AFFINE,
-            vdiv=float(R - 1.0), vmul=float(radius - (-radius)), vadd=float(-radius), presigned=fused,
+            density, sub=float(threshold), sign=1.0, flags=flags,
+            vdiv=float(R - 1.0), vmul=float(radius - (-radius)), vadd=float(-radius),
         )
         if pend.nverts == 0 or pend.ntris == 0:
             runtime.raise_for_empty_surface(density, float(threshold), 1.0)
         return v_pos, t_pos_idx
 
     def extract_mesh(self, scene_codes, enable_texture=False, mesh_name="NewMesh", resolution: int = 256, threshold: float = 25.0):
+        """system.py:171-200: per scene code, mesh -> (optional colour query at the vertices) -> sink, which receives
+        numpy arrays like the reference's ``import_obj_blender`` does.  The device->host copies go through pinned
+        memory (torch's caching host allocator), all queued before ONE synchronisation, instead of the reference's
+        pageable ``.cpu().numpy()`` per array; ``face_index_dtype = torch.int32`` hands the sink the index width
+        Blender stores (a third less PCIe traffic), the default int64 is the reference's LongTensor."""
         for scene_code in scene_codes:
-            v_pos, t_pos_idx = self.extract_mesh_tensors(scene_code, resolution, threshold)
-            color = None
-            extra = {}
+            v_pos, t_pos_idx = self.extract_mesh_tensors(scene_code, resolution, threshold, faces_dtype=self.face_index_dtype)
+            staged = [self._stage(v_pos), self._stage(t_pos_idx)]
+            extra_staged = None
             if enable_texture:
                 with torch.no_grad():
                     color = self.renderer.query_triplane(self.decoder, v_pos, scene_code, precision="tc")["color"]
+                staged.append(self._stage(color))
                 if self._sink_takes_loop_colors():
                     # the per-loop RGBA array the reference builds element by element (system.py:133-146),
                     # gathered on the GPU for sinks that foreach_set it (tsr/blender_io.py)
-                    extra["loop_colors"] = blender_io.loop_colors(color, t_pos_idx).cpu().numpy()
-                color = color.cpu().numpy()
-            self.import_obj_blender(v_pos.cpu().numpy(), t_pos_idx.cpu().numpy(), color, name=mesh_name, **extra)
+                    extra_staged = self._stage(blender_io.loop_colors(color, t_pos_idx.long()))
+            torch.cuda.current_stream(v_pos.device).synchronize()
+            extra = {} if extra_staged is None else {"loop_colors": extra_staged.numpy()}
+            color_np = staged[2].numpy() if enable_texture else None
+            self.import_obj_blender(staged[0].numpy(), staged[1].numpy(), color_np, name=mesh_name, **extra)
+
+    @staticmethod
+    def _stage(t: torch.Tensor) -> torch.Tensor:
+        """Asynchronous device -> pinned-host copy; the caller synchronises once for all staged arrays."""
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        return h
 
     def _sink_takes_loop_colors(self) -> bool:
         if self.mesh_sink is None:

@@ -76,7 +76,7 @@ def test_fused_sign_masks_equal_the_classification_pass(golden, R):
     dens0 = m.renderer.query_lattice(m.decoder, tp, R)
     thr = float(dens0.median())
     nwords = R * R * ((R + 31) // 32)
-    ws = runtime._mc_cache.get(dens0.device, (R, R, R))[0]
+    ws = runtime._mc_cache.get(dens0.device, (R, R, R)).ws
     dens = m.renderer.query_lattice(m.decoder, tp, R, mc_signs=(thr, 1.0))
     torch.cuda.synchronize()
     fused = ws[: 4 * nwords].clone().view(torch.int32)
@@ -135,13 +135,11 @@ def test_capi_host_extractor_matches_python_path(golden):
         f = np.ctypeslib.as_array(fp_, shape=(nt.value, 3)).copy()
         m = _model(g)
         v2, f2 = m.extract_mesh_tensors(torch.from_numpy(tp).cuda(), R, thr)
-        # the C host computes lattice coordinates with the scalar linspace formula (<= 2 ulp from
-        # aten's); through the fp16-operand MLP that moves density by up to the stated fp16 tolerance,
-        # so vertices may slide along their edges: same connectivity here, verts within 0.2 cell
-        cell = 2 * RADIUS / (R - 1)
-        assert f.shape == tuple(f2.shape) and np.array_equal(f, f2.cpu().numpy())
-        assert np.abs(v - v2.cpu().numpy()).max() < 0.2 * cell
-        # with the host's torch-built coordinates the C path is bit-identical to the Python drop-in
+        # the C host restates aten's linspace exactly (smb_lattice_axis_host), so without any help from torch the
+        # C path is bit-identical to the Python drop-in
+        np.testing.assert_array_equal(f, f2.cpu().numpy())
+        np.testing.assert_array_equal(v, v2.cpu().numpy())
+        # and stays so when the host supplies torch-built coordinates
         from sculptmate_b200 import runtime
 
         axis = np.ascontiguousarray(runtime.lattice_axis(R, RADIUS).numpy())
