@@ -181,30 +181,65 @@ def workload_config(args, world: int):
             "l2": "inputs rotated + 256 MiB L2 flush between steps"}
 
 
+# ------------------------------------------------------------------ helpers
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
+    (first touch then places the staging buffers on that node).  With 8 ranks all on node 0 the device->host copies
+    of the ranks whose GPUs sit on the other socket cross the inter-socket link (round 1: e2e efficiency 0.60 at N=8)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index(local_rank))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "note": "no NUMA affinity reported for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"node": None, "note": f"not bound ({type(e).__name__})"}
+
+
+def pct(xs):
+    xs = np.asarray(xs, dtype=np.float64)
+    return {"p10": float(np.percentile(xs, 10)), "p50": float(np.percentile(xs, 50)), "p90": float(np.percentile(xs, 90)), "max": float(xs.max())}
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
 # ------------------------------------------------------------------ SF3D (configs[4])
-def run_sf3d(args) -> int:
-    """One step = SF3D.triplane_to_meshes on one synthetic 3x40x384x384 triplane per GPU (independent
-    objects: weak scaling).  Tet grid: Kuhn grid of tet_n^3 cubes (the reference's blob is missing)."""
+def sf3d_measure(dev, rank: int, world: int, steps: int, warmup: int, tet_n: int, with_cpu: bool, cpu_seconds: float = 6.0):
+    """One step = SF3D.triplane_to_meshes on one synthetic 3x40x384x384 triplane per GPU (independent objects: weak
+    scaling).  Tet grid: Kuhn grid of tet_n^3 cubes (the reference's 160_tets.npz blob is missing).  Returns the
+    dict that is printed as the sf3d line / embedded as ``sf3d`` in the default line."""
     import tempfile
 
     import torch.distributed as dist
 
-    from sculptmate_b200 import _capi, runtime
-    from sculptmate_b200.sf3d import SF3D, save_tet_grid
+    from sculptmate_b200 import runtime
+    from sculptmate_b200.sf3d import SF3D, kuhn_tet_grid, save_tet_grid
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    _capi.check(_capi.load().smb_device_check(), "smb_device_check")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n = args.tet_n
+    n = tet_n
     path = save_tet_grid(os.path.join(tempfile.mkdtemp(), f"tets{n}.npz"), n)
     torch.manual_seed(0)
     m = SF3D(dict(isosurface_resolution=n, radius=RADIUS, tets_path=path)).to(dev)
-    scenes = [baked_triplane(200 + rank * 2 + s, 384, 384).to(dev) for s in range(2)]
+    host_tp = [baked_triplane(200 + rank * 2 + s, 384, 384).pin_memory() for s in range(2)]
+    scenes = [t.to(dev) for t in host_tp]
     h = m.isosurface_helper
     h.topology(dev)  # static index arrays, built once (the reference caches all_edges the same way)
     pos = m._positions(dev)
@@ -214,19 +249,18 @@ def run_sf3d(args) -> int:
         d = runtime.sf3d_query(runtime.prepare_planes_cl(tp), heads, -1.0, RADIUS, positions=pos, want=("density_act",))["density_act"]
         thr.append(float(d.median()))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def step(i):
         m.cfg.isosurface_threshold = thr[i % 2]
         return m.triplane_to_meshes(scenes[i % 2][None])[0]
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     rec = []
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(i & 0xFF)
         a, b = ev(), ev()
         a.record()
@@ -234,25 +268,182 @@ def run_sf3d(args) -> int:
         b.record()
         rec.append((a, b))
     torch.cuda.synchronize()
-    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in rec)], device=dev, dtype=torch.float64)
+    step_ms = [a.elapsed_time(b) for a, b in rec]
+    # the dominant kernel alone (K3: gather + both heads on tcgen05, fp16 planes), CUDA events on the launching stream
+    tcp = runtime.get_sf3d_points_pack(m.decoder, dev)
+    kq = []
+    for i in range(steps + 2):
+        flush.fill_(i & 0xFF)
+        planes = runtime.prepare_planes_half(scenes[i % 2])
+        a, b = ev(), ev()
+        a.record()
+        runtime.query_points_tc(planes, tcp, pos, RADIUS, -1.0, align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"))
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            kq.append(a.elapsed_time(b))
+    # e2e through the Python API the reference calls (sf3d/system.py:141-168): triplane in pinned host memory in,
+    # mesh in pinned host memory out, copies inside the timed region
+    stage_in = torch.empty_like(scenes[0])
+    e2e_s, d2h = 0.0, 0
+    for i in range(steps + 2):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stage_in.copy_(host_tp[i % 2], non_blocking=True)
+        m.cfg.isosurface_threshold = thr[i % 2]
+        me = m.triplane_to_meshes(stage_in[None])[0]
+        hv = torch.empty(me.v_pos.shape, dtype=me.v_pos.dtype, pin_memory=True)
+        hf = torch.empty(me.t_pos_idx.shape, dtype=me.t_pos_idx.dtype, pin_memory=True)
+        hv.copy_(me.v_pos, non_blocking=True)
+        hf.copy_(me.t_pos_idx, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if i >= 2:
+            e2e_s += time.perf_counter() - t0
+            d2h = hv.numel() * 4 + hf.numel() * 8
+    stats = torch.tensor([sum(step_ms), e2e_s * 1e3, float(np.mean(kq))], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kq_ms = [float(x) for x in stats.tolist()]
+    nv = int(h.grid_vertices.shape[0])
+    ms = total_ms / steps
+    peaks, peak_kind = measured_peaks()
+    sf3d_flop = 2 * (2 * 120 * 64 + 2 * 64 * 64 + 64 * 1 + 64 * 3)  # 47616: both MaterialMLP heads
+    ach = sf3d_flop * nv / (kq_ms * 1e-3) / 1e12
+    out = {
+        "metric": "sf3d_triplane_to_meshes_grid_vertices_per_s", "value": nv * world / (ms * 1e-3), "unit": "pts/s", "n_gpus": world,
+        "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms, "ms_per_step_pct": pct(step_ms), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (query + heads); f32 / int32 marching tets", "data": "synthetic",
+        "config": {"workload": f"SF3D triplane_to_meshes (BASELINE configs[4]): 3x40x384x384 triplane, MaterialMLP density+vertex_offset heads, "
+                               f"marching tets on a Kuhn grid n={n} (Nv={nv}, Nt={int(h.indices.shape[0])}); reference blob 160_tets.npz missing",
+                   "parallelism": f"dp{world}", "l2": "inputs rotated + 256 MiB L2 flush between steps"},
+        "mesh": {"verts": int(mesh.v_pos.shape[0]), "tris": int(mesh.t_pos_idx.shape[0])},
+        "e2e": {"value": nv * world / (e2e_ms / steps * 1e-3), "unit": "pts/s", "ms_per_step": e2e_ms / steps, "h2d_bytes_per_step": int(host_tp[0].numel() * 4),
+                "d2h_bytes_per_step": int(d2h), "api": "SF3D.triplane_to_meshes (Python drop-in); triplane from pinned host memory, mesh to pinned host memory"},
+        "roofline": {"kernel": "points_tc_kernel (gather + both heads on tcgen05, fp16 planes)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": f"{peak_kind} (burst)", "kernel_ms": kq_ms,
+                     "flop_per_point": sf3d_flop, "note": "gather-bound in practice (12 taps x 40 channels per point from L2-resident planes)"},
+        "gpu_launches": 8 * steps * world,
+    }
+    if with_cpu and rank == 0:
+        # the reference's CPU path for this config, restated (oracle/sf3d_oracle.py: query_triplane align_corners=True ->
+        # MaterialMLP heads -> marching tetrahedra), on a bounded sample: a smaller Kuhn grid of the same workload
+        from oracle import sf3d_oracle as so
+
+        ns = 40
+        verts, tets = kuhn_tet_grid(ns)
+        sd = {k: v.detach().cpu().numpy() for k, v in m.decoder.state_dict().items()}
+        tpn = host_tp[0].numpy()
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < cpu_seconds or reps == 0:
+            so.triplane_to_mesh(tpn, sd, verts, tets, ns, thr[0])
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {"value": verts.shape[0] / dt, "unit": "pts/s", "cores": 1, "kind": "port",
+                               "sample": f"oracle/sf3d_oracle.triplane_to_mesh (numpy) on a Kuhn grid n={ns} ({verts.shape[0]} vertices, {tets.shape[0]} tets), {reps} reps, {dt:.2f} s each"}
+    return out
+
+
+def run_sf3d(args) -> int:
+    import torch.distributed as dist
+
+    from sculptmate_b200 import _capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _capi.check(_capi.load().smb_device_check(), "smb_device_check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    out = sf3d_measure(dev, rank, world, args.steps, args.warmup, args.tet_n, with_cpu=not args.no_cpu_baseline and world == 1)
     if rank == 0:
-        nv = int(h.grid_vertices.shape[0])
-        ms = float(total_ms.item()) / args.steps
-        print(json.dumps({
-            "metric": "sf3d_triplane_to_meshes_grid_vertices_per_s", "value": nv * world / (ms * 1e-3), "unit": "pts/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (query + heads); f32 / int32 marching tets", "data": "synthetic",
-            "config": {"workload": f"SF3D triplane_to_meshes (BASELINE configs[4]): 3x40x384x384 triplane, MaterialMLP density+vertex_offset heads, "
-                                   f"marching tets on a Kuhn grid n={n} (Nv={nv}, Nt={int(h.indices.shape[0])}); reference blob 160_tets.npz missing",
-                       "parallelism": f"dp{world}", "l2": "inputs rotated + 256 MiB L2 flush between steps"},
-            "mesh": {"verts": int(mesh.v_pos.shape[0]), "tris": int(mesh.t_pos_idx.shape[0])},
-            "gpu_launches": 8 * args.steps * world,
-        }))
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+# ------------------------------------------------------------------ 512^3 x-slab strong scaling (configs[2])
+def sharded_measure(model, dev, rank: int, world: int, R: int, steps: int, warmup: int):
+    """T(1) on rank 0 through the best single-GPU path (TSR.extract_mesh_tensors), then T(N) with the lattice cut into
+    x-slabs over the ranks -- triplane broadcast INSIDE the timed region, mesh gathered on rank 0 by the emit kernels'
+    NVLink peer stores -- and the bit-exact comparison of the two meshes at this resolution.  Collective: every rank
+    calls it."""
+    import torch.distributed as dist
+
+    from sculptmate_b200.dist import extract_mesh_sharded
+
+    n_rot = 2
+    seeds = [300 + s for s in range(n_rot)]
+    real = [baked_triplane(s).to(dev) for s in seeds]  # every rank can build them, but only rank 0's copy is used:
+    work = [t.clone() if rank == 0 else torch.zeros_like(t) for t in real]  # the others receive the scene by broadcast
+    thr = torch.zeros(n_rot, dtype=torch.float64, device=dev)
+    if rank == 0:
+        for i, tp in enumerate(real):
+            thr[i] = float(model.renderer.query_lattice(model.decoder, tp, 128).median())
+    dist.broadcast(thr, src=0)
+    thr = [float(x) for x in thr.tolist()]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # ---- T(1): rank 0 alone
+    t1_ms, ref = [], None
+    if rank == 0:
+        for i in range(2 + steps):
+            flush.fill_(i & 0xFF)
+            a, b = ev(), ev()
+            a.record()
+            v1, f1 = model.extract_mesh_tensors(real[i % n_rot], R, thr[i % n_rot])
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                t1_ms.append(a.elapsed_time(b))
+            if i % n_rot == 0:
+                ref = (v1, f1)
+        del v1, f1
+    dist.barrier()
+    # ---- T(N)
+    tn_ms, phases, exact, nV, nF = [], {}, None, 0, 0
+    for i in range(max(warmup, 3) + steps):
+        timed = i >= max(warmup, 3)
+        k = i % n_rot
+        if rank != 0:
+            work[k].zero_()  # the scene really arrives by the broadcast of this step
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ph = {} if (timed and i == max(warmup, 3) + steps - 1) else None
+        a, b = ev(), ev()
+        a.record()
+        v, f = extract_mesh_sharded(model, work[k], R, thr[k], broadcast=True, phases=ph)
+        b.record()
+        torch.cuda.synchronize()
+        if timed:
+            tn_ms.append(a.elapsed_time(b))
+        if ph is not None:
+            names = ["start", "scene", "lattice", "count", "emit", "gathered", "end"]
+            have = [n for n in names if n in ph]
+            phases = {f"{x}->{y}": ph[x].elapsed_time(ph[y]) for x, y in zip(have[:-1], have[1:])}
+        if rank == 0 and k == 0 and exact is None and i >= 1:
+            exact = bool(v.shape == ref[0].shape and f.shape == ref[1].shape and torch.equal(v, ref[0]) and torch.equal(f, ref[1]))
+            nV, nF = int(v.shape[0]), int(f.shape[0])
+    stats = torch.tensor([sum(tn_ms)], device=dev, dtype=torch.float64)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    lat = torch.tensor([phases.get("scene->lattice", 0.0)], device=dev, dtype=torch.float64)
+    dist.all_reduce(lat, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    tN = float(stats.item()) / steps
+    t1 = float(np.mean(t1_ms))
+    return {
+        "workload": f"TripoSR extract_mesh {R}^3, ONE lattice cut into x-slabs over {world} GPUs (BASELINE configs[2]); T(1) = the same scene through TSR.extract_mesh_tensors on rank 0",
+        "resolution": R, "n_gpus": world, "steps": steps, "t1_ms": t1, "t1_ms_pct": pct(t1_ms), "tN_ms": tN, "tN_ms_pct": pct(tn_ms), "speedup": t1 / tN,
+        "points_per_s": float(R) ** 3 / (tN * 1e-3), "scaling": "strong", "bit_exact_vs_1gpu": exact, "mesh": {"verts": nV, "tris": nF},
+        "transport": "emit kernels store vertices + int32 faces into rank 0's buffers over NVLink peer memory (CUDA IPC); counts / completion by peer-memory flags, no collective on the data path; NCCL broadcast of the triplane inside the timed region",
+        "phases_ms_rank0_last_step": phases, "lattice_ms_max_over_ranks": float(lat.item()),
+        "timing": "CUDA events on each rank's stream around the whole call (broadcast -> mesh resident on rank 0), barrier before every step, max over ranks of the sum",
+    }
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -265,8 +456,11 @@ def main() -> int:
     ap.add_argument("--resolution", type=int, default=None)
     ap.add_argument("--mode", default="dp", choices=["dp", "sharded", "sf3d"])
     ap.add_argument("--batch", type=int, default=1, help="scene codes per GPU per step in dp mode (configs[3]: 8 per GPU on 8 GPUs)")
-    ap.add_argument("--tet-n", type=int, default=160, help="sf3d mode: Kuhn tet grid of n^3 cubes (the reference's 160_tets.npz blob is missing)")
+    ap.add_argument("--tet-n", type=int, default=160, help="sf3d: Kuhn tet grid of n^3 cubes (the reference's 160_tets.npz blob is missing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sf3d", action="store_true", help="skip the embedded SF3D (configs[4]) measurement of the default N=1 line")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the embedded 512^3 x-slab block of N>1 lines")
+    ap.add_argument("--sharded-steps", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.mode == "sf3d" and args.impl == "ours":
@@ -284,11 +478,11 @@ def main() -> int:
     import torch.distributed as dist
 
     from sculptmate_b200 import _capi, runtime
-    from sculptmate_b200.dist import extract_mesh_sharded
     from sculptmate_b200.tsr import TSR
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _capi.check(_capi.load().smb_device_check(), "smb_device_check")
@@ -299,82 +493,82 @@ def main() -> int:
     R = args.resolution
     torch.manual_seed(0)
     model = TSR().to(dev)  # random-init NeRFMLP, seed 0 on every rank
-    n_rot = 4
+    # nvidia-smi is started first: its start-up takes driver locks for tens of ms and must not land in a timed region
+    sampler = ClockSampler(gpu_index(local_rank)) if rank == 0 and not os.environ.get("SMB_BENCH_NO_SAMPLER") else None
+
     if args.mode == "sharded":
-        seeds = [100 + s for s in range(n_rot)]  # same scene on every rank
-    else:
-        n_rot = max(n_rot, args.batch)
-        seeds = [100 + rank * n_rot + s for s in range(n_rot)]
+        # BASELINE configs[2] as the line's own metric (strong scaling)
+        if world == 1:
+            raise SystemExit("--mode sharded needs torchrun with N > 1 (the N = 1 reference is measured inside the same run)")
+        blk = sharded_measure(model, dev, rank, world, R, args.steps, args.warmup)
+        clocks = sampler.stop() if sampler is not None else None
+        if rank == 0:
+            line = {
+                "metric": "extract_mesh_lattice_points_per_s", "value": blk["points_per_s"], "unit": "pts/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": blk["tN_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 operands, f32 accumulate (layer 0 and head bias/exp in f32)", "data": "synthetic", "config": workload_config(args, world),
+                "clocks": clocks, "sharded_512": blk, "gpu_launches": 9 * args.steps * world,
+            }
+            print(json.dumps(line))
+        dist.destroy_process_group()
+        return 0
+
+    n_rot = max(4, args.batch)
+    seeds = [100 + rank * n_rot + s for s in range(n_rot)]
     scenes = [baked_triplane(s).to(dev) for s in seeds]
     thresholds = []
     for tp in scenes:  # setup, untimed: data-dependent threshold (median)
         d = model.renderer.query_lattice(model.decoder, tp, min(R, 128))
         thresholds.append(float(d.median()))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    extractor = runtime.get_mesh_extractor(model.decoder, RADIUS, -1.0, 64, 64, dev)
+    extractor.enable_timing(True)  # CUDA events around the dominant kernel inside the public call
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    pack = runtime.get_decoder_pack(model.decoder, dev)
-    model.set_marching_cubes_resolution(R)
-    axis = model._axis(R, dev)
-
-    def step(i, record=None):
-        tp, thr = scenes[i % n_rot], thresholds[i % n_rot]
-        if args.mode == "sharded":
-            e0, e1 = ev(), ev()
-            e0.record()
-            v, f = extract_mesh_sharded(model, tp, R, thr, broadcast=False)
-            e1.record()
-            if record is not None:
-                record.append((e0, e1, None, None, None))
-            return v, f
-        e0, k0, k1, k2, e1 = ev(), ev(), ev(), ev(), ev()
-        e0.record()
-        for b in range(args.batch):  # serial over the batch like the reference (system.py:173)
-            tp, thr = scenes[(i + b) % n_rot], thresholds[(i + b) % n_rot]
-            scene = runtime.prepare_scene(tp, pack, want_cl=False, want_q=True)
-            if b == 0:
-                k0.record()
-            dens = runtime.query_lattice(scene, pack, axis, R, RADIUS, -1.0, mc_signs=(thr, 1.0))  # case bits balloted in-kernel
-            if b == 0:
-                k1.record()
-            v, f, _ = runtime.mc_extract(dens, sub=thr, sign=1.0, flags=7, vdiv=float(R - 1.0), vmul=float(RADIUS - (-RADIUS)), vadd=float(-RADIUS),
-                                         presigned=True, on_launched=k2.record if b == 0 else None)
-        e1.record()
-        if record is not None:
-            record.append((e0, e1, k0, k1, k2))
+    def step(i):
+        """The PUBLIC device-resident path: TSR.extract_mesh_tensors per scene code, serial over the batch like the
+        reference (system.py:173)."""
+        for b in range(args.batch):
+            v, f = model.extract_mesh_tensors(scenes[(i + b) % n_rot], R, thresholds[(i + b) % n_rot])
         return v, f
 
-    # nvidia-smi is started BEFORE the warm-up: its start-up takes driver locks for tens of ms and must not land in the
-    # timed region (it keeps sampling through it).  The warm-up visits every rotated scene once, so that no per-shape
-    # capacity (speculative emit buffers) is learnt inside the timed region.
-    sampler = ClockSampler(gpu_index(local_rank)) if rank == 0 else None
-    args.warmup = max(args.warmup, n_rot)
+    # the warm-up visits every rotated scene once, so that no per-resolution capacity (speculative emit buffers) is
+    # learnt inside the timed region
+    # ... and it keeps the previous step's mesh alive while the next one is produced, exactly like the timed loop below:
+    # torch's caching allocator then already owns BOTH sets of output blocks.  (Round 1's "one 25-100 ms step" was this:
+    # the second timed step was the first to need a second set -> cudaMalloc + implicit device synchronisation inside
+    # the timed region, always at step index 1.)
+    args.warmup = max(args.warmup, n_rot + 1)
+    v = f = None
     for i in range(args.warmup):
-        step(i)
+        v, f = step(i)
     torch.cuda.synchronize()
-    rec = []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    rec, kern_ms, mc_ms, prep_ms = [], [], [], []
     nV = nF = 0
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # L2 flush between timed steps (outside the event pairs)
-        v, f = step(i, rec)
-        if v is not None:
-            nV, nF = int(v.shape[0]), int(f.shape[0])
+        e0, e1 = ev(), ev()
+        e0.record()
+        v, f = step(i)
+        e1.record()
+        rec.append((e0, e1))
+        a, b, c = extractor.last_timing()  # the call above synchronised: events of its last scene code are complete
+        prep_ms.append(a)
+        kern_ms.append(b)
+        mc_ms.append(c)
+        nV, nF = int(v.shape[0]), int(f.shape[0])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    step_ms = [r[0].elapsed_time(r[1]) for r in rec]
+    step_ms = [a.elapsed_time(b) for a, b in rec]
     total_ms = float(sum(step_ms))
-    kern_ms = [k0.elapsed_time(k1) for _, _, k0, k1, _ in rec if k0 is not None]
-    # marching cubes on the device (count + totals + emit, launch gaps included) / the same up to the host knowing the sizes
-    mc_ms = [k1.elapsed_time(k2) for _, _, k0, k1, k2 in rec if k0 is not None] if args.batch == 1 else []
-    mc_host_ms = [k1.elapsed_time(e1) for _, e1, k0, k1, _ in rec if k0 is not None] if args.batch == 1 else []
 
-    # ---- e2e: C-ABI host-buffer call (H2D triplane, D2H mesh inside the timed region)
-    e2e_s, h2d, d2h = None, 0, 0
-    if args.mode == "dp" and args.batch == 1:
+    # ---- e2e (1): C-ABI host-buffer call (H2D triplane, D2H mesh inside the timed region); (2) the Python API
+    e2e, e2e_py, e2e_i32 = None, None, None
+    h2d = 0
+    if args.batch == 1:
         lib = _capi.load()
         _, ws, bs = decoder_numpy(0)
         fpp = ctypes.POINTER(ctypes.c_float)
@@ -383,6 +577,7 @@ def main() -> int:
         ex = ctypes.c_void_p()
         _capi.check(lib.smb_extractor_create(W, B, 9, RADIUS, -1.0, 64, 64, ctypes.byref(ex)), "smb_extractor_create")
         host_tp = [np.ascontiguousarray(baked_triplane(s).numpy()) for s in seeds]
+        h2d = host_tp[0].nbytes
         vp, fp_ = fpp(), ctypes.POINTER(ctypes.c_int64)()
         nv, nt = ctypes.c_int64(), ctypes.c_int64()
         # the step's input lives in PINNED host memory (the handle's staging buffer, written before the clock starts);
@@ -391,82 +586,141 @@ def main() -> int:
         _capi.check(lib.smb_extractor_pinned_input(ex, ctypes.byref(pin)), "smb_extractor_pinned_input")
         pin_np = np.ctypeslib.as_array(pin, shape=host_tp[0].shape)
 
-        def e2e_stage(i):
-            np.copyto(pin_np, host_tp[i % n_rot])
+        def e2e_leg(face_bytes):
+            ts, d2h = [], 0
+            for i in range(args.warmup + args.steps):
+                np.copyto(pin_np, host_tp[i % n_rot])
+                flush.fill_(i & 0xFF)
+                torch.cuda.synchronize()
+                if world > 1 and i == args.warmup:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                rc = lib.smb_extract_mesh_host(ex, pin, R, thresholds[i % n_rot], ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
+                dt = time.perf_counter() - t0
+                _capi.check(rc, "smb_extract_mesh_host")
+                if i >= args.warmup:
+                    ts.append(dt * 1e3)
+                    d2h = int(nv.value) * 12 + int(nt.value) * 3 * face_bytes
+            return ts, d2h
 
-        def e2e_step(i):
-            rc = lib.smb_extract_mesh_host(ex, pin, R, thresholds[i % n_rot],
-                                           ctypes.byref(vp), ctypes.byref(fp_), ctypes.byref(nv), ctypes.byref(nt))
-            _capi.check(rc, "smb_extract_mesh_host")
+        ts64, d2h64 = e2e_leg(8)
+        # once: the mesh the host-buffer call returns equals the device-resident path's (same scene, same threshold)
+        i_last = (args.warmup + args.steps - 1) % n_rot
+        vd, fd = model.extract_mesh_tensors(scenes[i_last], R, thresholds[i_last])
+        same = bool(nv.value == vd.shape[0] and nt.value == fd.shape[0]
+                    and np.array_equal(np.ctypeslib.as_array(vp, shape=(nv.value, 3)), vd.cpu().numpy())
+                    and np.array_equal(np.ctypeslib.as_array(fp_, shape=(nt.value, 3)), fd.cpu().numpy()))
+        _capi.check(lib.smb_extractor_set_faces_i32(ex, 1), "smb_extractor_set_faces_i32")
+        ts32, d2h32 = e2e_leg(4)
+        lib.smb_extractor_destroy(ex)
+        e2e = (ts64, d2h64, same)
+        e2e_i32 = (ts32, d2h32)
 
-        for i in range(args.warmup):
-            e2e_stage(i)
-            e2e_step(i)
-        if world > 1:
-            dist.barrier()
-        e2e_s = 0.0
-        for i in range(args.steps):
-            e2e_stage(i)
+        # (2) the Python plugin API the reference's caller uses (generate.py:39 -> system.py:171-200): TSR.extract_mesh with a
+        # sink that receives numpy arrays; the scene code starts in pinned host memory (H2D inside the timed region)
+        got = []
+        model.mesh_sink = lambda verts, faces, colors, name="NewMesh", **kw: got.append((verts.shape[0], faces.shape[0], faces.dtype.itemsize))
+        pin_tp = [torch.from_numpy(t).pin_memory() for t in host_tp]
+        stage = torch.empty_like(scenes[0])
+        tsp, d2hp = [], 0
+        for i in range(args.warmup + args.steps):
             flush.fill_(i & 0xFF)
             torch.cuda.synchronize()
+            if world > 1 and i == args.warmup:
+                dist.barrier()
             t0 = time.perf_counter()
-            e2e_step(i)
-            e2e_s += time.perf_counter() - t0
-            d2h = int(nv.value) * 12 + int(nt.value) * 24
-        h2d = host_tp[0].nbytes
-        lib.smb_extractor_destroy(ex)
+            stage.copy_(pin_tp[i % n_rot], non_blocking=True)
+            model.extract_mesh(stage[None], resolution=R, threshold=thresholds[i % n_rot])
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                tsp.append(dt * 1e3)
+                d2hp = got[-1][0] * 12 + got[-1][1] * 3 * got[-1][2]
+        model.mesh_sink = None
+        e2e_py = (tsp, d2hp)
+
+    # ---- the 512^3 x-slab strong-scaling block (BASELINE configs[2]) rides on every N > 1 line
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        try:
+            sharded = sharded_measure(model, dev, rank, world, 512, args.sharded_steps, 3)
+        except Exception as e:  # noqa: BLE001  (reported, the dp line must still be printed)
+            sharded = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
+    # ---- SF3D (configs[4]) rides on the default N = 1 line
+    sf3d = None
+    if world == 1 and not args.no_sf3d and args.batch == 1:
+        try:
+            sf3d = sf3d_measure(dev, 0, 1, min(args.steps, 10), 3, args.tet_n, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:  # noqa: BLE001
+            sf3d = {"error": f"{type(e).__name__}: {e}"}
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- max over ranks
-    stats = torch.tensor([total_ms, (e2e_s or 0.0) * 1e3, float(np.mean(kern_ms)) if kern_ms else 0.0,
-                          float(np.mean(mc_ms)) if mc_ms else 0.0, float(np.mean(mc_host_ms)) if mc_host_ms else 0.0], device=dev, dtype=torch.float64)
+    def tot(x):
+        return float(sum(x[0])) if x else 0.0
+
+    stats = torch.tensor([total_ms, tot(e2e), tot(e2e_py), tot(e2e_i32), float(np.mean(kern_ms)), float(np.mean(mc_ms)), float(np.mean(prep_ms))],
+                         device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms_avg, mc_ms_avg, mc_host_ms_avg = [float(x) for x in stats.tolist()]
+    total_ms, e2e_ms, e2e_py_ms, e2e_i32_ms, kern_ms_avg, mc_ms_avg, prep_ms_avg = [float(x) for x in stats.tolist()]
 
     if rank == 0:
-        units_per_step = float(R) ** 3 * (1 if args.mode == "sharded" else world * args.batch)
+        units_per_step = float(R) ** 3 * world * args.batch
         value = units_per_step * args.steps / (total_ms * 1e-3)
         peaks, peak_kind = measured_peaks()
+        p = pct(step_ms)
         line = {
             "metric": "extract_mesh_lattice_points_per_s", "value": value, "unit": "pts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.mode == "sharded" else "weak", "vs_baseline": None,
+            "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 accumulate (layer 0 and head bias/exp in f32)", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clocks,
-            "extract_mesh_ms": total_ms / args.steps, "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
+            "config": workload_config(args, world), "clocks": clocks, "numa": numa,
+            "api": "TSR.extract_mesh_tensors (the public device-resident call; one smb_extract_mesh_device per scene code)",
+            "extract_mesh_ms": total_ms / args.steps, "ms_per_step_p10": p["p10"], "ms_per_step_p50": p["p50"], "ms_per_step_p90": p["p90"],
+            "ms_per_step_max": p["max"], "ms_per_step_argmax": int(np.argmax(step_ms)), "unstable": bool(p["max"] > 2.0 * p["p50"]),
             "mesh": {"verts": nV, "tris": nF},
-            "gpu_launches": KERNELS_PER_STEP * args.steps * world * (args.batch if args.mode == "dp" else 1),
+            "gpu_launches": KERNELS_PER_STEP * args.steps * world * args.batch,
         }
-        if e2e_s is not None:
+        if e2e is not None:
             line["e2e"] = {"value": units_per_step * args.steps / (e2e_ms * 1e-3), "unit": "pts/s", "ms_per_step": e2e_ms / args.steps,
-                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "smb_extract_mesh_host (C ABI; triplane in pinned host memory, mesh returned in pinned host memory)"}
-        if kern_ms_avg > 0:
-            flops = FLOP_PER_POINT * float(R) ** 3
-            ach = flops / (kern_ms_avg * 1e-3) / 1e12
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tpath):
-                with open(tpath) as fh:
-                    traffic = json.load(fh).get(f"lattice_tc_kernel_R{R}")
-            line["roofline"] = {
-                "kernel": "lattice_tc_ta_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": f"{peak_kind} (burst)",
-                "kernel_ms": kern_ms_avg, "query_points_per_s": float(R) ** 3 / (kern_ms_avg * 1e-3),
-                "flop_per_point": FLOP_PER_POINT,
-                "note": "algorithmic FLOPs = the reference NeRFMLP count (SURVEY 8d); layer 0 runs as a projected-plane interpolation in fp32, not as an MMA",
-            }
-        if mc_ms_avg > 0 and nV:
+                           "ms_per_step_pct": pct(e2e[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e[1],
+                           "mesh_equals_device_path": e2e[2],
+                           "api": "smb_extract_mesh_host (C ABI; triplane in pinned host memory, mesh returned in pinned host memory, int64 faces like the reference's LongTensor)"}
+            line["e2e_i32_faces"] = {"value": units_per_step * args.steps / (e2e_i32_ms * 1e-3), "unit": "pts/s", "ms_per_step": e2e_i32_ms / args.steps,
+                                     "ms_per_step_pct": pct(e2e_i32[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_i32[1],
+                                     "api": "smb_extract_mesh_host after smb_extractor_set_faces_i32 (the index width Blender stores)"}
+            line["e2e_python"] = {"value": units_per_step * args.steps / (e2e_py_ms * 1e-3), "unit": "pts/s", "ms_per_step": e2e_py_ms / args.steps,
+                                  "ms_per_step_pct": pct(e2e_py[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_py[1],
+                                  "api": "TSR.extract_mesh(scene_codes, resolution, threshold) with a numpy sink (the reference's plugin call, system.py:171-200); pinned non_blocking copies"}
+        flops = FLOP_PER_POINT * float(R) ** 3
+        ach = flops / (kern_ms_avg * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(f"lattice_tc_kernel_R{R}")
+        line["roofline"] = {
+            "kernel": "lattice_tc_ta_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": f"{peak_kind} (burst)",
+            "kernel_ms": kern_ms_avg, "kernel_ms_pct": pct(kern_ms), "query_points_per_s": float(R) ** 3 / (kern_ms_avg * 1e-3),
+            "flop_per_point": FLOP_PER_POINT, "prepare_ms": prep_ms_avg,
+            "timing": "CUDA events recorded by the library on the launching stream around the kernel, inside the timed public call (smb_extractor_enable_timing)",
+            "note": "algorithmic FLOPs = the reference NeRFMLP count (SURVEY 8d); layer 0 runs as a projected-plane interpolation in fp32, not as an MMA",
+        }
+        if nV:
             # marching cubes is HBM-bound: algorithmic bytes = 4 R^3 (density read) + 12 V + 24 F (mesh write),
             # SURVEY 8d; the time spans count + totals + emit on the device (CUDA events on the launching stream)
             mc_bytes = 4.0 * float(R) ** 3 + 12.0 * nV + 24.0 * nF
             line["roofline_mc"] = {
                 "kernels": "mc_count+mc_totals+mc_emit (sign masks come from the lattice kernel; emit launched behind count; the sizes are read back after it)", "bound": "hbm",
                 "achieved": mc_bytes / (mc_ms_avg * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": mc_bytes / (mc_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": mc_ms_avg, "ms_until_host_has_sizes": mc_host_ms_avg,
-                "algorithmic_bytes": mc_bytes,
-                "peak_source": peak_kind,
+                "frac": mc_bytes / (mc_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": mc_ms_avg, "ms_pct": pct(mc_ms),
+                "algorithmic_bytes": mc_bytes, "peak_source": peak_kind,
             }
+        if sharded is not None:
+            line["sharded_512"] = sharded
+        if sf3d is not None:
+            line["sf3d"] = sf3d
         if not args.no_cpu_baseline and world == 1:
             v, desc, info = cpu_reference_sample(R, args.cpu_seconds, thresholds[0])
             line["cpu_baseline"] = {"value": v, "unit": "pts/s", "cores": info["threads"], "kind": "port", "sample": desc}

@@ -193,6 +193,29 @@ int smb_mc_emit_gather(const float* grid, int nx, int ny, int nz, float sub, flo
                        int emit_last_plane, int flags, float vdiv, float vmul, float vadd, const void* workspace,
                        const int64_t* all_counts_dev, int rank, float* verts_dst, int64_t verts_capacity,
                        int64_t* faces_dst, int64_t faces_capacity, void* stream);
+/* Gather mode without collectives: every rank owns a control block of SMB_PEER_CTRL_WORDS int64 (smb_dev_alloc +
+ * IPC, mapped by every process; zero it once).  Per call, with a sequence number seq = 1, 2, ... shared by the ranks:
+ *   smb_peer_wait_release(ctrl, seq-1)         first: the destination has consumed the previous call
+ *   ... lattice, smb_mc_count* into counts_dev ...
+ *   smb_peer_publish_counts(counts_dev, peers, rank, world, seq)    NVLink stores of the counts + flag into EVERY block
+ *   smb_mc_emit_gather_flags(..., ctrl, seq, rank, dst buffers)     waits (on the device) for the lower ranks' flags,
+ *                                                                   then stores its slab into the destination's buffers
+ *   smb_peer_signal_done(dst_ctrl, rank, seq)                        flag into the destination's block
+ *   smb_peer_wait_all(ctrl, peers, world, seq, wait_done, totals_dev)  -> totals_dev = {sum V, sum F, error, seq}:
+ *       destination (wait_done = 1): every slab stored; also releases the peers for call seq+1;
+ *       other ranks (wait_done = 0): every rank's counts have arrived (so that all ranks see the same totals)
+ * peers = DEVICE array of `world` pointers to the control blocks as mapped in this process.  No NCCL call, no host
+ * round trip; waits are bounded (about 3 s) and set the error word instead of hanging the GPU. */
+#define SMB_PEER_CTRL_WORDS 128
+int smb_peer_wait_release(void* ctrl_local, int64_t need, void* stream);
+int smb_peer_publish_counts(const smb_mc_counts* counts_dev, void* const* peer_ctrl_dev, int rank, int world, int64_t seq, void* stream);
+int smb_mc_emit_gather_flags(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                             int emit_last_plane, int flags, float vdiv, float vmul, float vadd, const void* workspace,
+                             void* ctrl_local, int64_t seq, int rank, float* verts_dst, int64_t verts_capacity,
+                             void* faces_dst, int64_t faces_capacity, void* stream);
+int smb_peer_signal_done(void* dst_ctrl, int rank, int64_t seq, void* stream);
+int smb_peer_wait_all(void* ctrl_local, void* const* peer_ctrl_dev, int world, int64_t seq, int wait_done, int64_t* totals_dev,
+                      void* stream);
 /* Peer-memory plumbing for the above: the destination rank allocates its mesh buffers with smb_dev_alloc,
  * exports a 64-byte handle, the other ranks map it (this also enables peer access). */
 int smb_dev_alloc(size_t bytes, void** out);
@@ -242,6 +265,13 @@ int smb_extractor_set_faces_i32(smb_extractor* ex, int enable);
 int smb_extract_mesh_device(smb_extractor* ex, const float* triplane_dev, int resolution, float threshold, int face_flags,
                             float* verts_out, int64_t verts_capacity, void* faces_out, int64_t faces_capacity,
                             float* density_out, int emit_only, void* stream, int64_t* nverts, int64_t* ntris);
+
+/* Optional phase timing of smb_extract_mesh_device: CUDA events on the caller's stream around prepare / the lattice
+ * kernel / marching cubes (count + totals + emit); smb_extractor_last_timing returns the last call's durations in ms
+ * (valid after that call returned: it synchronises the stream).  This is how bench.py measures the dominant kernel
+ * live inside its timed region. */
+int smb_extractor_enable_timing(smb_extractor* ex, int enable);
+int smb_extractor_last_timing(smb_extractor* ex, float* prepare_ms, float* lattice_ms, float* mc_ms);
 
 /* The same with enable_texture=True (system.py:190-200): also returns the vertex colours
  * colors_host (nverts,3) fp32 = query_triplane(decoder, v_pos, scene_code)["color"] (sigmoid of the three

@@ -114,6 +114,15 @@ SIGNATURES = {
         [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_int,
          c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     ),
+    "smb_peer_wait_release": (c_int, [c_void_p, c_int64, c_void_p]),
+    "smb_peer_publish_counts": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
+    "smb_mc_emit_gather_flags": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_int,
+         c_void_p, c_int64, c_void_p, c_int64, c_void_p],
+    ),
+    "smb_peer_signal_done": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    "smb_peer_wait_all": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "smb_dev_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "smb_dev_free": (c_int, [c_void_p]),
     "smb_ipc_export": (c_int, [c_void_p, c_void_p]),
@@ -130,6 +139,8 @@ SIGNATURES = {
     ),
     "smb_extractor_pinned_input": (c_int, [c_void_p, POINTER(POINTER(c_float))]),
     "smb_extractor_set_faces_i32": (c_int, [c_void_p, c_int]),
+    "smb_extractor_enable_timing": (c_int, [c_void_p, c_int]),
+    "smb_extractor_last_timing": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
     "smb_extract_mesh_device": (
         c_int,
         [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, POINTER(c_int64), POINTER(c_int64)],

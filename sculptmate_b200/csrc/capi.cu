@@ -208,6 +208,9 @@ struct smb_extractor {
   float* colors_pin = nullptr;
   float* loop_colors_pin = nullptr;
   size_t colors_cap = 0, loop_colors_cap = 0;
+  // optional phase timing of smb_extract_mesh_device (smb_extractor_enable_timing): events on the caller's stream
+  int timing = 0;
+  cudaEvent_t tev[4] = {};  // start, after prepare, after the lattice kernel, after emit
   int faces_i32 = 0;  // host extractor delivers (F,3) int32 faces (smb_extractor_set_faces_i32)
   int n_slabs = 3;  // equal slabs, measured on B200 at 256^3: 2-3 slabs 4.42 ms, 1 (off) 4.71 ms, >= 4 slower and noisier (per-slab launch + host event cost)
   // slab k holds a share ~ slab_ratio^k of the cell layers: only the LAST slab's copy is exposed, and the copy of
@@ -317,6 +320,8 @@ extern "C" void smb_extractor_destroy(smb_extractor* ex) {
   cudaFreeHost(ex->loop_colors_pin);
   for (int k = 0; k < smb_extractor::kSlabs; ++k)
     if (ex->slab_done[k]) cudaEventDestroy(ex->slab_done[k]);
+  for (int k = 0; k < 4; ++k)
+    if (ex->tev[k]) cudaEventDestroy(ex->tev[k]);
   if (ex->copy_stream) cudaStreamDestroy(ex->copy_stream);
   if (ex->stream) cudaStreamDestroy(ex->stream);
   delete ex;
@@ -573,6 +578,26 @@ extern "C" int smb_extract_mesh_host_textured(smb_extractor* ex, const float* tr
   return SMB_OK;
 }
 
+extern "C" int smb_extractor_enable_timing(smb_extractor* ex, int enable) {
+  if (!ex) return SMB_ERR_BAD_ARG;
+  if (enable)
+    for (int k = 0; k < 4; ++k)
+      if (!ex->tev[k] && cudaEventCreate(&ex->tev[k]) != cudaSuccess) return SMB_ERR_CUDA;
+  ex->timing = enable ? 1 : 0;
+  return SMB_OK;
+}
+extern "C" int smb_extractor_last_timing(smb_extractor* ex, float* prepare_ms, float* lattice_ms, float* mc_ms) {
+  if (!ex || !ex->timing || !ex->tev[3]) return SMB_ERR_BAD_ARG;
+  float a = 0.f, b = 0.f, c = 0.f;
+  if (cudaEventElapsedTime(&a, ex->tev[0], ex->tev[1]) != cudaSuccess || cudaEventElapsedTime(&b, ex->tev[1], ex->tev[2]) != cudaSuccess ||
+      cudaEventElapsedTime(&c, ex->tev[2], ex->tev[3]) != cudaSuccess)
+    return SMB_ERR_CUDA;
+  if (prepare_ms) *prepare_ms = a;
+  if (lattice_ms) *lattice_ms = b;
+  if (mc_ms) *mc_ms = c;
+  return SMB_OK;
+}
+
 extern "C" int smb_extractor_set_faces_i32(smb_extractor* ex, int enable) {
   if (!ex) return SMB_ERR_BAD_ARG;
   ex->faces_i32 = enable ? 1 : 0;
@@ -596,12 +621,16 @@ extern "C" int smb_extract_mesh_device(smb_extractor* ex, const float* triplane_
   const double r = (double)ex->cfg.radius;
   const int mc_flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (face_flags & SMB_MC_FACES_I32);
   const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
+  const bool timed = ex->timing && !emit_only;
   if (!emit_only) {
+    if (timed) EX_CUDA(cudaEventRecord(ex->tev[0], st));
     rc = smb_scene_prepare(triplane_dev, ex->cfg.Hp, ex->cfg.Wp, ex->blob_dev, &ex->layout, nullptr, ex->planes_q, st);
     if (rc != SMB_OK) return rc;
+    if (timed) EX_CUDA(cudaEventRecord(ex->tev[1], st));
     rc = smb_query_lattice_tc_signs(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, 0, R, dens, nullptr, threshold, 1.0f,
                                     ex->mc_ws, ex->mc_ws_bytes, st);
     if (rc != SMB_OK) return rc;
+    if (timed) EX_CUDA(cudaEventRecord(ex->tev[2], st));
     rc = smb_mc_count_presigned(R, R, R, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
     if (rc != SMB_OK) return rc;
   }
@@ -610,6 +639,7 @@ extern "C" int smb_extract_mesh_device(smb_extractor* ex, const float* triplane_
                              static_cast<int64_t*>(faces_out), faces_capacity, st);
     if (rc != SMB_OK) return rc;
   }
+  if (timed) EX_CUDA(cudaEventRecord(ex->tev[3], st));
   EX_CUDA(cudaMemcpyAsync(ex->counts_pin, ex->counts_dev, sizeof(smb_mc_counts), cudaMemcpyDeviceToHost, st));
   EX_CUDA(cudaStreamSynchronize(st));
   const int64_t V = ex->counts_pin->nverts, F = ex->counts_pin->ntris;

@@ -413,6 +413,11 @@ struct EmitParams {
   // sums over the lower ranks, and verts/faces point at the destination rank's buffers (peer memory)
   const long long* all_counts;
   int rank;
+  // peer-flag mode: all_counts lives in this rank's control block and is valid for the lower ranks once
+  // count_seq[g] == seq (written over NVLink by rank g's smb_peer_publish_counts)
+  const long long* count_seq;
+  long long seq;
+  long long* error_flag;
 };
 
 __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float vmul, float vadd) {
@@ -460,9 +465,26 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
   const McDims d = p.d;
   long long v_off = 0, f_off = 0;
   if (p.all_counts) {
+    if (p.count_seq) {
+      // the lower ranks' counts arrive as peer stores: one thread per CTA waits for their sequence flags
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int g = 0; g < p.rank; ++g) {
+          while (*reinterpret_cast<const volatile long long*>(p.count_seq + g) != p.seq) {
+            if (clock64() - t0 > 6000000000LL) {  // ~3 s: a peer died; report instead of hanging the GPU
+              if (p.error_flag) *p.error_flag = 1;
+              break;
+            }
+            __nanosleep(200);
+          }
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
     for (int g = 0; g < p.rank; ++g) {
-      v_off += p.all_counts[4 * g + 0];
-      f_off += p.all_counts[4 * g + 1];
+      v_off += *reinterpret_cast<const volatile long long*>(p.all_counts + 4 * g + 0);
+      f_off += *reinterpret_cast<const volatile long long*>(p.all_counts + 4 * g + 1);
     }
   }
   const long long id_off = p.id_offset + v_off;
@@ -784,7 +806,8 @@ extern "C" int smb_mc_count_presigned(int nx, int ny, int nz, int emit_last_plan
 static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
                        int emit_last_plane, int flags, float vdiv, float vmul, float vadd,
                        int64_t vertex_id_offset, const void* workspace, float* verts, int64_t verts_capacity,
-                       int64_t* faces, int64_t faces_capacity, const int64_t* all_counts, int rank, void* stream) {
+                       int64_t* faces, int64_t faces_capacity, const int64_t* all_counts, int rank, void* stream,
+                       const int64_t* count_seq = nullptr, int64_t seq = 0, int64_t* error_flag = nullptr) {
   if (!grid || !workspace || nx <= 0 || ny <= 0 || nz <= 0 || verts_capacity < 0 || faces_capacity < 0) return SMB_ERR_BAD_ARG;
   McDims d = make_dims(nx, ny, nz);
   McWorkspace w = carve(const_cast<void*>(workspace), d);
@@ -809,6 +832,9 @@ static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, flo
   p.fcap = faces ? faces_capacity : 0;
   p.all_counts = reinterpret_cast<const long long*>(all_counts);
   p.rank = rank;
+  p.count_seq = reinterpret_cast<const long long*>(count_seq);
+  p.seq = seq;
+  p.error_flag = reinterpret_cast<long long*>(error_flag);
   const long long nbatch = (d.nwords + 31) / 32;
   long long blocks = (nbatch + kEmitWarps - 1) / kEmitWarps;
   const long long cap = (long long)sm_count() * 8;
@@ -832,6 +858,111 @@ extern "C" int smb_mc_emit_gather(const float* grid, int nx, int ny, int nz, flo
   if (!all_counts_dev || rank < 0 || !verts_dst || !faces_dst) return SMB_ERR_BAD_ARG;
   return launch_emit(grid, nx, ny, nz, sub, sign, x_origin, emit_last_plane, flags, vdiv, vmul, vadd, 0, workspace, verts_dst,
                      verts_capacity, faces_dst, faces_capacity, all_counts_dev, rank, stream);
+}
+
+// ------------------------------------------------ peer control block (multi-GPU gather without collectives)
+// Layout of a rank's control block (int64 words): counts[16][4] at 0, count_seq[16] at 64, done_seq[16] at 80,
+// release_seq at 96, error at 97 (SMB_PEER_CTRL_WORDS = 128).  Every rank maps every block (CUDA IPC).
+namespace smb {
+constexpr int kPeerCounts = 0, kPeerCountSeq = 64, kPeerDoneSeq = 80, kPeerRelease = 96, kPeerError = 97;
+
+__global__ void peer_publish_counts(const smb_mc_counts* __restrict__ mine, long long* const* __restrict__ peers, int rank, int world,
+                                    long long seq) {
+  const int g = threadIdx.x;
+  if (g >= world) return;
+  volatile long long* c = peers[g] + kPeerCounts + 4 * rank;
+  c[0] = mine->nverts;
+  c[1] = mine->ntris;
+  c[2] = mine->nverts_numbered;
+  c[3] = 0;
+  __threadfence_system();
+  *reinterpret_cast<volatile long long*>(peers[g] + kPeerCountSeq + rank) = seq;
+}
+
+__global__ void peer_signal_done(long long* dst_ctrl, int rank, long long seq) {
+  __threadfence_system();  // everything this stream stored before (the emit kernel's peer stores) is performed first
+  *reinterpret_cast<volatile long long*>(dst_ctrl + kPeerDoneSeq + rank) = seq;
+}
+
+// wait_done != 0 (destination rank): wait until every rank has stored its slab, then release the peers for the next
+// call; wait_done == 0 (other ranks): wait until every rank's counts have arrived.  Either way sum the counts.
+__global__ void peer_wait_all(long long* ctrl, long long* const* __restrict__ peers, int world, long long seq, int wait_done,
+                              long long* totals) {
+  const int g = threadIdx.x;
+  const long long t0 = clock64();
+  if (g < world) {
+    const long long* flag = ctrl + (wait_done ? kPeerDoneSeq : kPeerCountSeq) + g;
+    while (*reinterpret_cast<const volatile long long*>(flag) != seq) {
+      if (clock64() - t0 > 6000000000LL) {
+        ctrl[kPeerError] = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (wait_done && g < world) *reinterpret_cast<volatile long long*>(peers[g] + kPeerRelease) = seq;
+  if (g == 0) {
+    long long v = 0, f = 0;
+    for (int r = 0; r < world; ++r) {
+      v += *reinterpret_cast<volatile long long*>(ctrl + kPeerCounts + 4 * r + 0);
+      f += *reinterpret_cast<volatile long long*>(ctrl + kPeerCounts + 4 * r + 1);
+    }
+    totals[0] = v;
+    totals[1] = f;
+    totals[2] = ctrl[kPeerError];
+    totals[3] = seq;
+  }
+}
+
+// every rank, first kernel of a call: the destination has consumed call seq-1 (nobody overwrites counts / mesh
+// buffers a slower rank or the destination's reader still needs)
+__global__ void peer_wait_release(long long* ctrl, long long need) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<volatile long long*>(ctrl + kPeerRelease) < need) {
+    if (clock64() - t0 > 6000000000LL) {
+      ctrl[kPeerError] = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+}  // namespace smb
+
+extern "C" int smb_peer_publish_counts(const smb_mc_counts* counts_dev, void* const* peer_ctrl_dev, int rank, int world, int64_t seq,
+                                       void* stream) {
+  if (!counts_dev || !peer_ctrl_dev || rank < 0 || world < 1 || world > 16 || rank >= world) return SMB_ERR_BAD_ARG;
+  peer_publish_counts<<<1, 32, 0, (cudaStream_t)stream>>>(counts_dev, reinterpret_cast<long long* const*>(peer_ctrl_dev), rank, world, seq);
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+extern "C" int smb_peer_signal_done(void* dst_ctrl, int rank, int64_t seq, void* stream) {
+  if (!dst_ctrl || rank < 0 || rank >= 16) return SMB_ERR_BAD_ARG;
+  peer_signal_done<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<long long*>(dst_ctrl), rank, seq);
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+extern "C" int smb_peer_wait_all(void* ctrl_local, void* const* peer_ctrl_dev, int world, int64_t seq, int wait_done, int64_t* totals_dev,
+                                 void* stream) {
+  if (!ctrl_local || !peer_ctrl_dev || !totals_dev || world < 1 || world > 16) return SMB_ERR_BAD_ARG;
+  peer_wait_all<<<1, 32, 0, (cudaStream_t)stream>>>(static_cast<long long*>(ctrl_local), reinterpret_cast<long long* const*>(peer_ctrl_dev), world,
+                                                   seq, wait_done, reinterpret_cast<long long*>(totals_dev));
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+extern "C" int smb_peer_wait_release(void* ctrl_local, int64_t need, void* stream) {
+  if (!ctrl_local) return SMB_ERR_BAD_ARG;
+  peer_wait_release<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<long long*>(ctrl_local), need);
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+extern "C" int smb_mc_emit_gather_flags(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,
+                                        int emit_last_plane, int flags, float vdiv, float vmul, float vadd, const void* workspace,
+                                        void* ctrl_local, int64_t seq, int rank, float* verts_dst, int64_t verts_capacity,
+                                        void* faces_dst, int64_t faces_capacity, void* stream) {
+  if (!ctrl_local || rank < 0 || rank >= 16 || !verts_dst || !faces_dst) return SMB_ERR_BAD_ARG;
+  int64_t* c = static_cast<int64_t*>(ctrl_local);
+  return launch_emit(grid, nx, ny, nz, sub, sign, x_origin, emit_last_plane, flags, vdiv, vmul, vadd, 0, workspace, verts_dst,
+                     verts_capacity, static_cast<int64_t*>(faces_dst), faces_capacity, c + smb::kPeerCounts, rank, stream,
+                     c + smb::kPeerCountSeq, seq, c + smb::kPeerError);
 }
 
 extern "C" int smb_mc_emit(const float* grid, int nx, int ny, int nz, float sub, float sign, int x_origin,

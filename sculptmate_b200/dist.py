@@ -11,13 +11,17 @@ no seam search, no welding pass.
 
 Two transports for the gather:
 
-``p2p`` (default on CUDA, world > 1) -- fused with the emit kernel.  The destination rank owns
-  the mesh buffers (cudaMalloc + CUDA IPC, mapped into every process once); per call each rank
-  runs  lattice -> mc_count -> [NCCL all_gather of the 4-int64 counts, device to device] ->
-  mc_emit in gather mode, whose kernel derives its output offsets from the gathered counts ON THE
-  DEVICE and stores vertices and faces (with global ids) straight into the destination's buffers
-  over NVLink peer memory -> [tiny NCCL all_reduce as the completion fence].  No staging buffer,
-  no send/recv pass, no host round trip between the kernels; one host sync per call (the sizes).
+``p2p`` (default on CUDA, world > 1) -- fused with the emit kernel, NO collective on the data path.  The
+  destination rank owns the mesh buffers and every rank a small control block (cudaMalloc + CUDA IPC, mapped into
+  every process once).  Per call each rank runs  lattice (+ sign ballot) -> mc_count -> ``peer_publish_counts``
+  (its counts + a sequence flag stored over NVLink into every rank's control block) -> ``mc_emit`` in gather mode:
+  the kernel waits ON THE DEVICE for the lower ranks' flags, sums their counts to get its output offsets and stores
+  vertices and int32 faces (global ids) straight into the destination's buffers over NVLink peer memory ->
+  ``peer_signal_done`` (a flag in the destination's block).  The destination's ``peer_wait_all`` kernel waits for all
+  flags, releases the peers for the next call and sums the counts.  No staging buffer, no send/recv pass, no NCCL
+  call, no host round trip between the kernels; one host sync per call (the sizes).  Round 1 used an NCCL
+  all_gather for the counts and an all_reduce as completion fence (two collective launches + their latency per
+  call) and carried int64 faces on the wire.
 ``nccl`` -- count -> all_gather -> emit locally -> grouped isend/irecv of the slab meshes to
   their final offsets.  Also what the gloo CPU tests exercise with the oracle as the backend.
 
@@ -160,12 +164,13 @@ def _global_rank(group: Optional[dist.ProcessGroup], group_rank: int) -> int:
 
 
 def broadcast_scene(scene_code: torch.Tensor, decoder: Optional[torch.nn.Module] = None, src: int = 0, group=None) -> None:
-    """Rank ``src`` -> all: the triplane (1.97 MB fp32) and, optionally, the decoder
+    """Rank ``src`` (rank inside ``group``) -> all: the triplane (1.97 MB fp32) and, optionally, the decoder
     parameters (0.17 MB).  In place."""
-    dist.broadcast(scene_code, src=src, group=group)
+    gsrc = _global_rank(group, src)  # torch.distributed.broadcast takes a GLOBAL rank; `src` here is group-relative
+    dist.broadcast(scene_code, src=gsrc, group=group)
     if decoder is not None:
         for p in decoder.parameters():
-            dist.broadcast(p.data, src=src, group=group)
+            dist.broadcast(p.data, src=gsrc, group=group)
 
 
 # ------------------------------------------------------------------ p2p transport
@@ -206,31 +211,68 @@ class _DevAlloc:
 
 
 class PeerGather:
-    """Persistent state of the ``p2p`` transport for one (process group, destination): the
-    destination's double-buffered mesh storage, its mapping in every other process, and the
-    device/pinned count buffers.  Capacities grow by re-running ``setup`` collectively."""
+    """Persistent state of the ``p2p`` transport for one (process group, destination):
+      * the destination's double-buffered mesh storage, mapped into every other process (CUDA IPC);
+      * one control block per rank (counts, sequence flags), every block mapped by every process, and the device
+        table of those pointers;
+      * device / pinned totals.
+    Capacities grow by re-running ``setup_mesh`` collectively (every rank reads the same totals each call)."""
 
     SETS = 2  # results stay valid until the call after the next one
+    CTRL_WORDS = 128
 
     def __init__(self, device: torch.device, group=None, dst: int = 0):
+        from . import _capi
+
         self.device, self.group, self.dst = device, group, dst
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("the peer-flag gather supports up to 16 ranks per node")
         self.vcap = self.fcap = 0
         self.allocs: list = []  # dst: [(_DevAlloc verts, _DevAlloc faces)] * SETS
         self.ptrs: list = []  # every rank: [(verts ptr, faces ptr)] * SETS in THIS process' address space
         self.turn = 0
+        self.seq = 0
         self.counts_dev = torch.zeros(4, dtype=torch.int64, device=device)
-        self.all_counts_dev = torch.zeros(4 * self.world, dtype=torch.int64, device=device)
-        self.all_counts_pin = torch.zeros(4 * self.world, dtype=torch.int64).pin_memory()
-        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
+        self.totals_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self._lib = _capi.load()
+        self._setup_ctrl()
 
-    def setup(self, vcap: int, fcap: int) -> None:
+    def _setup_ctrl(self) -> None:
+        """Collective, once: allocate this rank's control block, map everybody else's."""
+        import ctypes
+
+        from . import _capi
+
+        lib = self._lib
+        with torch.cuda.device(self.device):
+            self.ctrl = _DevAlloc(8 * self.CTRL_WORDS)
+            torch.as_tensor(_CaiView(self.ctrl, self.ctrl.ptr, (self.CTRL_WORDS,), "<i8"), device=self.device).zero_()
+            torch.cuda.synchronize(self.device)
+            mine = self.ctrl.handle().to(self.device)
+            allh = torch.zeros(64 * self.world, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=self.group)
+            hb = allh.cpu().numpy().tobytes()
+            self.ctrl_ptrs = []
+            for g in range(self.world):
+                if g == self.rank:
+                    self.ctrl_ptrs.append(self.ctrl.ptr)
+                    continue
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(hb[64 * g : 64 * (g + 1)])
+                q = ctypes.c_void_p()
+                _capi.check(lib.smb_ipc_open(h, ctypes.byref(q)), "smb_ipc_open")
+                self.ctrl_ptrs.append(int(q.value))
+            self.ctrl_table = torch.tensor(self.ctrl_ptrs, dtype=torch.int64, device=self.device)
+        dist.barrier(self.group)  # every block is zeroed and mapped before anyone publishes into it
+
+    def setup_mesh(self, vcap: int, fcap: int) -> None:
         """Collective.  (Re)allocate the destination buffers and map them everywhere."""
         import ctypes
 
         from . import _capi
 
-        lib = _capi.load()
+        lib = self._lib
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)  # nobody is still writing into the old buffers
         if self.rank != self.dst:
@@ -243,7 +285,7 @@ class PeerGather:
             if self.rank == self.dst:
                 hs = []
                 for _ in range(self.SETS):
-                    av, af = _DevAlloc(12 * vcap), _DevAlloc(24 * fcap)
+                    av, af = _DevAlloc(12 * vcap), _DevAlloc(24 * fcap)  # faces sized for int64; int32 uses half
                     self.allocs.append((av, af))
                     self.ptrs.append((av.ptr, af.ptr))
                     hs += [av.handle(), af.handle()]
@@ -255,25 +297,27 @@ class PeerGather:
                     out = []
                     for j in range(2):
                         h = (ctypes.c_ubyte * 64).from_buffer_copy(hb[(2 * k + j) * 64 : (2 * k + j + 1) * 64])
-                        p = ctypes.c_void_p()
-                        _capi.check(lib.smb_ipc_open(h, ctypes.byref(p)), "smb_ipc_open")
-                        out.append(int(p.value))
+                        q = ctypes.c_void_p()
+                        _capi.check(lib.smb_ipc_open(h, ctypes.byref(q)), "smb_ipc_open")
+                        out.append(int(q.value))
                     self.ptrs.append(tuple(out))
         self.vcap, self.fcap = int(vcap), int(fcap)
         dist.barrier(self.group)
 
-    def views(self, k: int, V: int, F: int):
+    def views(self, k: int, V: int, F: int, faces_dtype: torch.dtype):
         av, af = self.allocs[k]
         verts = torch.as_tensor(_CaiView(av, av.ptr, (V, 3), "<f4"), device=self.device)
-        faces = torch.as_tensor(_CaiView(af, af.ptr, (F, 3), "<i8"), device=self.device)
+        faces = torch.as_tensor(_CaiView(af, af.ptr, (F, 3), "<i4" if faces_dtype == torch.int32 else "<i8"), device=self.device)
         return verts, faces
 
 
-def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precision):
-    import ctypes  # noqa: F401
-
+def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precision, faces_dtype=torch.int64, wire_i32=True,
+                      broadcast=False, phases=None):
+    """One sharded extract with the peer-flag gather.  ``wire_i32``: faces cross NVLink as int32 (global ids < 2^31) and
+    are widened on the destination when ``faces_dtype`` is int64.  ``phases`` (optional dict) receives CUDA events
+    at the phase boundaries of this rank (developer timing)."""
     from . import _capi, runtime
-    from ._capi import MC_AFFINE, MC_DIV, MC_FLIP
+    from ._capi import MC_AFFINE, MC_DIV, MC_FACES_I32, MC_FLIP
 
     dev = scene_code.device
     key = (id(group), dst, str(dev))
@@ -284,54 +328,90 @@ def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precis
     world, rank = pg.world, pg.rank
     a, b = slab_partition(resolution, world)[rank]
     nx, R, last = b - a + 1, resolution, rank == world - 1
-    lib = _capi.load()
+    lib = pg._lib
     tsr.set_marching_cubes_resolution(R)
-    with torch.no_grad():
-        # the tensor-core lattice kernel also ballots the marching-cubes sign masks of the slab into the workspace
-        fused = precision == "tc"
-        slab = tsr.renderer.query_lattice(tsr.decoder, scene_code, R, axis_u=tsr._axis(R, dev), x_begin=a, nx=nx, precision=precision,
-                                          mc_signs=(float(threshold), 1.0) if fused else None)
-    ws, _, _ = runtime._mc_cache.get(dev, (nx, R, R))
     r = tsr.renderer.cfg.radius
-    flags = MC_FLIP | MC_DIV | MC_AFFINE
+    i32 = bool(wire_i32) or faces_dtype == torch.int32
+    flags = MC_FLIP | MC_DIV | MC_AFFINE | (MC_FACES_I32 if i32 else 0)
 
-    def counts_to_host():
-        pg.all_counts_pin.copy_(pg.all_counts_dev, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        c = pg.all_counts_pin.view(world, 4)
-        return int(c[:, 0].sum()), int(c[:, 1].sum())
+    def mark(name):
+        if phases is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            phases[name] = e
 
     with torch.cuda.device(dev):
         st = runtime._stream_ptr(dev)
-        if fused:
-            _capi.check(lib.smb_mc_count_presigned(nx, R, R, int(last), ws.data_ptr(), ws.numel(), pg.counts_dev.data_ptr(), st), "smb_mc_count_presigned")
+        mark("start")
+        pg.seq += 1
+        _capi.check(lib.smb_peer_wait_release(pg.ctrl.ptr, pg.seq - 1, st), "smb_peer_wait_release")
+        if broadcast:
+            broadcast_scene(scene_code, None, src=dst, group=group)
+            if rank != dst:
+                tsr.renderer._scene_ref = None  # the tensor was rewritten in place by NCCL: never reuse planes prepared from its old content
+        mark("scene")
+        with torch.no_grad():
+            # the tensor-core lattice kernel also ballots the marching-cubes sign masks of the slab into the workspace
+            fused = precision == "tc"
+            slab = tsr.renderer.query_lattice(tsr.decoder, scene_code, R, axis_u=tsr._axis(R, dev), x_begin=a, nx=nx, precision=precision,
+                                              mc_signs=(float(threshold), 1.0) if fused else None)
+        mark("lattice")
+        w = runtime._mc_cache.get(dev, (nx, R, R))
+        w.generation += 1
+        if fused and w.signed_matches(slab, threshold, 1.0):
+            _capi.check(lib.smb_mc_count_presigned(nx, R, R, int(last), w.ws.data_ptr(), w.ws.numel(), pg.counts_dev.data_ptr(), st), "smb_mc_count_presigned")
         else:
-            _capi.check(lib.smb_mc_count(slab.data_ptr(), nx, R, R, float(threshold), 1.0, int(last), ws.data_ptr(), ws.numel(),
+            _capi.check(lib.smb_mc_count(slab.data_ptr(), nx, R, R, float(threshold), 1.0, int(last), w.ws.data_ptr(), w.ws.numel(),
                                          pg.counts_dev.data_ptr(), st), "smb_mc_count")
-        dist.all_gather_into_tensor(pg.all_counts_dev, pg.counts_dev, group=group)
-        totals = None
-        if pg.vcap == 0:  # first call: learn the sizes, then map buffers with 25 % head room
-            totals = counts_to_host()
-            pg.setup(totals[0] * 5 // 4 + 4096, totals[1] * 5 // 4 + 4096)
+        first = True
         while True:
-            k = pg.turn % pg.SETS
-            pv, pf = pg.ptrs[k]
-            _capi.check(
-                lib.smb_mc_emit_gather(slab.data_ptr(), nx, R, R, float(threshold), 1.0, a, int(last), flags, float(R - 1.0),
-                                       float(r - (-r)), float(-r), ws.data_ptr(), pg.all_counts_dev.data_ptr(), rank,
-                                       pv, pg.vcap, pf, pg.fcap, st),
-                "smb_mc_emit_gather",
-            )
-            dist.all_reduce(pg.token, group=group)  # completion fence: every slab has been stored
-            if totals is None:
-                totals = counts_to_host()
-            if totals[0] <= pg.vcap and totals[1] <= pg.fcap:
-                break
-            pg.setup(totals[0] * 5 // 4 + 4096, totals[1] * 5 // 4 + 4096)  # outgrown (every rank sees the same counts)
-        pg.turn += 1
-        if rank == dst:
+            if not first:  # capacity grown (collectively): a fresh sequence number, only publish + emit are repeated
+                pg.seq += 1
+                _capi.check(lib.smb_peer_wait_release(pg.ctrl.ptr, pg.seq - 1, st), "smb_peer_wait_release")
+            _capi.check(lib.smb_peer_publish_counts(pg.counts_dev.data_ptr(), pg.ctrl_table.data_ptr(), rank, world, pg.seq, st), "smb_peer_publish_counts")
+            mark("count")
+            if pg.vcap > 0:
+                k = pg.turn % pg.SETS
+                pv, pf = pg.ptrs[k]
+                _capi.check(
+                    lib.smb_mc_emit_gather_flags(slab.data_ptr(), nx, R, R, float(threshold), 1.0, a, int(last), flags, float(R - 1.0),
+                                                 float(r - (-r)), float(-r), w.ws.data_ptr(), pg.ctrl.ptr, pg.seq, rank,
+                                                 pv, pg.vcap, pf, pg.fcap, st),
+                    "smb_mc_emit_gather_flags",
+                )
+            mark("emit")
+            _capi.check(lib.smb_peer_signal_done(pg.ctrl_ptrs[dst], rank, pg.seq, st), "smb_peer_signal_done")
+            _capi.check(lib.smb_peer_wait_all(pg.ctrl.ptr, pg.ctrl_table.data_ptr(), world, pg.seq, int(rank == dst), pg.totals_dev.data_ptr(), st),
+                        "smb_peer_wait_all")
+            mark("gathered")
+            pg.totals_pin.copy_(pg.totals_dev, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-            return pg.views(k, totals[0], totals[1])
+            V, F, err = int(pg.totals_pin[0]), int(pg.totals_pin[1]), int(pg.totals_pin[2])
+            if err:
+                raise RuntimeError("sharded extract_mesh: a peer did not arrive within the device-side timeout")
+            if i32 and V >= 2**31:
+                raise ValueError("vertex ids do not fit int32; call with wire_i32=False")
+            if V <= pg.vcap and F <= pg.fcap and pg.vcap > 0:
+                break
+            pg.setup_mesh(max(pg.vcap, V * 5 // 4 + 4096), max(pg.fcap, F * 5 // 4 + 4096))  # every rank sees the same totals
+            first = False
+        pg.turn += 1
+        if V == 0 or F == 0:
+            # same exception types as the single-GPU path (skimage's, isosurface.py:46-48), decided on the GLOBAL
+            # value range so that every rank raises the same one
+            lo, hi = runtime.grid_minmax(slab, float(threshold), 1.0)
+            mm = torch.tensor([-lo, hi], dtype=torch.float32, device=dev)
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+            lo, hi = -float(mm[0]), float(mm[1])
+            if lo > 0.0 or hi < 0.0:
+                raise ValueError("Surface level must be within volume data range.")
+            raise RuntimeError("No surface found at the given iso value.")
+        if rank == dst:
+            verts, faces = pg.views(k, V, F, torch.int32 if i32 else torch.int64)
+            if i32 and faces_dtype == torch.int64:
+                faces = faces.to(torch.int64)  # widened once on the destination (the wire carried 12 B per triangle)
+            mark("end")
+            return verts, faces
     return None, None
 
 
@@ -345,16 +425,21 @@ def extract_mesh_sharded(
     precision: str = "tc",
     broadcast: bool = True,
     transport: str = "p2p",
+    faces_dtype: torch.dtype = torch.int64,
+    phases: Optional[dict] = None,
 ):
     """TSR.extract_mesh for one scene code with the lattice sharded over the group.
     Returns (v_pos, t_pos_idx) on ``dst`` (device tensors), (None, None) elsewhere.  With the
-    ``p2p`` transport the tensors are views of persistent buffers, valid until the call after
-    the next one."""
+    ``p2p`` transport the vertex tensor (and int32 faces) are views of persistent buffers, valid until the
+    call after the next one.  Single process / world size 1: the single-GPU path (``extract_mesh_tensors``)."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi and scene_code.is_cuda:
+        return tsr.extract_mesh_tensors(scene_code, resolution, threshold, precision=precision, faces_dtype=faces_dtype)
+    if multi and transport == "p2p" and scene_code.is_cuda:
+        return _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precision, faces_dtype=faces_dtype,
+                                 broadcast=broadcast, phases=phases)
     if broadcast and multi:
         broadcast_scene(scene_code, None, src=dst, group=group)
-    if multi and transport == "p2p" and scene_code.is_cuda:
-        return _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precision)
     backend = CudaSlabBackend(tsr, scene_code, resolution, threshold, precision)
     verts, faces, _ = gather_slab_meshes(backend, resolution, group=group, dst=dst)
     return verts, faces

@@ -484,6 +484,16 @@ class MeshExtractor:
 
     __del__ = close
 
+    def enable_timing(self, on: bool = True) -> None:
+        """CUDA events around prepare / lattice kernel / marching cubes inside ``extract`` (see ``last_timing``)."""
+        check(_capi.load().smb_extractor_enable_timing(self._h, int(on)), "smb_extractor_enable_timing")
+
+    def last_timing(self) -> Tuple[float, float, float]:
+        """(prepare_ms, lattice_ms, mc_ms) of the last ``extract`` call (mc = count + totals + emit on the device)."""
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        check(_capi.load().smb_extractor_last_timing(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "smb_extractor_last_timing")
+        return a.value, b.value, c.value
+
     def extract(self, triplane: torch.Tensor, resolution: int, threshold: float, faces_dtype: torch.dtype = torch.int64,
                 axis_u: Optional[torch.Tensor] = None, want_density: bool = False):
         """-> (v_pos (V,3) fp32 in (-radius, radius), t_pos_idx (F,3) ``faces_dtype``[, density_act (R,R,R)]) on the device.
