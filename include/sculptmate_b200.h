@@ -152,6 +152,8 @@ int smb_query_lattice_tc_signs(const float* planes_q, const void* decoder_blob, 
 #define SMB_MC_FLIP 1    /* faces[:, [1,0,2]]            isosurface.py:52 */
 #define SMB_MC_DIV 2     /* verts / vdiv (IEEE fp32)     isosurface.py:53 */
 #define SMB_MC_AFFINE 4  /* verts * vmul + vadd          system.py:185-189 */
+#define SMB_MC_COALESCE 16 /* emit assembles each warp's output run in shared memory and writes it with coalesced 128-byte
+                           * stores: for destinations in PEER memory (NVLink), where scattered 4-byte stores are slow */
 #define SMB_MC_FACES_I32 8 /* `faces` is (F,3) int32 instead of int64: the index width Blender's loop arrays use
                            * (system.py:127-131 hands the array to bpy); same values, half the bytes on PCIe / NVLink */
 
@@ -393,10 +395,13 @@ int smb_bake_interpolate(const float* attr, int channels, const int32_t* faces, 
  *   smb_mesh_loop_colors: loop_colors (3*ntris, 4) fp32, row 3*f + c = (vertex_colors[faces[f][c]], alpha) --
  *     from_pydata numbers polygon loops 3*f + c; alpha = 1 is the column system.py:133-135 appends.
  *     bad_index_flag (optional device int, caller zeroes it) is set when a face index is outside [0, nverts).
- *   smb_mesh_faces_i32: faces narrowed to int32 (MeshLoop.vertex_index is a 32-bit int). */
+ *   smb_mesh_faces_i32: faces narrowed to int32 (MeshLoop.vertex_index is a 32-bit int);
+ *   smb_mesh_faces_i64: the reverse (faces emitted / gathered as int32 widened to the reference's LongTensor width;
+ *     both pointers 16-byte aligned). */
 int smb_mesh_loop_colors(const float* vertex_colors, const int64_t* faces, int64_t nverts, int64_t ntris, float alpha,
                          float* loop_colors, int* bad_index_flag, void* stream);
 int smb_mesh_faces_i32(const int64_t* faces, int64_t ntris, int32_t* faces_i32, void* stream);
+int smb_mesh_faces_i64(const int32_t* faces_i32, int64_t ntris, int64_t* faces, void* stream);
 
 #ifdef __cplusplus
 }

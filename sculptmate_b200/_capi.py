@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsculptmate_b200.so")
 
 OK = 0
 ERR_CUDA, ERR_BAD_ARG, ERR_WORKSPACE, ERR_ARCH, ERR_LEVEL_RANGE, ERR_NO_SURFACE, ERR_CAPACITY = -1, -2, -3, -4, -5, -6, -7
-MC_FLIP, MC_DIV, MC_AFFINE, MC_FACES_I32 = 1, 2, 4, 8
+MC_FLIP, MC_DIV, MC_AFFINE, MC_FACES_I32, MC_COALESCE = 1, 2, 4, 8, 16
 
 
 class DecoderLayout(ctypes.Structure):
@@ -89,6 +89,7 @@ SIGNATURES = {
     "smb_ray_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "smb_mesh_loop_colors": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
     "smb_mesh_faces_i32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "smb_mesh_faces_i64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "smb_query_lattice_tc_signs": (
         c_int,
         [c_void_p, c_void_p, POINTER(DecoderLayout), POINTER(QueryCfg), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float,

@@ -61,6 +61,28 @@ extern "C" int smb_mesh_loop_colors(const float* vertex_colors, const int64_t* f
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 
+// int32 -> int64 (the reference's LongTensor) for faces that crossed NVLink / were emitted as int32: 4 values per thread,
+// one 16-byte load and two 16-byte stores
+__global__ void __launch_bounds__(256) faces_i64_kernel(const int* __restrict__ in, long long n, long long* __restrict__ out) {
+  const long long n4 = n >> 2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(in) + t);
+    reinterpret_cast<longlong2*>(out)[2 * t] = make_longlong2(v.x, v.y);
+    reinterpret_cast<longlong2*>(out)[2 * t + 1] = make_longlong2(v.z, v.w);
+  }
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < (n & 3)) out[4 * n4 + t] = in[4 * n4 + t];
+}
+
+extern "C" int smb_mesh_faces_i64(const int32_t* faces_i32, int64_t ntris, int64_t* faces, void* stream) {
+  if (ntris < 0) return SMB_ERR_BAD_ARG;
+  if (ntris == 0) return SMB_OK;
+  if (!faces || !faces_i32 || ((uintptr_t)faces_i32 & 15) || ((uintptr_t)faces & 15)) return SMB_ERR_BAD_ARG;
+  const long long n = 3 * (long long)ntris;
+  faces_i64_kernel<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(faces_i32, n, reinterpret_cast<long long*>(faces));
+  return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
+}
+
 extern "C" int smb_mesh_faces_i32(const int64_t* faces, int64_t ntris, int32_t* faces_i32, void* stream) {
   if (ntris < 0) return SMB_ERR_BAD_ARG;
   if (ntris == 0) return SMB_OK;

@@ -233,6 +233,7 @@ class PeerGather:
         self.ptrs: list = []  # every rank: [(verts ptr, faces ptr)] * SETS in THIS process' address space
         self.turn = 0
         self.seq = 0
+        self.wide: list = []  # dst: per set, the int64 copy of the faces (when the caller wants the reference's LongTensor)
         self.counts_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_dev = torch.zeros(4, dtype=torch.int64, device=device)
         self.totals_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
@@ -302,6 +303,7 @@ class PeerGather:
                         out.append(int(q.value))
                     self.ptrs.append(tuple(out))
         self.vcap, self.fcap = int(vcap), int(fcap)
+        self.wide = []
         dist.barrier(self.group)
 
     def views(self, k: int, V: int, F: int, faces_dtype: torch.dtype):
@@ -317,7 +319,7 @@ def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precis
     are widened on the destination when ``faces_dtype`` is int64.  ``phases`` (optional dict) receives CUDA events
     at the phase boundaries of this rank (developer timing)."""
     from . import _capi, runtime
-    from ._capi import MC_AFFINE, MC_DIV, MC_FACES_I32, MC_FLIP
+    from ._capi import MC_AFFINE, MC_COALESCE, MC_DIV, MC_FACES_I32, MC_FLIP
 
     dev = scene_code.device
     key = (id(group), dst, str(dev))
@@ -332,7 +334,8 @@ def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precis
     tsr.set_marching_cubes_resolution(R)
     r = tsr.renderer.cfg.radius
     i32 = bool(wire_i32) or faces_dtype == torch.int32
-    flags = MC_FLIP | MC_DIV | MC_AFFINE | (MC_FACES_I32 if i32 else 0)
+    # ranks other than the destination store into PEER memory: coalesced 128-byte stores (staged in shared memory)
+    flags = MC_FLIP | MC_DIV | MC_AFFINE | (MC_FACES_I32 if i32 else 0) | (MC_COALESCE if rank != dst else 0)
 
     def mark(name):
         if phases is not None:
@@ -409,7 +412,15 @@ def _extract_mesh_p2p(tsr, scene_code, resolution, threshold, group, dst, precis
         if rank == dst:
             verts, faces = pg.views(k, V, F, torch.int32 if i32 else torch.int64)
             if i32 and faces_dtype == torch.int64:
-                faces = faces.to(torch.int64)  # widened once on the destination (the wire carried 12 B per triangle)
+                # widened once on the destination (the wire carried 12 B per triangle) into a persistent buffer of the same
+                # double-buffered lifetime as the mapped ones
+                wide = pg.wide[k] if len(pg.wide) > k and pg.wide[k] is not None and pg.wide[k].shape[0] >= F else None
+                if wide is None:
+                    while len(pg.wide) <= k:
+                        pg.wide.append(None)
+                    wide = pg.wide[k] = torch.empty((pg.fcap, 3), dtype=torch.int64, device=dev)
+                _capi.check(lib.smb_mesh_faces_i64(faces.data_ptr(), F, wide.data_ptr(), st), "smb_mesh_faces_i64")
+                faces = wide[:F]
             mark("end")
             return verts, faces
     return None, None

@@ -157,3 +157,24 @@ def test_ragged_and_minimum_shapes_bit_exact(shape):
     assert pend.nverts == len(v_ref) and pend.ntris == len(f_ref)
     np.testing.assert_array_equal(v, v_ref)
     np.testing.assert_array_equal(f, f_ref)
+
+
+@pytest.mark.parametrize("kind,shape", [("gyroid", (33, 32, 64)), ("noise", (9, 32, 32)), ("torus", (64, 64, 64)), ("gyroid", (40, 96, 96))])
+@pytest.mark.parametrize("faces_dtype", [torch.int64, torch.int32])
+def test_emit_variants_equal_the_default(kind, shape, faces_dtype):
+    """The coalescing emit (MC_COALESCE: a warp's output run assembled in shared memory and written with 128-byte stores;
+    what the multi-GPU gather uses for peer memory) and the int32 face width produce the same mesh as the default kernel,
+    on whole grids and on an interior slab with an id offset.  ny * ceil(nz/32) is a multiple of 32 here, the shape class
+    the staged kernel handles; other shapes fall back to the direct kernel inside the library."""
+    from sculptmate_b200 import _capi, runtime
+
+    R = max(shape)
+    g = volume(kind, R, seed=3)[: shape[0], : shape[1], : shape[2]].copy()
+    gd = torch.from_numpy(g).cuda()
+    for emit_last, x_origin, off in ((True, 0, 0), (False, 5, 1000)):
+        pend = runtime.mc_count(gd, sub=0.01, sign=1.0, emit_last_plane=emit_last)
+        v0, f0 = runtime.mc_emit(pend, x_origin=x_origin, flags=FLAGS, vdiv=float(R - 1), vmul=1.74, vadd=-0.87, vertex_id_offset=off)
+        fl = FLAGS | _capi.MC_COALESCE | (_capi.MC_FACES_I32 if faces_dtype == torch.int32 else 0)
+        v1, f1 = runtime.mc_emit(pend, x_origin=x_origin, flags=fl, vdiv=float(R - 1), vmul=1.74, vadd=-0.87, vertex_id_offset=off)
+        assert f1.dtype == faces_dtype and pend.ntris > 0
+        assert torch.equal(v0, v1) and torch.equal(f0, f1.to(torch.int64))
