@@ -249,3 +249,69 @@ def test_full_size_256_mesh_properties(golden):
                                               vdiv=float(R - 1.0), vmul=1.74, vadd=-0.87)
     np.testing.assert_array_equal(vs.cpu().numpy(), vr)
     np.testing.assert_array_equal(fs.cpu().numpy(), fr)
+
+
+@pytest.mark.parametrize("R", [256, 512])
+def test_full_grid_mesh_bit_exact_vs_oracle(golden, R):
+    """BASELINE configs[1] / [2] sizes, WHOLE grid (not sub-slabs): the mesh of the public device path
+    (TSR.extract_mesh_tensors: fused sign ballot, speculative emit) equals the C oracle's on the same density grid,
+    vertices and faces bit for bit; int32 faces carry the same indices."""
+    from oracle import mc_oracle
+
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    ex_dens = m.renderer.query_lattice(m.decoder, tp, R)
+    thr = float(ex_dens[:: max(1, R // 128)].median())
+    v, f = m.extract_mesh_tensors(tp, R, thr)
+    v32, f32 = m.extract_mesh_tensors(tp, R, thr, faces_dtype=torch.int32)
+    assert f32.dtype == torch.int32 and torch.equal(v, v32) and torch.equal(f, f32.to(torch.int64))
+    vr, fr, _ = mc_oracle.marching_cubes_slab(ex_dens.cpu().numpy(), sub=np.float32(thr), flags=7, vdiv=float(R - 1.0), vmul=2 * RADIUS, vadd=-RADIUS)
+    assert len(vr) > 100000
+    np.testing.assert_array_equal(v.cpu().numpy(), vr)
+    np.testing.assert_array_equal(f.cpu().numpy(), fr)
+
+
+def test_scene_cache_is_not_fooled_by_a_recycled_address(golden):
+    """The add-on's loop: scene_codes = model(img); extract_mesh(scene_codes); next image.  The freed scene code's
+    block is handed to the next one by the caching allocator (same address, same shape, _version 0): the renderer must
+    prepare the NEW planes, not reuse the previous image's (round-1 bug: cache keyed on data_ptr)."""
+    g = golden("extract_mesh.npz")
+    m = _model(g)
+    R = 48
+    base = torch.from_numpy(g["triplane"])
+    tp = base.clone().cuda()
+    ptr = tp.data_ptr()
+    d1 = m.renderer.query_lattice(m.decoder, tp, R).clone()
+    del tp
+    hits = 0
+    for k in range(4):
+        tp2 = (base * (1.0 + 0.25 * (k + 1))).cuda()  # a different scene, very likely in the freed block
+        hits += int(tp2.data_ptr() == ptr)
+        d2 = m.renderer.query_lattice(m.decoder, tp2, R)
+        ref = m.renderer.query_lattice(m.decoder, tp2.clone(), R)
+        assert torch.equal(d2, ref) and not torch.equal(d2, d1)
+        c = m.renderer.query_triplane(m.decoder, torch.zeros(5, 3, device="cuda"), tp2)["density"]
+        c_ref = m.renderer.query_triplane(m.decoder, torch.zeros(5, 3, device="cuda"), tp2.clone())["density"]
+        assert torch.equal(c, c_ref)
+        del tp2
+    assert hits > 0, "the allocator never reused the block: the test did not exercise the aliasing case"
+
+
+def test_pending_emit_survives_another_count_of_the_same_shape():
+    """count(A), count(B), emit(A) with equal shapes: the workspace is shared per shape, so emit(A) must notice that
+    its records were overwritten and redo A's pass instead of emitting B's records."""
+    from conftest import volume
+    from sculptmate_b200 import runtime
+
+    a = torch.from_numpy(volume("gyroid", 40)).cuda()
+    b = torch.from_numpy(volume("torus", 40)).cuda()
+    pa = runtime.mc_count(a, sub=0.0, sign=1.0)
+    va, fa = runtime.mc_emit(pa, flags=3, vdiv=39.0)
+    pa2 = runtime.mc_count(a, sub=0.0, sign=1.0)
+    pb = runtime.mc_count(b, sub=0.0, sign=1.0)
+    assert pa2.stale() and not pb.stale()
+    va2, fa2 = runtime.mc_emit(pa2, flags=3, vdiv=39.0)
+    assert torch.equal(va, va2) and torch.equal(fa, fa2)
+    vb, fb = runtime.mc_emit(runtime.mc_count(b, sub=0.0, sign=1.0), flags=3, vdiv=39.0)
+    assert (vb.shape, fb.shape) != (va.shape, fa.shape)

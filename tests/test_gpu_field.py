@@ -3,8 +3,8 @@
 Tolerances (stated, per north_star): the fp32 CUDA-core kernel must agree with the
 reference within fp32 reimplementation noise; the tensor-core lattice kernel feeds fp16
 operands to tcgen05.mma with fp32 accumulation and uses tanh.approx for SiLU, so it is
-held to  max|dlogit| <= 2e-2,  mean|dlogit| <= 2e-4,  max rel err of density_act <= 2e-2
-on N(0,1) planes (logit span ~6), and 5x tighter on the baked field the benchmark uses.
+held to  max|dlogit| <= 1e-2,  mean|dlogit| <= 2e-4,  max rel err of density_act <= 1e-2
+on N(0,1) planes (logit span ~6) -- about 2.5x what is measured -- and to 3e-3 on the baked field the benchmark uses.
 """
 import hashlib
 
@@ -17,7 +17,11 @@ from conftest import golden_decoder
 pytestmark = pytest.mark.gpu
 
 RADIUS = 0.87
-TC_MAX_ABS, TC_MEAN_ABS, TC_MAX_REL = 2e-2, 2e-4, 2e-2
+# measured (round 2): max |dlogit| 4.2e-3 on N(0,1) planes (logit span ~6; worst over R = 8..256), mean 5.6e-5; 8.9e-4 on the
+# baked bench field.  The bounds are 2.5-3x the measurement so that a numerical regression (e.g. a worse activation
+# approximation) fails the suite: 1e-2 on N(0,1) planes, 3e-3 on the baked field (round 1 asserted 2e-2 for both).
+TC_MAX_ABS, TC_MEAN_ABS, TC_MAX_REL = 1e-2, 2e-4, 1e-2
+TC_BAKED_MAX_REL = 3e-3
 
 
 def _pack(g):
@@ -143,7 +147,7 @@ def test_lattice_reference_golden_density(golden):
     dtc = m.renderer.query_lattice(m.decoder, tp, R, precision="tc").cpu().numpy()
     assert np.abs(d32 / g["density_act"] - 1).max() < 2e-5
     # baked field (what the benchmark uses): small logit span -> 5x tighter
-    assert np.abs(dtc / g["density_act"] - 1).max() < TC_MAX_REL / 5
+    assert np.abs(dtc / g["density_act"] - 1).max() < TC_BAKED_MAX_REL
 
 
 def test_full_size_256_sampled_planes(golden):
@@ -203,3 +207,27 @@ def test_nerfmlp_forward_on_features(golden):
     assert out["density"].shape == (3, 70, 1) and out["features"].shape == (3, 70, 3)
     assert np.abs(out["density"].cpu().numpy().reshape(-1, 1) - ref["density"]).max() < 2e-5
     assert np.abs(out["features"].cpu().numpy().reshape(-1, 3) - ref["features"]).max() < 2e-5
+
+
+def test_full_size_256_planes_vs_cpu_oracle(golden):
+    """256^3 tensor-core lattice against the CPU ORACLE itself (numpy fp32 restatement of query_triplane + NeRFMLP, pinned
+    to the reference's goldens), not against another CUDA kernel: three whole x-planes incl. both lattice borders."""
+    from oracle import field_oracle as fo
+    from sculptmate_b200 import runtime
+
+    g = golden("field_64.npz")
+    ws, bs, pack = _pack(g)
+    tp = _triplane64(g)
+    scene = runtime.prepare_scene(tp.cuda(), pack)
+    R = 256
+    ax = runtime.lattice_axis(R, RADIUS, device="cuda")
+    full, raw = runtime.query_lattice(scene, pack, ax, R, RADIUS, -1.0, want_raw=True)
+    axis = fo.grid_axis(R)
+    for i in (0, 131, 255):
+        x, y, z = np.meshgrid(axis[i : i + 1], axis, axis, indexing="ij")
+        pos = fo.scale_tensor(np.stack([x.reshape(-1), y.reshape(-1), z.reshape(-1)], -1), (0, 1), (-RADIUS, RADIUS))
+        ref = fo.query_triplane(pos, tp.numpy(), ws, bs, radius=RADIUS)
+        d = np.abs(raw[i].cpu().numpy().reshape(-1) - (ref["density"].reshape(-1)))
+        rel = np.abs(full[i].cpu().numpy().reshape(-1) / ref["density_act"].reshape(-1) - 1)
+        print(f"plane {i}: max|dlogit| {d.max():.2e} mean {d.mean():.2e} max rel {rel.max():.2e}")
+        assert d.max() <= TC_MAX_ABS and d.mean() <= TC_MEAN_ABS and rel.max() <= TC_MAX_REL
