@@ -16,7 +16,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsculptmate_b200.so")
-SOURCES = ["capi.cu", "field_f32.cu", "field_tc.cu", "mcubes.cu", "sf3d.cu", "field_pts_tc.cu", "field_tc_ta.cu", "field_tc_pair.cu", "mesh_io.cu", "render.cu", "bake.cu"]
+SOURCES = ["capi.cu", "field_f32.cu", "lattice_api.cu", "mcubes.cu", "sf3d.cu", "field_pts_tc.cu", "field_tc_ta.cu", "mesh_io.cu", "render.cu", "bake.cu"]
+# developer build (`python -m sculptmate_b200.build --dev` or SMB_DEV_VARIANTS=1): superseded / experimental lattice kernels and their
+# instrumentation, compiled with -DSMB_DEV_VARIANTS; the product library does not contain them
+DEV_SOURCES = ["field_tc.cu", "field_tc_pair.cu"]
 HEADERS = ["field_common.cuh", "field_tc_common.cuh", "ptx_sm100.cuh", "mc_tables.h", os.path.join("..", "..", "include", "sculptmate_b200.h")]
 
 NVCC_FLAGS = [
@@ -35,9 +38,14 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; the CUDA extension cannot be built")
 
 
+def _dev() -> bool:
+    return bool(os.environ.get("SMB_DEV_VARIANTS")) or "--dev" in sys.argv
+
+
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    for name in SOURCES + HEADERS:
+    h.update(b"dev" if _dev() else b"product")
+    for name in SOURCES + DEV_SOURCES + HEADERS:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -55,9 +63,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     objs: List[str] = []
     procs = []
-    for src in SOURCES:
+    dev = _dev()
+    for src in SOURCES + (DEV_SOURCES if dev else []):
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DSMB_DEV_VARIANTS"] if dev else []), "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

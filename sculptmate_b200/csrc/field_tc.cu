@@ -37,6 +37,7 @@
 //   SiLU    silu(x) = h + h*tanh(h), h = x/2; the 1/2 is folded into weights and
 //            biases on the host, so one MUFU.TANH + one FFMA per activation.  The SFU
 //            (16 tanh/clk/SM, 576 per sample) is the practical bound of this kernel.
+#ifdef SMB_DEV_VARIANTS  // developer build only (python -m sculptmate_b200.build --dev): superseded by field_tc_ta.cu
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -384,124 +385,18 @@ static int launch_tc(const TcParams& p, int sms, cudaStream_t st) {
 
 }  // namespace smb
 
-using namespace smb;
 
-static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob,
-                                 const smb_decoder_layout* layout, const smb_query_cfg* cfg,
-                                 const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
-                                 float* out_density, bool want_signs, float sub, float sign, void* mc_workspace,
-                                 size_t mc_workspace_bytes, void* stream) {
-  if (!planes_q || !decoder_blob || !layout || !cfg || !axis_u || !out_density_act) return SMB_ERR_BAD_ARG;
-  if (R < 2 || nx < 0 || x_begin < 0 || x_begin + nx > R) return SMB_ERR_BAD_ARG;
-  if (nx == 0) return SMB_OK;
-  const int nh = (int)layout->n_hidden;
-  if (nh < 2 || nh > kMaxHidden) return SMB_ERR_BAD_ARG;
-  // rows of the (.,z) planes one 128-sample segment can touch (+2 for the taps, +1 slack)
-  int rows;
-  {
-    double span = 127.0 * cfg->Hp / (double)(R - 1);
-    rows = (int)span + 3;
-    if (rows > cfg->Hp + 2) rows = cfg->Hp + 2;  // rows -1 .. Hp (the two zero borders)
-    if (rows < 2) rows = 2;
-    if (rows > kTRowsMax) return SMB_ERR_BAD_ARG;
-  }
-  // layout contract: [hidden | head | bias_half | bias_final] contiguous in the blob
-  if (layout->off_tc_final != layout->off_tc_hidden + (uint32_t)(nh - 1) * kWBytes ||
-      layout->off_bias_half != layout->off_tc_final + kWFinalBytes ||
-      layout->off_bias_final != layout->off_bias_half + (uint32_t)nh * kHid * 4)
-    return SMB_ERR_BAD_ARG;
-
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-
-  TcParams p{};
-  p.planes_q = planes_q;
-  p.tc_weights = static_cast<const unsigned char*>(decoder_blob) + layout->off_tc_hidden;
-  p.tc_biasblk = static_cast<const unsigned char*>(decoder_blob) + layout->off_tc_biasblk;
-  p.bias0_half = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_bias_half);
-  p.axis_u = axis_u;
-  p.R = R;
-  p.x_begin = x_begin;
-  p.nx = nx;
-  p.H = cfg->Hp;
-  p.W = cfg->Wp;
-  p.align_corners = cfg->align_corners;
-  p.n_hidden = nh;
-  p.trows = rows;
-  p.slot_bytes = tc_slot_bytes(rows);
-  p.density_bias = cfg->density_bias;
-  p.out_act = out_density_act;
-  p.out_raw = out_density;
-  {
-    const char* e = getenv("SMB_TC_TRACE");
-    p.dbg = e ? atoi(e) : 0;
-    e = getenv("SMB_TC_WAITNS");
-    p.wait_ns = e ? atoi(e) : 2000;
-    e = getenv("SMB_TC_TA_STAGGER");
-    p.stagger_clk = e ? atoi(e) : 0;
-    e = getenv("SMB_TC_TA_TOKENS");
-    p.xu_tokens = e ? atoi(e) : 0;
-  }
-  // as many consumer warpgroups (2 slots each) as shared memory allows
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if (want_signs) {
-    if (!mc_workspace || smb_mc_workspace_bytes(nx, R, R) > mc_workspace_bytes) return SMB_ERR_WORKSPACE;
-    p.sign_out = static_cast<uint32_t*>(mc_workspace);  // the sign masks are the first region of an MC workspace
-    p.sign_sub = sub;
-    p.sign_mul = sign;
-    p.sign_wz = (R + 31) / 32;
-  }
-  // default: activations-in-TMEM kernel (field_tc_ta.cu); SMB_TC_VARIANT=smem selects this file's
-  // shared-memory-A kernel (kept for comparison and as the home of the timeline instrumentation)
-  {
-    const char* v = getenv("SMB_TC_VARIANT");
-    if ((!p.dbg || p.dbg == 3) && v && v[0] == 'p') {  // SMB_TC_VARIANT=pair: round-2 experiment (field_tc_pair.cu), not faster yet
-      const char* e = getenv("SMB_TC_POLY");
-      const int rc2 = launch_tc_pair(p, sms, e ? atoi(e) : 0, st);
-      if (rc2 != SMB_ERR_BAD_ARG) return rc2;  // eight table buffers did not fit in shared memory: kernel below
-    }
-    if ((!p.dbg || p.dbg == 2) && !(v && v[0] == 's')) return launch_tc_ta(p, sms, st);
-  }
-  p.sign_out = nullptr;  // the shared-memory-A kernel does not ballot: stand-alone sign pass below
-  if (p.dbg) {  // SMB_TC_TRACE=1: developer timeline instrumentation (tools/trace_lattice.py)
-    rc = launch_tc<3, true>(p, sms, st);
-  } else {
-    rc = launch_tc<3, false>(p, sms, st);
-    if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<2, false>(p, sms, st);
-    if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<1, false>(p, sms, st);
-  }
-  if (rc == SMB_OK && want_signs) rc = launch_mc_signs(out_density_act, nx, R, R, sub, sign, mc_workspace, mc_workspace_bytes, st);
+namespace smb {
+int launch_tc_smem(const TcParams& p, int sms, bool trace, cudaStream_t st) {
+  if (trace) return launch_tc<3, true>(p, sms, st);
+  int rc = launch_tc<3, false>(p, sms, st);
+  if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<2, false>(p, sms, st);
+  if (rc == SMB_ERR_BAD_ARG) rc = launch_tc<1, false>(p, sms, st);
   return rc;
 }
-
-extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_blob,
-                                    const smb_decoder_layout* layout, const smb_query_cfg* cfg,
-                                    const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
-                                    float* out_density, void* stream) {
-  return query_lattice_tc_impl(planes_q, decoder_blob, layout, cfg, axis_u, R, x_begin, nx, out_density_act, out_density, false, 0.f,
-                               1.f, nullptr, 0, stream);
-}
-
-extern "C" int smb_query_lattice_tc_signs(const float* planes_q, const void* decoder_blob,
-                                          const smb_decoder_layout* layout, const smb_query_cfg* cfg,
-                                          const float* axis_u, int R, int x_begin, int nx, float* out_density_act,
-                                          float* out_density, float sub, float sign, void* mc_workspace,
-                                          size_t mc_workspace_bytes, void* stream) {
-  if (!mc_workspace) return SMB_ERR_BAD_ARG;
-  return query_lattice_tc_impl(planes_q, decoder_blob, layout, cfg, axis_u, R, x_begin, nx, out_density_act, out_density, true, sub,
-                               sign, mc_workspace, mc_workspace_bytes, stream);
-}
-
-// developer instrumentation: copies the clock64 trace of the last SMB_TC_TRACE=1 launch
-namespace smb { int pair_debug_dump(); int pair_prof_read(unsigned int* host, int n); int pair_evt_read(unsigned int* host, int n); }
-extern "C" int smb_debug_pair_evt(unsigned int* host, int n) { return smb::pair_evt_read(host, n); }
-extern "C" int smb_debug_pair_prof(unsigned int* host, int n) { return smb::pair_prof_read(host, n); }
-extern "C" int smb_debug_pair_dump(void) { return smb::pair_debug_dump(); }
-extern "C" int smb_debug_read_trace_ta(long long* host, int n) { return smb::read_trace_ta(host, n); }
-
-extern "C" int smb_debug_read_trace(long long* host, int n) {
+int read_trace_smem(long long* host, int n) {
   if (!host || n <= 0 || n > 4 * 512 * 4) return SMB_ERR_BAD_ARG;
-  return smb_check(cudaMemcpyFromSymbol(host, smb::g_trace, sizeof(long long) * n));
+  return smb_check(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * n));
 }
+}  // namespace smb
+#endif  // SMB_DEV_VARIANTS

@@ -1,4 +1,6 @@
-// K1, round 2: lattice field kernel with TILE PAIRS SHARING ONE ACCUMULATOR (default tensor-core lattice kernel).
+// K1 experiment, round 2: lattice field kernel with TILE PAIRS SHARING ONE ACCUMULATOR.  NOT the default: measured 3.04 ms
+// at 256^3 against 2.89 ms of field_tc_ta.cu; kept (developer build) with its instrumentation because DESIGN.md argues
+// from these measurements.
 //
 // Path (reference): TSR.extract_mesh's density query -- F.grid_sample x3 + NeRFMLP over the R^3 lattice
 // (/root/reference/TripoSR/tsr/models/nerf_renderer.py:41-91, tsr/models/network_utils.py:35-124).
@@ -33,6 +35,7 @@
 //   a_ready[s]             consumers -> issuer: activation columns A_s written (tcgen05.wait::st done), 4 arrivals
 //   d_free[h]              consumers -> issuer: half h of D has been read into registers, 4 arrivals
 //   acc[s][h]              issuer -> consumers: tcgen05.commit after the MMAs of half h of tile s
+#ifdef SMB_DEV_VARIANTS  // developer build only: an experiment that did not beat field_tc_ta.cu
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -550,3 +553,4 @@ int launch_tc_pair(const TcParams& p, int sms, int poly_pairs, cudaStream_t st) 
 }
 
 }  // namespace smb
+#endif  // SMB_DEV_VARIANTS

@@ -30,6 +30,12 @@
 
 namespace smb {
 
+#ifdef SMB_DEV_VARIANTS
+constexpr bool kDev = true;  // developer build: bias-MMA / polynomial / token / stagger / trace variants are compiled
+#else
+constexpr bool kDev = false;  // product build: one kernel (5 warpgroups) and its 4-warpgroup fallback, no experiment code
+#endif
+
 // TMEM columns per warpgroup: 64 accumulator + 32 activation (+ 8 constant bias columns, padded to 128, with kBiasMMA)
 __host__ __device__ constexpr int ta_cols_per_wg(bool bias_mma) { return bias_mma ? 128 : 96; }
 
@@ -59,7 +65,11 @@ __device__ __forceinline__ float silu_mix(float h, int i) {
 
 // developer instrumentation (kTrace, SMB_TC_TRACE=2): clock64 stamps of block 0, every consumer warp, first kTraceSteps layer steps
 constexpr int kTraceSteps = 160;
+#ifdef SMB_DEV_VARIANTS
 __device__ long long g_trace_ta[5 * 4 * kTraceSteps * 4];
+#else
+__device__ long long g_trace_ta[4];  // kTrace is never instantiated in the product build
+#endif
 
 template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly, bool kTrace = false>
 __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc_ta_kernel(TcParams p) {
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
       mbar_init(smem_u32(&bars[3 + 3 * g]), 1);  // acc_full: tcgen05.commit
     }
     mbar_fence_init();
-    for (int q = 0; q < 4; ++q) xu_sem[q] = p.xu_tokens;
+    for (int q = 0; q < 4; ++q) xu_sem[q] = kDev ? p.xu_tokens : 0;
   }
   if (wid == 0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     // the SFU idle for a whole MMA round trip per step.  Two ways to break it: a one-off start offset
     // per warpgroup (stagger_clk), or a semaphore that lets only xu_tokens warps of a sub-partition
     // into an activation stretch at a time (the others wait while their MMA would be waiting anyway).
-    const bool use_tok = p.xu_tokens > 0;
+    const bool use_tok = kDev && p.xu_tokens > 0;
     auto xu_acquire = [&]() {
       if (!use_tok) return;
       if (lane == 0) {
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         mbar_wait_sleep(smem_u32(&bars[1 + 3 * wg]), par_t, (uint32_t)p.wait_ns);
         par_t ^= 1u;
         if (kTrace) tr1 = clock64();
-        if (n == 0 && p.stagger_clk > 0 && wg > 0) {
+        if (kDev && n == 0 && p.stagger_clk > 0 && wg > 0) {
           const long long t0 = clock64();
           while (clock64() - t0 < (long long)wg * p.stagger_clk) {}
         }
@@ -366,30 +376,32 @@ static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
 
 // Default: FIVE consumer warpgroups (all of tensor memory: 5 x 96 = 480 columns; 768 threads, the producer
 // warpgroup hands 40 of its 80 registers to the consumers with setmaxnreg so that they run at 88), bias in the
-// epilogue, every tanh on the SFU, no stagger, no tokens: 2.88 ms at 256^3 against 2.93 ms with four warpgroups on
-// the same GPU (SMB_TC_TA_WG=4).  The other variants are kept as developer switches because their measurements are
-// what DESIGN.md 4/K1 argues from (tools/sweep_lattice.py): SMB_TC_TA_BIAS=1 (bias through a fifth
-// K=16 MMA: 2.89 ms), SMB_TC_TA_POLY=4 (4 of 16 tanh on the FMA pipe: 3.22 ms; with the bias MMA
-// 3.36 ms), SMB_TC_TA_STAGGER=<clk> (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms).
+// epilogue, every tanh on the SFU: 2.88 ms at 256^3 against 2.93 ms with four warpgroups on the same GPU.  The
+// product library instantiates exactly these two (the second is the fallback when five table buffers do not fit
+// in shared memory).  A developer build (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements
+// DESIGN.md 4/K1 argues from (tools/sweep_lattice.py): SMB_TC_TA_BIAS=1 (bias through a fifth K=16 MMA: 2.89 ms),
+// SMB_TC_TA_POLY=4 (4 of 16 tanh on the FMA pipe: 3.22 ms; with the bias MMA 3.36 ms), SMB_TC_TA_STAGGER=<clk>
+// (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms), SMB_TC_TA_WG=4, SMB_TC_TRACE=2 (timeline).
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
-  const char* v = getenv("SMB_TC_TA_BIAS");
-  const bool bias = v ? atoi(v) != 0 : false;
-  v = getenv("SMB_TC_TA_POLY");
-  const int poly = v ? atoi(v) : 0;
-  v = getenv("SMB_TC_TA_WG");
-  const int wgs = v ? atoi(v) : 5;
+#ifdef SMB_DEV_VARIANTS
+  static const int bias = getenv("SMB_TC_TA_BIAS") ? atoi(getenv("SMB_TC_TA_BIAS")) : 0;
+  static const int poly = getenv("SMB_TC_TA_POLY") ? atoi(getenv("SMB_TC_TA_POLY")) : 0;
+  static const int wgs = getenv("SMB_TC_TA_WG") ? atoi(getenv("SMB_TC_TA_WG")) : 5;
   if (p.dbg == 2) return wgs == 5 ? launch_tc_ta_n<5, 4, false, 0, true>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0, true>(p, sms, st);
-  if (wgs == 5 && !bias && !poly) {
-    const int rc = launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
-    if (rc != SMB_ERR_BAD_ARG) return rc;  // five table buffers did not fit in shared memory: four warpgroups below
-  }
   if (bias) return poly ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
-  return poly ? launch_tc_ta_n<4, 4, false, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
+  if (poly) return launch_tc_ta_n<4, 4, false, 4>(p, sms, st);
+  if (wgs != 5) return launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
+#endif
+  const int rc = launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
+  if (rc != SMB_ERR_BAD_ARG) return rc;  // five table buffers did not fit in shared memory: four warpgroups
+  return launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
 }
 
+#ifdef SMB_DEV_VARIANTS
 int read_trace_ta(long long* host, int n) {
   if (!host || n <= 0 || n > 5 * 4 * kTraceSteps * 4) return SMB_ERR_BAD_ARG;
   return smb_check(cudaMemcpyFromSymbol(host, g_trace_ta, sizeof(long long) * n));
 }
+#endif
 
 }  // namespace smb

@@ -615,7 +615,8 @@ def prepare_planes_cl(triplane: torch.Tensor) -> ScenePlanes:
     return ScenePlanes(cl, None, Hp, Wp)
 
 
-_sf3d_heads_cache: Dict[int, Tuple[Tuple, torch.Tensor]] = {}
+# weak in the decoder module: an entry dies with its decoder (no growth, no stale hit on a recycled id())
+_sf3d_heads_cache: "weakref.WeakKeyDictionary[torch.nn.Module, Tuple[Tuple, torch.Tensor]]" = weakref.WeakKeyDictionary()
 
 
 def get_sf3d_heads(decoder: torch.nn.Module, device: torch.device) -> torch.Tensor:
@@ -630,7 +631,7 @@ def get_sf3d_heads(decoder: torch.nn.Module, device: torch.device) -> torch.Tens
         for m in lin:
             params += [m.weight, m.bias]
     key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (str(device),)
-    hit = _sf3d_heads_cache.get(id(decoder))
+    hit = _sf3d_heads_cache.get(decoder)
     if hit is not None and hit[0] == key:
         return hit[1]
     total = _capi.load().smb_sf3d_heads_floats()
@@ -645,7 +646,7 @@ def get_sf3d_heads(decoder: torch.nn.Module, device: torch.device) -> torch.Tens
         off = start + (off - start + 3) // 4 * 4  # each head is padded to a multiple of 4 floats
     assert off == total, (off, total)
     blob = blob.to(device)
-    _sf3d_heads_cache[id(decoder)] = (key, blob)
+    _sf3d_heads_cache[decoder] = (key, blob)
     return blob
 
 

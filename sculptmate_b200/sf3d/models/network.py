@@ -27,21 +27,42 @@ class HeadSpec:
     out_bias: float = 0.0
 
 
+# eps of the reference's normalize() helper per dtype (sf3d/models/utils.py:57-76): F.normalize's own default
+# (1e-12) is NOT what the shipped perturb_normal head uses
+_NORMALIZE_EPS = {torch.float16: 1e-4, torch.bfloat16: 1e-4, torch.float32: 1e-7, torch.float64: 1e-8}
+
+
+def _normalize(x: torch.Tensor, dim: int = -1) -> torch.Tensor:
+    return F.normalize(x, dim=dim, p=2, eps=_NORMALIZE_EPS[x.dtype])
+
+
+def _lin2srgb(x: torch.Tensor) -> torch.Tensor:
+    return torch.where(x > 0.0031308, torch.pow(torch.clamp(x, min=0.0031308), 1.0 / 2.4) * 1.055 - 0.055, 12.92 * x).clamp(0.0, 1.0)
+
+
+# name -> callable, the full table of network.py:98-136 (forward semantics; trunc_exp's forward is exp, its clamp only
+# acts in backward, :85-92)
+_ACTIVATIONS = {
+    "none": lambda x: x, "linear": lambda x: x, "identity": lambda x: x,
+    "lin2srgb": _lin2srgb,
+    "exp": torch.exp, "trunc_exp": torch.exp,
+    "shifted_exp": lambda x: torch.exp(x - 1.0), "shifted_trunc_exp": lambda x: torch.exp(x - 1.0),
+    "sigmoid": torch.sigmoid, "tanh": torch.tanh,
+    "shifted_softplus": lambda x: F.softplus(x - 1.0),
+    "scale_-11_01": lambda x: x * 0.5 + 0.5,
+    "negative": lambda x: -x,
+    "normalize_channel_last": _normalize,
+    "normalize_channel_first": lambda x: _normalize(x, dim=1),
+}
+
+
 def get_activation(name) -> Callable:
-    """network.py:98-136 (the names the shipped config uses)."""
+    """network.py:98-136: every name the reference knows, else torch.nn.functional.<name>, else ValueError."""
     if name is None:
         return lambda x: x
     name = name.lower()
-    if name in ("none", "linear", "identity"):
-        return lambda x: x
-    if name in ("exp", "trunc_exp"):  # trunc_exp forward is exp (network.py:85)
-        return lambda x: torch.exp(x)
-    if name == "sigmoid":
-        return lambda x: torch.sigmoid(x)
-    if name == "tanh":
-        return lambda x: torch.tanh(x)
-    if name == "normalize_channel_last":
-        return lambda x: F.normalize(x, dim=-1)
+    if name in _ACTIVATIONS:
+        return _ACTIVATIONS[name]
     try:
         return getattr(F, name)
     except AttributeError:

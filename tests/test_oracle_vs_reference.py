@@ -130,3 +130,27 @@ def test_rays_intersect_bbox_mirror_vs_live_reference():
     want2 = ref.utils.rays_intersect_bbox(o.view(40, 100, 3), d.view(40, 100, 3), RADIUS)
     for a, b in zip(got2, want2):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_sf3d_activation_table_vs_live_reference():
+    """Every name of the reference's get_activation (sf3d/models/network.py:98-136) gives the same values through the
+    drop-in's table, including normalize's dtype-dependent eps (models/utils.py:57-76) -- ADVICE round 1."""
+    from sculptmate_b200.sf3d.models import network as mine
+
+    ref = ref_shim.load_sf3d()
+    import importlib
+
+    ref_net = importlib.import_module("sf3d.models.network")
+    torch.manual_seed(0)
+    x = torch.randn(64, 7, 3) * 2
+    x[0] = 0.0  # zero vectors: the eps of normalize decides the result
+    x[1] = 1e-9
+    names = ["none", "linear", "identity", "lin2srgb", "exp", "shifted_exp", "trunc_exp", "shifted_trunc_exp", "sigmoid", "tanh",
+             "shifted_softplus", "scale_-11_01", "negative", "normalize_channel_last", "normalize_channel_first", "relu", "silu", None]
+    for n in names:
+        a, b = mine.get_activation(n)(x), ref_net.get_activation(n)(x)
+        assert torch.equal(a, b), n
+    assert torch.equal(mine.get_activation("normalize_channel_last")(x.half()), ref_net.get_activation("normalize_channel_last")(x.half()))
+    with pytest.raises(ValueError):
+        mine.get_activation("no_such_activation")
+    del ref
