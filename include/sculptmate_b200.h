@@ -268,6 +268,15 @@ int smb_extract_mesh_device(smb_extractor* ex, const float* triplane_dev, int re
                             float* verts_out, int64_t verts_capacity, void* faces_out, int64_t faces_capacity,
                             float* density_out, int emit_only, void* stream, int64_t* nverts, int64_t* ntris);
 
+/* Device triplane in, mesh out in the CALLER's pinned host buffers (capacities in vertices / triangles): the plugin call
+ * TSR.extract_mesh ends in `.cpu().numpy()` of both arrays (system.py:200).  Slab pipeline as in smb_extract_mesh_host (the mesh
+ * of slab k crosses PCIe while slab k+1 is computed) but into buffers the caller owns, so results never alias across calls.
+ * SMB_ERR_CAPACITY with *nverts / *ntris set when the mesh does not fit (first call: pass capacities 0 to learn the sizes).
+ * Runs on the handle's own streams, ordered after `stream`; returns after the copies have landed. */
+int smb_extract_mesh_device_to_host(smb_extractor* ex, const float* triplane_dev, int resolution, float threshold, int face_flags,
+                                    float* verts_host_pinned, int64_t verts_capacity, void* faces_host_pinned,
+                                    int64_t faces_capacity, void* stream, int64_t* nverts, int64_t* ntris);
+
 /* Optional phase timing of smb_extract_mesh_device: CUDA events on the caller's stream around prepare / the lattice
  * kernel / marching cubes (count + totals + emit); smb_extractor_last_timing returns the last call's durations in ms
  * (valid after that call returned: it synchronises the stream).  This is how bench.py measures the dominant kernel

@@ -140,6 +140,10 @@ SIGNATURES = {
     ),
     "smb_extractor_pinned_input": (c_int, [c_void_p, POINTER(POINTER(c_float))]),
     "smb_extractor_set_faces_i32": (c_int, [c_void_p, c_int]),
+    "smb_extract_mesh_device_to_host": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_int64), POINTER(c_int64)],
+    ),
     "smb_extractor_enable_timing": (c_int, [c_void_p, c_int]),
     "smb_extractor_last_timing": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
     "smb_extract_mesh_device": (

@@ -371,13 +371,18 @@ extern "C" int smb_extractor_set_axis(smb_extractor* ex, int R, const float* axi
 // part of the mesh to pinned memory on a second stream while the next slab is being computed.
 // Returns 1 when the mesh was delivered, 0 when the caller must take the single-pass path
 // (empty surface, or the mesh outgrew the remembered capacities), < 0 on error.
-static int extract_pipelined(smb_extractor* ex, int R, float threshold, int64_t* nverts, int64_t* ntris) {
+// dst_v / dst_f: pinned host destinations (capacities in vertices / triangles); null = the handle's own staging buffers.
+static int extract_pipelined(smb_extractor* ex, int R, float threshold, int64_t* nverts, int64_t* ntris, int faces_i32,
+                             float* dst_v = nullptr, size_t dst_v_cap = 0, void* dst_f = nullptr, size_t dst_f_cap = 0) {
   const int S = ex->n_slabs;
-  const size_t fbytes = ex->faces_i32 ? sizeof(int32_t) : sizeof(int64_t);  // buffers are sized for int64 either way
+  const size_t fbytes = faces_i32 ? sizeof(int32_t) : sizeof(int64_t);  // device buffers are sized for int64 either way
   if (S < 2 || ex->verts_cap == 0 || ex->faces_cap == 0 || R - 1 < 8 * S) return 0;
+  float* host_v = dst_v ? dst_v : ex->verts_pin;
+  char* host_f = reinterpret_cast<char*>(dst_f ? dst_f : (void*)ex->faces_pin);
+  const size_t host_v_cap = dst_v ? dst_v_cap : ex->verts_pin_cap, host_f_cap = dst_f ? dst_f_cap : ex->faces_pin_cap;
   cudaStream_t st = ex->stream;
   const double r = (double)ex->cfg.radius;
-  const int flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (ex->faces_i32 ? SMB_MC_FACES_I32 : 0);
+  const int flags = SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (faces_i32 ? SMB_MC_FACES_I32 : 0);
   const float vdiv = (float)(R - 1.0), vmul = (float)(r - (-r)), vadd = (float)(-r);
   // geometric slab sizes (at least 8 cell layers each), first slab largest
   const int cells = R - 1;
@@ -420,20 +425,20 @@ static int extract_pipelined(smb_extractor* ex, int R, float threshold, int64_t*
     EX_CUDA(cudaEventSynchronize(ex->slab_done[k]));
     const int64_t Vk = ex->slab_counts_pin[k].nverts, Fk = ex->slab_counts_pin[k].ntris;
     fits = fits && (size_t)(V + Vk) <= ex->verts_cap && (size_t)(F + Fk) <= ex->faces_cap &&
-           (size_t)(V + Vk) <= ex->verts_pin_cap && (size_t)(F + Fk) <= ex->faces_pin_cap;
+           (size_t)(V + Vk) <= host_v_cap && (size_t)(F + Fk) <= host_f_cap;
     if (fits) {
       EX_CUDA(cudaStreamWaitEvent(ex->copy_stream, ex->slab_done[k], 0));
-      if (Vk) EX_CUDA(cudaMemcpyAsync(ex->verts_pin + 3 * V, ex->verts_dev + 3 * V, sizeof(float) * 3 * Vk, cudaMemcpyDeviceToHost, ex->copy_stream));
-      if (Fk) EX_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(ex->faces_pin) + fbytes * 3 * F, reinterpret_cast<char*>(ex->faces_dev) + fbytes * 3 * F,
+      if (Vk) EX_CUDA(cudaMemcpyAsync(host_v + 3 * V, ex->verts_dev + 3 * V, sizeof(float) * 3 * Vk, cudaMemcpyDeviceToHost, ex->copy_stream));
+      if (Fk) EX_CUDA(cudaMemcpyAsync(host_f + fbytes * 3 * F, reinterpret_cast<char*>(ex->faces_dev) + fbytes * 3 * F,
                                       fbytes * 3 * Fk, cudaMemcpyDeviceToHost, ex->copy_stream));
     }
     V += Vk;
     F += Fk;
   }
   EX_CUDA(cudaStreamSynchronize(ex->copy_stream));
-  if (!fits || V == 0 || F == 0) return 0;
   *nverts = V;
   *ntris = F;
+  if (!fits || V == 0 || F == 0) return 0;
   return 1;
 }
 
@@ -449,7 +454,7 @@ extern "C" int smb_extract_mesh_host(smb_extractor* ex, const float* triplane_ho
   EX_CUDA(cudaMemcpyAsync(ex->triplane_dev, ex->triplane_pin, tp_bytes, cudaMemcpyHostToDevice, st));
   rc = smb_scene_prepare(ex->triplane_dev, ex->cfg.Hp, ex->cfg.Wp, ex->blob_dev, &ex->layout, nullptr, ex->planes_q, st);
   if (rc != SMB_OK) return rc;
-  rc = extract_pipelined(ex, R, threshold, nverts, ntris);
+  rc = extract_pipelined(ex, R, threshold, nverts, ntris, ex->faces_i32);
   if (rc < 0) return rc;
   if (rc == 1) {
     *verts_host = ex->verts_pin;
@@ -575,6 +580,82 @@ extern "C" int smb_extract_mesh_host_textured(smb_extractor* ex, const float* tr
   EX_CUDA(cudaStreamSynchronize(st));
   *colors_host = ex->colors_pin;
   if (loop_colors_host) *loop_colors_host = ex->loop_colors_pin;
+  return SMB_OK;
+}
+
+// Device triplane in, mesh in the CALLER's pinned host buffers out: what the Python plugin call TSR.extract_mesh needs
+// (tsr/system.py:171-200 ends in .cpu().numpy() of both arrays).  Uses the slab pipeline of smb_extract_mesh_host -- the mesh of
+// slab k crosses PCIe while slab k+1 is computed -- but writes straight into buffers the caller owns (e.g. a torch tensor
+// from the caching pinned allocator), so nothing aliases across calls and nothing is copied twice.  The handle keeps device
+// staging buffers of at least the given capacities.  SMB_ERR_CAPACITY (+ sizes) when the mesh does not fit: retry with
+// larger buffers.  Work runs on the handle's own streams, ordered after `stream` (where triplane_dev was produced).
+extern "C" int smb_extract_mesh_device_to_host(smb_extractor* ex, const float* triplane_dev, int R, float threshold, int face_flags,
+                                               float* verts_host_pinned, int64_t verts_capacity, void* faces_host_pinned,
+                                               int64_t faces_capacity, void* stream, int64_t* nverts, int64_t* ntris) {
+  if (!ex || !triplane_dev || R < 2 || !nverts || !ntris || verts_capacity < 0 || faces_capacity < 0) return SMB_ERR_BAD_ARG;
+  if ((verts_capacity > 0 && !verts_host_pinned) || (faces_capacity > 0 && !faces_host_pinned)) return SMB_ERR_BAD_ARG;
+  int rc = ensure_resolution(ex, R);
+  if (rc != SMB_OK) return rc;
+  const int i32 = (face_flags & SMB_MC_FACES_I32) ? 1 : 0;
+  cudaStream_t st = ex->stream;
+  *nverts = 0;
+  *ntris = 0;
+  // order the handle's stream after the producer of triplane_dev
+  cudaEvent_t ready = ex->slab_done[smb_extractor::kSlabs - 1];
+  EX_CUDA(cudaEventRecord(ready, (cudaStream_t)stream));
+  EX_CUDA(cudaStreamWaitEvent(st, ready, 0));
+  if ((size_t)verts_capacity > ex->verts_cap) {
+    EX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(ex->verts_dev);
+    ex->verts_cap = 0;
+    EX_CUDA(cudaMalloc(&ex->verts_dev, sizeof(float) * 3 * (size_t)verts_capacity));
+    ex->verts_cap = (size_t)verts_capacity;
+  }
+  if ((size_t)faces_capacity > ex->faces_cap) {
+    EX_CUDA(cudaStreamSynchronize(st));
+    cudaFree(ex->faces_dev);
+    ex->faces_cap = 0;
+    EX_CUDA(cudaMalloc(&ex->faces_dev, sizeof(int64_t) * 3 * (size_t)faces_capacity));
+    ex->faces_cap = (size_t)faces_capacity;
+  }
+  rc = smb_scene_prepare(triplane_dev, ex->cfg.Hp, ex->cfg.Wp, ex->blob_dev, &ex->layout, nullptr, ex->planes_q, st);
+  if (rc != SMB_OK) return rc;
+  if (verts_capacity > 0 && faces_capacity > 0) {
+    rc = extract_pipelined(ex, R, threshold, nverts, ntris, i32, verts_host_pinned, (size_t)verts_capacity, faces_host_pinned,
+                           (size_t)faces_capacity);
+    if (rc < 0) return rc;
+    if (rc == 1) return SMB_OK;
+    if (*nverts > 0 && *ntris > 0 && R - 1 >= 8 * ex->n_slabs && ex->n_slabs >= 2) return SMB_ERR_CAPACITY;  // sizes are set
+  }
+  // first call / tiny lattice / empty surface: single pass to learn the sizes (or classify the error)
+  rc = smb_query_lattice_tc_signs(ex->planes_q, ex->blob_dev, &ex->layout, &ex->cfg, ex->axis_dev, R, 0, R, ex->density, nullptr, threshold,
+                                  1.0f, ex->mc_ws, ex->mc_ws_bytes, st);
+  if (rc != SMB_OK) return rc;
+  rc = smb_mc_count_presigned(R, R, R, 1, ex->mc_ws, ex->mc_ws_bytes, ex->counts_dev, st);
+  if (rc != SMB_OK) return rc;
+  EX_CUDA(cudaMemcpyAsync(ex->counts_pin, ex->counts_dev, sizeof(smb_mc_counts), cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaStreamSynchronize(st));
+  const int64_t V = ex->counts_pin->nverts, F = ex->counts_pin->ntris;
+  *nverts = V;
+  *ntris = F;
+  if (V == 0 || F == 0) {
+    rc = smb_grid_minmax(ex->density, (int64_t)R * R * R, threshold, 1.0f, ex->minmax_dev, st);
+    if (rc != SMB_OK) return rc;
+    EX_CUDA(cudaMemcpyAsync(ex->minmax_pin, ex->minmax_dev, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    EX_CUDA(cudaStreamSynchronize(st));
+    if (ex->minmax_pin[0] > 0.0f || ex->minmax_pin[1] < 0.0f) return SMB_ERR_LEVEL_RANGE;
+    return SMB_ERR_NO_SURFACE;
+  }
+  if (V > verts_capacity || F > faces_capacity) return SMB_ERR_CAPACITY;
+  // fits, but the pipeline was not applicable (tiny lattice): emit + copy in one go
+  const double r = (double)ex->cfg.radius;
+  rc = smb_mc_emit_bounded(ex->density, R, R, R, threshold, 1.0f, 0, 1, SMB_MC_FLIP | SMB_MC_DIV | SMB_MC_AFFINE | (i32 ? SMB_MC_FACES_I32 : 0),
+                           (float)(R - 1.0), (float)(r - (-r)), (float)(-r), 0, ex->mc_ws, ex->verts_dev, (int64_t)ex->verts_cap, ex->faces_dev,
+                           (int64_t)ex->faces_cap, st);
+  if (rc != SMB_OK) return rc;
+  EX_CUDA(cudaMemcpyAsync(verts_host_pinned, ex->verts_dev, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaMemcpyAsync(faces_host_pinned, ex->faces_dev, (i32 ? sizeof(int32_t) : sizeof(int64_t)) * 3 * F, cudaMemcpyDeviceToHost, st));
+  EX_CUDA(cudaStreamSynchronize(st));
   return SMB_OK;
 }
 

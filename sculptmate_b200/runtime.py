@@ -473,6 +473,7 @@ class MeshExtractor:
             check(lib.smb_extractor_create(W, B, len(ws) - 1, float(radius), float(density_bias), int(Hp), int(Wp), ctypes.byref(self._h)), "smb_extractor_create")
         self._axis_set = set()
         self._caps: Dict[int, Tuple[int, int]] = {}
+        self._host_caps: Dict[int, Tuple[int, int]] = {}
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
@@ -537,6 +538,44 @@ class MeshExtractor:
             self._caps.pop(next(iter(self._caps)))
         out = (verts[: nv.value], faces[: nt.value])
         return out + (dens,) if want_density else out
+
+
+    def extract_to_host(self, triplane: torch.Tensor, resolution: int, threshold: float, faces_dtype: torch.dtype = torch.int64,
+                        axis_u: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (v_pos, t_pos_idx) as PINNED HOST tensors the caller owns (fresh per call, from torch's caching pinned
+        allocator): the slab pipeline of the library moves each slab's part of the mesh across PCIe while the next slab is
+        computed, so only the tail of the device->host copy is exposed.  Same errors as ``extract``."""
+        _require_cuda(triplane, "triplane")
+        lib = _capi.load()
+        dev = triplane.device
+        R = int(resolution)
+        tp = triplane.detach().to(torch.float32).contiguous()
+        fpp = ctypes.POINTER(ctypes.c_float)
+        with torch.cuda.device(dev):
+            if axis_u is not None and R not in self._axis_set:
+                a = axis_u.detach().to("cpu", torch.float32).contiguous()
+                check(lib.smb_extractor_set_axis(self._h, R, ctypes.cast(a.data_ptr(), fpp)), "smb_extractor_set_axis")
+                self._axis_set = {R}
+            vcap, fcap = self._host_caps.get(R, (0, 0))
+            flags = _capi.MC_FACES_I32 if faces_dtype == torch.int32 else 0
+            nv, nt = ctypes.c_int64(), ctypes.c_int64()
+            while True:
+                hv = torch.empty((vcap, 3), dtype=torch.float32, pin_memory=True) if vcap else None
+                hf = torch.empty((fcap, 3), dtype=faces_dtype, pin_memory=True) if fcap else None
+                rc = lib.smb_extract_mesh_device_to_host(self._h, tp.data_ptr(), R, float(threshold), flags, _ptr(hv), vcap, _ptr(hf), fcap,
+                                                         _stream_ptr(dev), ctypes.byref(nv), ctypes.byref(nt))
+                if rc != _capi.ERR_CAPACITY:
+                    break
+                vcap, fcap = max(vcap, nv.value * 5 // 4 + 1024), max(fcap, nt.value * 5 // 4 + 1024)
+        if rc == _capi.ERR_LEVEL_RANGE:
+            raise ValueError("Surface level must be within volume data range.")
+        if rc == _capi.ERR_NO_SURFACE:
+            raise RuntimeError("No surface found at the given iso value.")
+        check(rc, "smb_extract_mesh_device_to_host")
+        self._host_caps[R] = (max(vcap, nv.value * 5 // 4 + 1024), max(fcap, nt.value * 5 // 4 + 1024))
+        if len(self._host_caps) > 4:
+            self._host_caps.pop(next(iter(self._host_caps)))
+        return hv[: nv.value], hf[: nt.value]
 
 
 _extractor_cache: "weakref.WeakKeyDictionary[torch.nn.Module, Dict[Tuple, MeshExtractor]]" = weakref.WeakKeyDictionary()

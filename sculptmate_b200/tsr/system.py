@@ -131,6 +131,19 @@ class TSR(BaseModule):
         pageable ``.cpu().numpy()`` per array; ``face_index_dtype = torch.int32`` hands the sink the index width
         Blender stores (a third less PCIe traffic), the default int64 is the reference's LongTensor."""
         for scene_code in scene_codes:
+            if not enable_texture:
+                # mesh only: the library's slab pipeline moves each slab's part of the mesh to (caller-owned) pinned host
+                # memory while the next slab is computed; only the tail of the 58 MB copy (at 256^3) is exposed
+                runtime._require_cuda(scene_code, "scene_code")
+                self.set_marching_cubes_resolution(resolution)
+                self.renderer._check_supported()
+                ex = runtime.get_mesh_extractor(self.decoder, self.renderer.cfg.radius, self.renderer.cfg.density_bias,
+                                                int(scene_code.shape[-2]), int(scene_code.shape[-1]), scene_code.device)
+                with torch.no_grad():
+                    hv, hf = ex.extract_to_host(scene_code, resolution, float(threshold), faces_dtype=self.face_index_dtype,
+                                                axis_u=self._axis(resolution, scene_code.device))
+                self.import_obj_blender(hv.numpy(), hf.numpy(), None, name=mesh_name)
+                continue
             v_pos, t_pos_idx = self.extract_mesh_tensors(scene_code, resolution, threshold, faces_dtype=self.face_index_dtype)
             staged = [self._stage(v_pos), self._stage(t_pos_idx)]
             extra_staged = None
