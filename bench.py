@@ -163,7 +163,7 @@ def run_reference_arm(args, rank: int):
         "impl": "reference", "metric": "extract_mesh_lattice_points_per_s", "value": value, "unit": "pts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": "pts/s", "cores": info.get("threads", 1), "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -266,7 +266,113 @@ void run2(int warps) {
   cudaFree(out);
 }
 
+// ---- third experiment: does the ORDER of the epilogue's instructions matter?  k3<0>: as the compiler schedules the plain
+// source (all 16 tanh of a chunk back to back, then the FFMAs and packs: the warp sits in mio_throttle during the burst and
+// does its other arithmetic afterwards); k3<1>: software-pipelined by half a chunk -- the tanh of 8 columns are issued, then
+// the FFMA / pack / store work of the PREVIOUS 8 columns, fully unrolled -- so that a warp's FMA-pipe work overlaps its own
+// queued SFU work.  Same loads (x16, one chunk ahead), same bias LDS, same stores.
+template <int PIPE>
+__global__ void __launch_bounds__(640, 1) k3(float* out, int steps) {
+  __shared__ uint32_t slot;
+  __shared__ __align__(16) float sbias[64];
+  if (threadIdx.x < 64) sbias[threadIdx.x] = 0.001f * threadIdx.x;
+  if (threadIdx.x < 32) tmem_alloc<512>(smem_u32(&slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t d_t = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 96);
+  const uint32_t a_t = d_t + 64;
+  {
+    uint32_t z[8];
+    for (int i = 0; i < 8; ++i) z[i] = __float_as_uint(0.01f * (float)((threadIdx.x + i) & 63) - 0.3f);
+    for (int c = 0; c < 8; ++c) st8(d_t + 8 * c, z);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  const float4* bl = reinterpret_cast<const float4*>(sbias);
+  float keep = 0.f;
+  for (int s = 0; s < steps; ++s) {
+    uint32_t r[2][16];
+    tmem_ld16(d_t, r[0]);
+    float hp[8], tp[8];  // previous half chunk: pre-activation and its tanh
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld_wait();
+      if (c + 1 < 4) tmem_ld16(d_t + (c + 1) * 16, r[(c + 1) & 1]);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float h[8], t[8];
+        const float4 b0 = bl[4 * c + 2 * hh], b1 = bl[4 * c + 2 * hh + 1];
+        const uint32_t* rc = r[c & 1] + 8 * hh;
+        h[0] = __uint_as_float(rc[0]) + b0.x; h[1] = __uint_as_float(rc[1]) + b0.y; h[2] = __uint_as_float(rc[2]) + b0.z; h[3] = __uint_as_float(rc[3]) + b0.w;
+        h[4] = __uint_as_float(rc[4]) + b1.x; h[5] = __uint_as_float(rc[5]) + b1.y; h[6] = __uint_as_float(rc[6]) + b1.z; h[7] = __uint_as_float(rc[7]) + b1.w;
+        if (PIPE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t[i]) : "f"(h[i]));
+          if (c > 0 || hh > 0) {  // finish the previous half chunk while this one's tanh are in the SFU queue
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[i] = pack_half2(fmaf(hp[2 * i], tp[2 * i], hp[2 * i]), fmaf(hp[2 * i + 1], tp[2 * i + 1], hp[2 * i + 1]));
+            const int q = 2 * c + hh - 1;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_t + 4 * q), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { hp[i] = h[i]; tp[i] = t[i]; }
+        } else {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[i] = pack_half2(silu_from_half_arg(h[2 * i]), silu_from_half_arg(h[2 * i + 1]));
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_t + 4 * (2 * c + hh)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+      }
+    }
+    if (PIPE) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pk[i] = pack_half2(fmaf(hp[2 * i], tp[2 * i], hp[2 * i]), fmaf(hp[2 * i + 1], tp[2 * i + 1], hp[2 * i + 1]));
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_t + 28), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    keep += hp[0];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = keep;
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(base);
+}
+
+template <int PIPE>
+void run3(int warps) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  float* out;
+  cudaMalloc(&out, sizeof(float) * sms * 1024);
+  const int steps = 4000;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  k3<PIPE><<<sms, warps * 32>>>(out, 50);
+  cudaDeviceSynchronize();
+  cudaEventRecord(a);
+  k3<PIPE><<<sms, warps * 32>>>(out, steps);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double clk = 1.965e9;
+  const double acts = (double)steps * warps * 32 * 64;
+  printf("order pipe=%d warps=%2d  %.3f ms  clk/step/warp %.0f  MUFU/clk/SM %.2f  err=%s\n", PIPE, warps, ms, ms * 1e-3 * clk / steps, acts / (ms * 1e-3) / clk,
+         cudaGetErrorString(cudaGetLastError()));
+  cudaFree(out);
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'o') {
+    for (int w : {4, 8, 12, 16, 20}) run3<0>(w);
+    for (int w : {4, 8, 12, 16, 20}) run3<1>(w);
+    return 0;
+  }
   if (argc > 1) {
     for (int w : {8, 16}) run<1, 1, 1, 0>(w);
     for (int w : {4, 8, 12, 16}) run2<1, 0>(w);
