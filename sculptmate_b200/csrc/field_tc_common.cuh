@@ -21,6 +21,7 @@ struct TcParams {
   const unsigned char* tc_weights;  // blob + off_tc_hidden: hidden images, head image, biases (contiguous)
   const unsigned char* tc_biasblk;  // blob + off_tc_biasblk: (n_hidden-1) bias K-block images
   const float* bias0_half;          // b0/2 (64)
+  const float* head_w_f32;          // row 0 of the last Linear, fp32 (64): the density head, fused into the last epilogue
   const float* axis_u;
   int R, x_begin, nx, H, W, align_corners, n_hidden;
   int trows;       // rows of a slot's T table

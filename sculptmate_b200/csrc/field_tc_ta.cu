@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   // bars[0] = weights; per warpgroup g: [1+3g] t_full, [2+3g] t_empty, [3+3g] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * kTaWG);
   int* xu_sem = reinterpret_cast<int*>(tmem_slot + 4);  // [4]: permits per SM sub-partition (p.xu_tokens > 0)
+  float* sHeadW = reinterpret_cast<float*>(xu_sem + 4);  // [64] fp32: row 0 of the last Linear (density), see the fused head below
 
   const int tid_cta = threadIdx.x;
   const int wid = tid_cta >> 5;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     mbar_fence_init();
     for (int q = 0; q < 4; ++q) xu_sem[q] = kDev ? p.xu_tokens : 0;
   }
+  if (tid_cta < kHid) sHeadW[tid_cta] = p.head_w_f32[tid_cta];
   if (wid == 0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
@@ -273,63 +275,81 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         issue_layer(1);
         if (kTrace) tr_put(tr0, tr1, tr2, clock64());
       }
-      for (int l = 1; l <= nh; ++l) {
+      // Hidden layers 1 .. nh-1.  The epilogue of the LAST one does not write an A operand: the head of the density decoder
+      // (network_utils.py:122, out[...,0]) is a 64-term dot product per sample, evaluated right here in fp32 on the
+      // activations while they are in registers (weights broadcast from shared memory).  Round 1 ran it as a tenth
+      // tensor-core step (N = 16 MMA: 1749 clocks per tile, almost all of it hand-off latency for 3 % of the FLOPs) on
+      // activations rounded to fp16; fusing it removes a tcgen05.st + wait::st + barrier + MMA round trip + tcgen05.ld per
+      // tile and is closer to the fp32 reference.  The three `features` outputs are not needed on the lattice
+      // (extract_mesh uses density_act only, system.py:176-184).
+      for (int l = 1; l < nh; ++l) {
         if (kTrace) tr0 = clock64();
         mbar_wait_sleep(bar_acc, par_acc, (uint32_t)p.wait_ns);
         par_acc ^= 1u;
         tc_fence_after();
         if (kTrace) tr1 = clock64();
-        if (l < nh) {
-          xu_acquire();
-          const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
-          uint32_t r[2][16];
-          float4 bb[2][4];
-          tmem_ld16(d_tmem + lane_off, r[0]);
-          if (!kBiasMMA) {
+        const bool last = l == nh - 1;
+        xu_acquire();
+        const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
+        const float4* hw = reinterpret_cast<const float4*>(sHeadW);
+        float dacc = 0.0f;
+        uint32_t r[2][16];
+        float4 bb[2][4];
+        tmem_ld16(d_tmem + lane_off, r[0]);
+        if (!kBiasMMA) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) bb[0][i] = bl[i];
+          for (int i = 0; i < 4; ++i) bb[0][i] = bl[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < 4) {
+            tmem_ld16(d_tmem + lane_off + (c + 1) * 16, r[(c + 1) & 1]);
+            if (!kBiasMMA) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = bl[(c + 1) * 4 + i];
+            }
+          }
+          const uint32_t* rc = r[c & 1];
+          float h[16];
+          if (kBiasMMA) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h[i] = __uint_as_float(rc[i]);
+          } else {
+            const float4* bc = bb[c & 1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              h[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + bc[i].x;
+              h[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + bc[i].y;
+              h[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + bc[i].z;
+              h[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + bc[i].w;
+            }
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld_wait();
-            if (c + 1 < 4) {
-              tmem_ld16(d_tmem + lane_off + (c + 1) * 16, r[(c + 1) & 1]);
-              if (!kBiasMMA) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) bb[(c + 1) & 1][i] = bl[(c + 1) * 4 + i];
-              }
-            }
-            const uint32_t* rc = r[c & 1];
-            float h[16];
-            if (kBiasMMA) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) h[i] = __uint_as_float(rc[i]);
-            } else {
-              const float4* bc = bb[c & 1];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                h[4 * i + 0] = __uint_as_float(rc[4 * i + 0]) + bc[i].x;
-                h[4 * i + 1] = __uint_as_float(rc[4 * i + 1]) + bc[i].y;
-                h[4 * i + 2] = __uint_as_float(rc[4 * i + 2]) + bc[i].z;
-                h[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + bc[i].w;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) h[i] = silu_mix<kPoly>(h[i], i);
+          for (int i = 0; i < 16; ++i) h[i] = silu_mix<kPoly>(h[i], i);
+          if (!last) {
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h[2 * i], h[2 * i + 1]);
             tmem_st8(a_tmem + lane_off + 8 * c, pk);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = hw[4 * c + i];
+              dacc = fmaf(h[4 * i + 0], w.x, dacc);
+              dacc = fmaf(h[4 * i + 1], w.y, dacc);
+              dacc = fmaf(h[4 * i + 2], w.z, dacc);
+              dacc = fmaf(h[4 * i + 3], w.w, dacc);
+            }
           }
-          xu_release();
-          if (kTrace) tr2 = clock64();
+        }
+        xu_release();
+        if (kTrace) tr2 = clock64();
+        if (!last) {
           issue_layer(l + 1);
           if (kTrace) tr_put(tr0, tr1, tr2, clock64());
         } else {
-          uint32_t r[4];
-          tmem_ld4(d_tmem + lane_off, r);
-          tmem_ld_wait();
-          const float d = __uint_as_float(r[0]) + sBiasF[0];
+          const float d = dacc + sBiasF[0];
           const float act = expf(__fadd_rn(d, p.density_bias));
           if (m < tg.nvalid) {
             const long long o = tg.line * p.R + tg.k0 + m;
@@ -362,7 +382,7 @@ template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly, bool kTrace = f
 static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   const int wbytes = tc_weight_bytes(p.n_hidden);
   const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (kBiasMMA ? (size_t)(p.n_hidden - 1) * kWBytes : 0) +
-                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32;
+                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32 + kHid * 4;
   if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
   auto kern = lattice_tc_ta_kernel<kTaWG, kTaProducers, kBiasMMA, kPoly, kTrace>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -79,6 +79,9 @@ static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob
   p.tc_weights = static_cast<const unsigned char*>(decoder_blob) + layout->off_tc_hidden;
   p.tc_biasblk = static_cast<const unsigned char*>(decoder_blob) + layout->off_tc_biasblk;
   p.bias0_half = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_bias_half);
+  // plain fp32 copy of the parameters: [W0 (64x120) b0 (64)] [(W_l (64x64) b_l (64)) x (nh-1)] [W_L (4x64) b_L (4)]
+  p.head_w_f32 = reinterpret_cast<const float*>(static_cast<const char*>(decoder_blob) + layout->off_f32) + (kHid * kFeat + kHid) +
+                 (size_t)(nh - 1) * (kHid * kHid + kHid);
   p.axis_u = axis_u;
   p.R = R;
   p.x_begin = x_begin;
