@@ -63,10 +63,14 @@ struct TileGeom {  // what producer and consumer both derive from a tile index
 
 __device__ __forceinline__ TileGeom tile_geom(long long t, int tiles_per_line, const TcParams& p) {
   TileGeom g;
-  const int seg = (int)(t % tiles_per_line);
-  g.line = t / tiles_per_line;
-  g.i = (int)(g.line / p.R);
-  g.j = (int)(g.line - (long long)g.i * p.R);
+  // 32-bit arithmetic: the launchers reject lattices with 2^31 tiles or more (64-bit divisions cost ~100 instructions each
+  // and this runs once per tile in every producer lane)
+  const unsigned tu = (unsigned)t, tpl = (unsigned)tiles_per_line, Ru = (unsigned)p.R;
+  const unsigned line = tu / tpl;
+  const int seg = (int)(tu - line * tpl);
+  g.line = (long long)line;
+  g.i = (int)(line / Ru);
+  g.j = (int)(line - (unsigned)g.i * Ru);
   g.k0 = seg * kTileM;
   g.nvalid = min(kTileM, p.R - g.k0);
   const float fz_first = unnormalize(p.axis_u[g.k0], p.H, p.align_corners);

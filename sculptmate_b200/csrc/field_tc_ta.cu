@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * kTaWG);
   int* xu_sem = reinterpret_cast<int*>(tmem_slot + 4);  // [4]: permits per SM sub-partition (p.xu_tokens > 0)
   float* sHeadW = reinterpret_cast<float*>(xu_sem + 4);  // [64] fp32: row 0 of the last Linear (density), see the fused head below
+  // per (z-segment of a line, sample m): layer-0 interpolation weight w1 and table row r0.  They depend only on the sample's
+  // z index, so they are computed once per launch; round 1 recomputed them (a global load, floor, clamps and two 64-bit
+  // divisions of the tile index) in every consumer thread for every tile
+  float2* sGeo = reinterpret_cast<float2*>(sHeadW + kHid);
 
   const int tid_cta = threadIdx.x;
   const int wid = tid_cta >> 5;
@@ -105,6 +109,16 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     for (int q = 0; q < 4; ++q) xu_sem[q] = kDev ? p.xu_tokens : 0;
   }
   if (tid_cta < kHid) sHeadW[tid_cta] = p.head_w_f32[tid_cta];
+  {
+    const int tpl = (p.R + kTileM - 1) / kTileM;
+    for (int i = tid_cta; i < tpl * kTileM; i += blockDim.x) {
+      const int k0 = (i / kTileM) * kTileM;
+      const float fz = unnormalize(p.axis_u[min(i, p.R - 1)], p.H, p.align_corners);
+      const float hf = floorf(fz);
+      const int hlo = (int)floorf(unnormalize(p.axis_u[k0], p.H, p.align_corners));
+      sGeo[i] = make_float2(__fsub_rn(fz, hf), __int_as_float(min(max((int)hf - hlo, 0), p.trows - 2)));
+    }
+  }
   if (wid == 0) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
@@ -231,16 +245,20 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
     for (long long n = 0;; ++n) {
       const long long t = (n * gridDim.x + blockIdx.x) * kTaWG + wg;
       if (t >= ntiles) break;
-      const TileGeom tg = tile_geom(t, tiles_per_line, p);
+      struct { long long line; int k0, nvalid; } tg;  // 32-bit tile arithmetic (launch_tc_ta_n rejects >= 2^31 tiles)
+      {
+        const unsigned tu = (unsigned)t, tpl = (unsigned)tiles_per_line;
+        const unsigned line = tu / tpl;
+        tg.line = (long long)line;
+        tg.k0 = (int)(tu - line * tpl) * kTileM;
+        tg.nvalid = min(kTileM, p.R - tg.k0);
+      }
       {
         // ---- layer 0 from the producer's table -> activation columns ------------------
-        const int kk = min(tg.k0 + m, p.R - 1);
-        const float fz = unnormalize(p.axis_u[kk], p.H, p.align_corners);
-        const float hf = floorf(fz);
-        const float w1 = __fsub_rn(fz, hf);
+        const float2 ge = sGeo[tg.k0 + m];
+        const float w1 = ge.x;
         const float w0 = __fsub_rn(1.0f, w1);
-        int r0 = (int)hf - tg.hlo;
-        r0 = min(max(r0, 0), p.trows - 2);
+        const int r0 = __float_as_int(ge.y);
         if (kTrace) tr0 = clock64();
         mbar_wait_sleep(smem_u32(&bars[1 + 3 * wg]), par_t, (uint32_t)p.wait_ns);
         par_t ^= 1u;
@@ -382,12 +400,14 @@ template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly, bool kTrace = f
 static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   const int wbytes = tc_weight_bytes(p.n_hidden);
   const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (kBiasMMA ? (size_t)(p.n_hidden - 1) * kWBytes : 0) +
-                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32 + kHid * 4;
+                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32 + kHid * 4 +
+                      (size_t)((p.R + kTileM - 1) / kTileM) * kTileM * 8;
   if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
   auto kern = lattice_tc_ta_kernel<kTaWG, kTaProducers, kBiasMMA, kPoly, kTrace>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SMB_ERR_CUDA;
   const long long ntiles = (long long)p.nx * p.R * ((p.R + kTileM - 1) / kTileM);
+  if (ntiles >= 0x7fffffffLL) return SMB_ERR_CUDA;  // 32-bit tile arithmetic in the kernel (R^3 / 128 tiles: R up to ~6500)
   long long grid = (ntiles + kTaWG - 1) / kTaWG;
   if (grid > sms) grid = sms;
   kern<<<(unsigned)grid, kTaWG * 128 + kTaProducers * 32, smem, st>>>(p);
