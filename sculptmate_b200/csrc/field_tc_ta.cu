@@ -13,15 +13,16 @@
 //     columns); a warpgroup's MMA latency is covered by the other three.
 //   * 4 producer warps (one per warpgroup) build the layer-0 tables (T, c) one tile ahead, as in
 //     field_tc.cu (measured at 256^3: 1 producer 4.69 ms, 2: 2.90 ms, 4: 2.85 ms).
-//   * kBiasMMA: the bias of a hidden layer enters the accumulator through a fifth K=16 MMA -- a
+//   * kBiasMMA (default since round 2): the bias of a hidden layer enters the accumulator through a fifth K=16 MMA -- a
 //     constant activation block (1, 1, 0, ...) in TMEM against a weight block whose K rows 0/1 hold
-//     b_l/2 as fp16 hi + lo -- instead of 16 LDS.128 + 64 FADD per sample and layer in the epilogue.
-//   * kPoly: kPoly of every 16 activations take their tanh from an FMA-pipe polynomial (silu_poly
+//     b_l/2 as fp16 hi + lo -- instead of 16 LDS.128 + 64 FADD per sample and layer in the epilogue (a quarter of the
+//     epilogue's instructions).  The constant block is the same for every tile, so ONE copy serves all warpgroups
+//     (5 x 96 + 8 = 488 TMEM columns); round 1 gave each warpgroup its own (128 columns per slot -> only four tiles in
+//     flight), which is why it measured no gain then.  256^3: 2.85 -> 2.76 ms on the same GPU.
+//   * kPoly (developer build): kPoly of every 16 activations take their tanh from an FMA-pipe polynomial (silu_poly
 //     below, tools/fit_tanh_poly.py) -- the software-exponential trick of FlashAttention-4 applied to
-//     SiLU: SFU demand drops by kPoly/16 at the price of 10 more instructions per such activation.
-//   Both are OFF by default: measured on B200 they are slower (see launch_tc_ta and DESIGN.md 4/K1 --
-//   the kernel is bound by the latency each warp exposes between its SFU ops, not by SFU throughput,
-//   so added instructions cost more than the SFU slots they free).
+//     SiLU: SFU demand drops by kPoly/16 at the price of 10 more instructions per such activation.  Slower
+//     (the kernel is bound by the per-step fixed costs of its in-order warps, not by SFU throughput).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -36,8 +37,9 @@ constexpr bool kDev = true;  // developer build: bias-MMA / polynomial / token /
 constexpr bool kDev = false;  // product build: one kernel (5 warpgroups) and its 4-warpgroup fallback, no experiment code
 #endif
 
-// TMEM columns per warpgroup: 64 accumulator + 32 activation (+ 8 constant bias columns, padded to 128, with kBiasMMA)
-__host__ __device__ constexpr int ta_cols_per_wg(bool bias_mma) { return bias_mma ? 128 : 96; }
+// TMEM columns per warpgroup: 64 accumulator + 32 activation.  With kBiasMMA the constant activation block (8 columns: it is the
+// same for every tile) is shared by all warpgroups and sits behind their slots: 5 x 96 + 8 = 488 of 512 columns.
+__host__ __device__ constexpr int ta_cols_per_wg(bool) { return 96; }
 
 // silu(2h) = h + |h| tanh(|h|) with tanh(|h|) ~= hc q(hc^2), hc = min(|h|, 4): degree-8 polynomial in hc^2,
 // max abs error of tanh 1.0e-3 (MUFU.TANH: 5e-4; the result is rounded to fp16 = 5e-4 relative anyway).
@@ -88,7 +90,8 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
   // bars[0] = weights; per warpgroup g: [1+3g] t_full, [2+3g] t_empty, [3+3g] acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * kTaWG);
   int* xu_sem = reinterpret_cast<int*>(tmem_slot + 4);  // [4]: permits per SM sub-partition (p.xu_tokens > 0)
-  float* sHeadW = reinterpret_cast<float*>(xu_sem + 4);  // [64] fp32: row 0 of the last Linear (density), see the fused head below
+  // [64] fp32, 16-byte aligned (read as float4): row 0 of the last Linear (density), see the fused head below
+  float* sHeadW = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(xu_sem + 4) + 15) & ~(uintptr_t)15);
   // per (z-segment of a line, sample m): layer-0 interpolation weight w1 and table row r0.  They depend only on the sample's
   // z index, so they are computed once per launch; round 1 recomputed them (a global load, floor, clamps and two 64-bit
   // divisions of the tile index) in every consumer thread for every tile
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
 
     if (kBiasMMA) {  // constant activation block: k = 64, 65 -> 1.0 (bias hi, lo rows), k = 66..79 -> 0
       const uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      tmem_st8(d_tmem + 96 + lane_off, one);
+      tmem_st8(tmem_base + (uint32_t)(kTaWG * 96) + lane_off, one);  // every warpgroup writes the same constants (idempotent)
     }
     mbar_wait(bar_w, 0);
 
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
 #pragma unroll
         for (int kc = 0; kc < kHid / 16; ++kc)  // K = 16 per instruction = 8 packed columns of A, +32 B of B
           umma_f16_ts(d_tmem, a_tmem + 8 * kc, b_desc + 2 * kc, idesc, kc > 0 ? 1u : 0u);
-        if (kBiasMMA && !head) umma_f16_ts(d_tmem, d_tmem + 96, umma_desc_k_sw128(smem_u32(sBB + (L - 1) * kWBytes)), idesc, 1u);
+        if (kBiasMMA && !head)
+          umma_f16_ts(d_tmem, tmem_base + (uint32_t)(kTaWG * 96), umma_desc_k_sw128(smem_u32(sBB + (L - 1) * kWBytes)), idesc, 1u);
         umma_commit(bar_acc);
       }
     };
@@ -400,7 +404,7 @@ template <int kTaWG, int kTaProducers, bool kBiasMMA, int kPoly, bool kTrace = f
 static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   const int wbytes = tc_weight_bytes(p.n_hidden);
   const size_t smem = (size_t)((wbytes + 1023) / 1024) * 1024 + (kBiasMMA ? (size_t)(p.n_hidden - 1) * kWBytes : 0) +
-                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 32 + kHid * 4 +
+                      (size_t)kTaWG * ta_table_bytes(p.trows) + 8 * (1 + 3 * kTaWG) + 48 + kHid * 4 +
                       (size_t)((p.R + kTileM - 1) / kTileM) * kTileM * 8;
   if (smem > 227 * 1024) return SMB_ERR_BAD_ARG;
   auto kern = lattice_tc_ta_kernel<kTaWG, kTaProducers, kBiasMMA, kPoly, kTrace>;
@@ -414,27 +418,33 @@ static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
   return smb_check(cudaGetLastError());
 }
 
-// Default: FIVE consumer warpgroups (all of tensor memory: 5 x 96 = 480 columns; 768 threads, the producer
-// warpgroup hands 40 of its 80 registers to the consumers with setmaxnreg so that they run at 88), bias in the
-// epilogue, every tanh on the SFU: 2.88 ms at 256^3 against 2.93 ms with four warpgroups on the same GPU.  The
-// product library instantiates exactly these two (the second is the fallback when five table buffers do not fit
-// in shared memory).  A developer build (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements
-// DESIGN.md 4/K1 argues from (tools/sweep_lattice.py): SMB_TC_TA_BIAS=1 (bias through a fifth K=16 MMA: 2.89 ms),
-// SMB_TC_TA_POLY=4 (4 of 16 tanh on the FMA pipe: 3.22 ms; with the bias MMA 3.36 ms), SMB_TC_TA_STAGGER=<clk>
-// (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms), SMB_TC_TA_WG=4, SMB_TC_TRACE=2 (timeline).
+// Default: FIVE consumer warpgroups (5 x 96 + 8 = 488 of the 512 TMEM columns; 768 threads, the producer warpgroup hands 40
+// of its 80 registers to the consumers with setmaxnreg so that they run at 88), hidden-layer bias through a fifth K=16
+// MMA, every tanh on the SFU, the density head fused into the last epilogue.  The product library instantiates exactly this
+// kernel and its four-warpgroup form (the fallback when five table buffers do not fit in shared memory).  A developer
+// build (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements DESIGN.md 4/K1 argues from
+// (tools/sweep_lattice.py): SMB_TC_TA_BIAS=0 (bias in the epilogue: 2.85 vs 2.76 ms), SMB_TC_TA_POLY=4 (4 of 16 tanh on
+// the FMA pipe: slower), SMB_TC_TA_STAGGER=<clk> (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms in round 1),
+// SMB_TC_TA_WG=4, SMB_TC_TRACE=2 (timeline).
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
 #ifdef SMB_DEV_VARIANTS
-  static const int bias = getenv("SMB_TC_TA_BIAS") ? atoi(getenv("SMB_TC_TA_BIAS")) : 0;
+  static const int bias = getenv("SMB_TC_TA_BIAS") ? atoi(getenv("SMB_TC_TA_BIAS")) : 1;
   static const int poly = getenv("SMB_TC_TA_POLY") ? atoi(getenv("SMB_TC_TA_POLY")) : 0;
   static const int wgs = getenv("SMB_TC_TA_WG") ? atoi(getenv("SMB_TC_TA_WG")) : 5;
   if (p.dbg == 2) return wgs == 5 ? launch_tc_ta_n<5, 4, false, 0, true>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0, true>(p, sms, st);
-  if (bias) return poly ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
-  if (poly) return launch_tc_ta_n<4, 4, false, 4>(p, sms, st);
-  if (wgs != 5) return launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
+  if (poly) return bias ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 4>(p, sms, st);
+  if (!bias) {
+    if (wgs == 5) {
+      const int rc = launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
+      if (rc != SMB_ERR_BAD_ARG) return rc;
+    }
+    return launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
+  }
+  if (wgs != 5) return launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
 #endif
-  const int rc = launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
+  const int rc = launch_tc_ta_n<5, 4, true, 0>(p, sms, st);
   if (rc != SMB_ERR_BAD_ARG) return rc;  // five table buffers did not fit in shared memory: four warpgroups
-  return launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
+  return launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
 }
 
 #ifdef SMB_DEV_VARIANTS
