@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 RADIUS = 0.87
 FLOP_PER_POINT = 2 * (120 * 64 + 8 * 64 * 64 + 64 * 4)  # 81408: the reference's NeRFMLP (all 4 outputs), SURVEY 8d
-KERNELS_PER_STEP = 5  # project_planes, lattice_tc_ta_kernel (also ballots the MC sign masks), mc_count, mc_totals, mc_emit
+KERNELS_PER_STEP = 6  # project_planes, lattice_axis_tables, lattice_tc_ta_kernel (also ballots the MC sign masks), mc_count, mc_totals, mc_emit
 
 
 def baked_triplane(seed: int, H: int = 64, W: int = 64, noise: float = 0.05) -> torch.Tensor:

@@ -21,6 +21,10 @@ struct TcParams {
   const unsigned char* tc_weights;  // blob + off_tc_hidden: hidden images, head image, biases (contiguous)
   const unsigned char* tc_biasblk;  // blob + off_tc_biasblk: (n_hidden-1) bias K-block images
   const float* bias0_half;          // b0/2 (64)
+  // per-launch axis tables (lattice_api.cu): t1[i][h] = x-interpolated row h of the (x,z) plane at lattice x = x_begin + i,
+  // t2[j][h] = the same for the (y,z) plane at lattice y = j; (rows, H, 64) fp32.  A tile's table row is t1 + t2.
+  const float* t1;
+  const float* t2;
   const float* head_w_f32;          // row 0 of the last Linear, fp32 (64): the density head, fused into the last epilogue
   const float* axis_u;
   int R, x_begin, nx, H, W, align_corners, n_hidden;
@@ -145,7 +149,12 @@ __device__ __forceinline__ void build_table(const TcParams& p, const TableGeom& 
     for (int r = 2 * part + (lane >> 4); r < tg.nrow; r += 2 * nparts) {
       const int h = tg.hlo + r;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (h >= 0 && h < p.H) {
+      if (h >= 0 && h < p.H && p.t1) {
+        // both in-plane interpolations were done once per launch for every lattice x / y (axis tables): two loads and an add
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.t1 + ((long long)tg.i * p.H + h) * kHid) + n4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.t2 + ((long long)tg.j * p.H + h) * kHid) + n4);
+        v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      } else if (h >= 0 && h < p.H) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i0) * kHid) + n4);
         const float4 b = __ldg(reinterpret_cast<const float4*>(Q1 + ((long long)h * p.W + txw.i1) * kHid) + n4);
         const float4 c = __ldg(reinterpret_cast<const float4*>(Q2 + ((long long)h * p.W + tyw.i0) * kHid) + n4);

@@ -34,6 +34,30 @@ static const TcEnv& tc_env() {
   }();
   return env;
 }
+// Axis tables of one launch: for every lattice x of the slab the x-interpolated rows of the projected (x,z) plane, for every
+// lattice y those of the (y,z) plane -- the two in-plane bilinear interpolations of layer 0 depend on ONE lattice coordinate
+// each, so they are done (nx + R) * H times per launch instead of once per tile (R^2 * nx * tiles_per_line times) by the
+// producer warps, whose table build then is two loads and an add per element.  (Zero padding is folded into the tap weights.)
+__global__ void __launch_bounds__(256) lattice_axis_tables(TcParams p, float* __restrict__ t1, float* __restrict__ t2) {
+  const long long HW = (long long)p.H * p.W;
+  const float* Q1 = p.planes_q + HW * kHid;
+  const float* Q2 = Q1 + HW * kHid;
+  const long long n1 = (long long)p.nx * p.H * (kHid / 4), n2 = (long long)p.R * p.H * (kHid / 4);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n1 + n2; t += (long long)gridDim.x * blockDim.x) {
+    const bool second = t >= n1;
+    const long long u = second ? t - n1 : t;
+    const int n4 = (int)(u % (kHid / 4));
+    const long long rh = u / (kHid / 4);
+    const int h = (int)(rh % p.H), row = (int)(rh / p.H);
+    const Tap2 tap = make_tap(p.axis_u[second ? row : p.x_begin + row], p.W, p.align_corners);
+    const float* Q = second ? Q2 : Q1;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(Q + ((long long)h * p.W + tap.i0) * kHid) + n4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(Q + ((long long)h * p.W + tap.i1) * kHid) + n4);
+    const float4 v = make_float4(tap.w0 * a.x + tap.w1 * b.x, tap.w0 * a.y + tap.w1 * b.y, tap.w0 * a.z + tap.w1 * b.z, tap.w0 * a.w + tap.w1 * b.w);
+    reinterpret_cast<float4*>(second ? t2 : t1)[u] = v;
+  }
+}
+
 #ifdef SMB_DEV_VARIANTS
 int launch_tc_smem(const TcParams& p, int sms, bool trace, cudaStream_t st);
 int read_trace_smem(long long* host, int n);
@@ -121,7 +145,35 @@ static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob
     return rc;
   }
 #endif
-  return launch_tc_ta(p, sms, st);
+  // axis tables in stream-ordered scratch memory (the pool keeps the block between calls: no allocation cost after the first)
+  const size_t tab_floats = ((size_t)nx + (size_t)R) * cfg->Hp * kHid;
+  float* tabs = nullptr;
+  {
+    // keep freed scratch in the device's default pool instead of returning it to the driver at every synchronisation
+    // (release threshold 0 is the default: each call would then pay a fresh allocation)
+    static int pool_dev = -1;
+    if (pool_dev != dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_dev = dev;
+    }
+  }
+  if (!getenv("SMB_NO_AXIS_TABLES") && cudaMallocAsync(reinterpret_cast<void**>(&tabs), tab_floats * sizeof(float), st) == cudaSuccess) {
+    p.t1 = tabs;
+    p.t2 = tabs + (size_t)nx * cfg->Hp * kHid;
+    const long long items = (long long)tab_floats / 4;
+    const int blocks = (int)((items + 255) / 256 < (long long)sms * 8 ? (items + 255) / 256 : (long long)sms * 8);
+    lattice_axis_tables<<<blocks, 256, 0, st>>>(p, tabs, tabs + (size_t)nx * cfg->Hp * kHid);
+  } else {
+    (void)cudaGetLastError();  // no scratch: the producers interpolate per tile (the round-1 path)
+    p.t1 = p.t2 = nullptr;
+  }
+  const int rc = launch_tc_ta(p, sms, st);
+  if (tabs) cudaFreeAsync(tabs, st);
+  return rc;
 }
 
 extern "C" int smb_query_lattice_tc(const float* planes_q, const void* decoder_blob,
