@@ -705,7 +705,7 @@ def main() -> int:
             "kernel_ms": kern_ms_avg, "kernel_ms_pct": pct(kern_ms), "query_points_per_s": float(R) ** 3 / (kern_ms_avg * 1e-3),
             "flop_per_point": FLOP_PER_POINT, "prepare_ms": prep_ms_avg,
             "timing": "CUDA events recorded by the library on the launching stream around the kernel, inside the timed public call (smb_extractor_enable_timing)",
-            "note": "algorithmic FLOPs = the reference NeRFMLP count (SURVEY 8d); layer 0 runs as a projected-plane interpolation in fp32, not as an MMA",
+            "note": "algorithmic FLOPs = the reference NeRFMLP count (SURVEY 8d); layer 0 runs as a projected-plane interpolation in fp32 and the density head as an fp32 dot product in the last epilogue, not as MMAs; kernel_ms spans lattice_axis_tables (~10 us) + lattice_tc_ta_kernel",
         }
         if nV:
             # marching cubes is HBM-bound: algorithmic bytes = 4 R^3 (density read) + 12 V + 24 F (mesh write),

@@ -19,10 +19,10 @@
 //     epilogue's instructions).  The constant block is the same for every tile, so ONE copy serves all warpgroups
 //     (5 x 96 + 8 = 488 TMEM columns); round 1 gave each warpgroup its own (128 columns per slot -> only four tiles in
 //     flight), which is why it measured no gain then.  256^3: 2.85 -> 2.76 ms on the same GPU.
-//   * kPoly (developer build): kPoly of every 16 activations take their tanh from an FMA-pipe polynomial (silu_poly
-//     below, tools/fit_tanh_poly.py) -- the software-exponential trick of FlashAttention-4 applied to
-//     SiLU: SFU demand drops by kPoly/16 at the price of 10 more instructions per such activation.  Slower
-//     (the kernel is bound by the per-step fixed costs of its in-order warps, not by SFU throughput).
+//   * kPoly (default 3): kPoly of the 64 activations of a layer step take their tanh from an FMA-pipe polynomial (silu_poly
+//     below) -- the software-exponential trick of FlashAttention-4 applied to SiLU.  In round 1 (latency-bound kernel, a
+//     polynomial with 1e-3 error) it was slower; with the leaner steps of round 2 the SFU is busy 85 % of the time and
+//     moving 3 of 64 activations off it buys 4 % (more than 6 of 64 costs more FMA-pipe time than it frees SFU time).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -41,28 +41,31 @@ constexpr bool kDev = false;  // product build: one kernel (5 warpgroups) and it
 // same for every tile) is shared by all warpgroups and sits behind their slots: 5 x 96 + 8 = 488 of 512 columns.
 __host__ __device__ constexpr int ta_cols_per_wg(bool) { return 96; }
 
-// silu(2h) = h + |h| tanh(|h|) with tanh(|h|) ~= hc q(hc^2), hc = min(|h|, 4): degree-8 polynomial in hc^2,
-// max abs error of tanh 1.0e-3 (MUFU.TANH: 5e-4; the result is rounded to fp16 = 5e-4 relative anyway).
-// 1 FMNMX + 2 FMUL + 9 FFMA, no MUFU.  Coefficients: `python tools/fit_tanh_poly.py 4.0 8`.
+// silu(2h) = h + |h| tanh(|h|) on the FMA pipe (no MUFU):  tanh(|h|) ~= q(x),  x = min(|h| * (2/4.5) - 1, 1)  in [-1, 1].
+// q: degree-9 minimax polynomial of tanh(2.25 (x + 1)) in the CENTRED variable -- every coefficient below 1 in magnitude, so
+// the fp32 Horner evaluation is well conditioned (the round-1 form, a polynomial in h^2 on [0, 16], loses 3 digits to
+// cancellation and stalled at 1.0e-3).  Max abs error of tanh over all h, clamp included (1 - tanh(4.5) = 2.5e-4), under fp32
+// evaluation: 2.5e-4 -- BELOW tanh.approx.f32's 5e-4, so an activation that takes this path is no less accurate than one
+// that takes the SFU.  1 FFMA (x) + 1 FMNMX + 9 FFMA + 1 FFMA = 12 instructions.
 __device__ __forceinline__ float silu_poly(float h) {
   const float a = fabsf(h);
-  const float hc = fminf(a, 4.0f);
-  const float u = hc * hc;
-  float q = 7.428608762e-09f;
-  q = fmaf(q, u, -5.504116545e-07f);
-  q = fmaf(q, u, 1.724979285e-05f);
-  q = fmaf(q, u, -2.989478161e-04f);
-  q = fmaf(q, u, 3.156803466e-03f);
-  q = fmaf(q, u, -2.129765012e-02f);
-  q = fmaf(q, u, 9.570061363e-02f);
-  q = fmaf(q, u, -3.115132217e-01f);
-  q = fmaf(q, u, 9.962177177e-01f);
-  return fmaf(a, hc * q, h);
+  const float x = fminf(fmaf(a, 2.0f / 4.5f, -1.0f), 1.0f);
+  float q = 3.815771247e-02f;
+  q = fmaf(q, x, 1.059716077e-01f);
+  q = fmaf(q, x, -2.874662484e-01f);
+  q = fmaf(q, x, -1.656126921e-02f);
+  q = fmaf(q, x, 3.707452418e-01f);
+  q = fmaf(q, x, -3.581689483e-01f);
+  q = fmaf(q, x, 2.788679147e-01f);
+  q = fmaf(q, x, -2.090362925e-01f);
+  q = fmaf(q, x, 9.955515848e-02f);
+  q = fmaf(q, x, 9.778961789e-01f);
+  return fmaf(a, q, h);
 }
-// activation i of a 16-column chunk: kPoly of the 16 go to the FMA pipe
+// activation j (0..63) of a layer step: kPoly of the 64 go to the FMA pipe, spread evenly over the step
 template <int kPoly>
-__device__ __forceinline__ float silu_mix(float h, int i) {
-  return (((i * kPoly) & 15) < kPoly) ? silu_poly(h) : silu_from_half_arg(h);
+__device__ __forceinline__ float silu_mix(float h, int j) {
+  return (((j * kPoly) & 63) < kPoly) ? silu_poly(h) : silu_from_half_arg(h);
 }
 
 // developer instrumentation (kTrace, SMB_TC_TRACE=2): clock64 stamps of block 0, every consumer warp, first kTraceSteps layer steps
@@ -285,8 +288,8 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
             const float h1 = cv.y + w0 * a.y + w1 * b.y;
             const float h2 = cv.z + w0 * a.z + w1 * b.z;
             const float h3 = cv.w + w0 * a.w + w1 * b.w;
-            pk[2 * g4 + 0] = pack_half2(silu_mix<kPoly>(h0, 4 * g4 + 0), silu_mix<kPoly>(h1, 4 * g4 + 1));
-            pk[2 * g4 + 1] = pack_half2(silu_mix<kPoly>(h2, 4 * g4 + 2), silu_mix<kPoly>(h3, 4 * g4 + 3));
+            pk[2 * g4 + 0] = pack_half2(silu_mix<kPoly>(h0, 16 * c + 4 * g4 + 0), silu_mix<kPoly>(h1, 16 * c + 4 * g4 + 1));
+            pk[2 * g4 + 1] = pack_half2(silu_mix<kPoly>(h2, 16 * c + 4 * g4 + 2), silu_mix<kPoly>(h3, 16 * c + 4 * g4 + 3));
           }
           tmem_st8(a_tmem + lane_off + 8 * c, pk);
         }
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
             }
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) h[i] = silu_mix<kPoly>(h[i], i);
+          for (int i = 0; i < 16; ++i) h[i] = silu_mix<kPoly>(h[i], 16 * c + i);
           if (!last) {
             uint32_t pk[8];
 #pragma unroll
@@ -420,31 +423,42 @@ static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
 
 // Default: FIVE consumer warpgroups (5 x 96 + 8 = 488 of the 512 TMEM columns; 768 threads, the producer warpgroup hands 40
 // of its 80 registers to the consumers with setmaxnreg so that they run at 88), hidden-layer bias through a fifth K=16
-// MMA, every tanh on the SFU, the density head fused into the last epilogue.  The product library instantiates exactly this
-// kernel and its four-warpgroup form (the fallback when five table buffers do not fit in shared memory).  A developer
-// build (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements DESIGN.md 4/K1 argues from
-// (tools/sweep_lattice.py): SMB_TC_TA_BIAS=0 (bias in the epilogue: 2.85 vs 2.76 ms), SMB_TC_TA_POLY=4 (4 of 16 tanh on
-// the FMA pipe: slower), SMB_TC_TA_STAGGER=<clk> (no effect), SMB_TC_TA_TOKENS=1|2|3 (4.81 / 3.37 / 2.99 ms in round 1),
-// SMB_TC_TA_WG=4, SMB_TC_TRACE=2 (timeline).
+// MMA, the density head fused into the last epilogue, and kDefaultPoly = 3 of the 64 activations of a layer step evaluated
+// on the FMA pipe (silu_poly, at least as accurate as tanh.approx) instead of the SFU.  Measured on one B200 at 256^3
+// (profiles/r02j_k1_steps.log): 2.72 ms with every tanh on the SFU, 2.64 / 2.60 / 2.63 / 2.62 / 2.63 / 2.67 ms with
+// 2 / 3 / 4 / 5 / 6 / 8 of 64 on the FMA pipe.  The product library instantiates exactly this kernel and its
+// four-warpgroup form (the fallback when five table buffers do not fit in shared memory).  A developer build
+// (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements DESIGN.md 4/K1 argues from: SMB_TC_TA_POLY=<n of 64>,
+// SMB_TC_TA_BIAS=0 (bias in the epilogue), SMB_TC_TA_STAGGER=<clk>, SMB_TC_TA_TOKENS=1|2|3, SMB_TC_TA_WG=4, SMB_TC_TRACE=2.
+constexpr int kDefaultPoly = 3;
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
 #ifdef SMB_DEV_VARIANTS
   static const int bias = getenv("SMB_TC_TA_BIAS") ? atoi(getenv("SMB_TC_TA_BIAS")) : 1;
-  static const int poly = getenv("SMB_TC_TA_POLY") ? atoi(getenv("SMB_TC_TA_POLY")) : 0;
+  static const int poly = getenv("SMB_TC_TA_POLY") ? atoi(getenv("SMB_TC_TA_POLY")) : kDefaultPoly;
   static const int wgs = getenv("SMB_TC_TA_WG") ? atoi(getenv("SMB_TC_TA_WG")) : 5;
   if (p.dbg == 2) return wgs == 5 ? launch_tc_ta_n<5, 4, false, 0, true>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0, true>(p, sms, st);
-  if (poly) return bias ? launch_tc_ta_n<4, 4, true, 4>(p, sms, st) : launch_tc_ta_n<4, 4, false, 4>(p, sms, st);
+  if (bias && wgs == 5 && poly != kDefaultPoly) {
+    switch (poly) {
+      case 0: return launch_tc_ta_n<5, 4, true, 0>(p, sms, st);
+      case 2: return launch_tc_ta_n<5, 4, true, 2>(p, sms, st);
+      case 4: return launch_tc_ta_n<5, 4, true, 4>(p, sms, st);
+      case 5: return launch_tc_ta_n<5, 4, true, 5>(p, sms, st);
+      case 6: return launch_tc_ta_n<5, 4, true, 6>(p, sms, st);
+      default: return launch_tc_ta_n<5, 4, true, 8>(p, sms, st);
+    }
+  }
   if (!bias) {
     if (wgs == 5) {
-      const int rc = launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
+      const int rc = poly ? launch_tc_ta_n<5, 4, false, kDefaultPoly>(p, sms, st) : launch_tc_ta_n<5, 4, false, 0>(p, sms, st);
       if (rc != SMB_ERR_BAD_ARG) return rc;
     }
     return launch_tc_ta_n<4, 4, false, 0>(p, sms, st);
   }
-  if (wgs != 5) return launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
+  if (wgs != 5) return launch_tc_ta_n<4, 4, true, kDefaultPoly>(p, sms, st);
 #endif
-  const int rc = launch_tc_ta_n<5, 4, true, 0>(p, sms, st);
+  const int rc = launch_tc_ta_n<5, 4, true, kDefaultPoly>(p, sms, st);
   if (rc != SMB_ERR_BAD_ARG) return rc;  // five table buffers did not fit in shared memory: four warpgroups
-  return launch_tc_ta_n<4, 4, true, 0>(p, sms, st);
+  return launch_tc_ta_n<4, 4, true, kDefaultPoly>(p, sms, st);
 }
 
 #ifdef SMB_DEV_VARIANTS
