@@ -31,6 +31,7 @@
 // (i,j,k) then table order.  Slabs concatenate bit-exactly (see smb_mc_emit).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/sculptmate_b200.h"
 #define SMB_TABLE_QUAL __device__ const
@@ -79,6 +80,8 @@ struct McWorkspace {
   WordRec* rec;      // nwords
   ChunkRec* ctot;    // nchunks totals
   ChunkRec* cbase;   // nchunks bases
+  uint32_t* ticket;  // mc_emit's unit counter (zeroed by mc_totals, wraps back to 0 at the end of every emit)
+  uint32_t* order;   // nchunks chunk numbers, heaviest first: the order mc_emit draws its units in
   size_t bytes;
 };
 
@@ -98,6 +101,8 @@ __host__ inline McWorkspace carve(void* base, const McDims& d) {
   w.rec = reinterpret_cast<WordRec*>(take(nw * sizeof(WordRec)));
   w.ctot = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
   w.cbase = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
+  w.ticket = reinterpret_cast<uint32_t*>(take(256));
+  w.order = reinterpret_cast<uint32_t*>(take((size_t)d.nchunks * 4));
   w.bytes = off;
   return w;
 }
@@ -325,7 +330,8 @@ __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos
 // plane i, the in-plane counts of its chunks, then the x-edge counts of its chunks.
 // Triangles: chunk order.  Sequential over tiles of 1024 with a running carry.
 __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ ctot, ChunkRec* __restrict__ cbase,
-                                                  McDims d, int emit_last_plane, smb_mc_counts* __restrict__ counts) {
+                                                  McDims d, int emit_last_plane, smb_mc_counts* __restrict__ counts,
+                                                  uint32_t* __restrict__ ticket, uint32_t* __restrict__ order) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -392,6 +398,37 @@ __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ c
     counts->ntris = totals[1];
     counts->nverts_numbered = totals[0];
     counts->reserved = 0;
+    *ticket = 0u;
+  }
+  // ---- the order mc_emit draws its work in: chunks by weight (vertices + triangles), heaviest first, in 64 linear
+  // classes -- longest-processing-time-first keeps the kernel's tail short when the surface is concentrated in a part of
+  // the volume.  The order inside a class depends on the atomics; it only affects scheduling, never the output.
+  __shared__ uint32_t s_hist[64], s_cur[64], s_max;
+  if (tid < 64) s_hist[tid] = 0u;
+  if (tid == 0) s_max = 0u;
+  __syncthreads();
+  uint32_t mx = 0u;
+  for (long long c = tid; c < d.nchunks; c += 1024) mx = max(mx, ctot[c].a + ctot[c].b + ctot[c].t);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) atomicMax(&s_max, mx);
+  __syncthreads();
+  const unsigned long long wmax = max(s_max, 1u);
+  for (long long c = tid; c < d.nchunks; c += 1024) {
+    const uint32_t w = ctot[c].a + ctot[c].b + ctot[c].t;
+    atomicAdd(&s_hist[63u - (uint32_t)((unsigned long long)w * 63ull / wmax)], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0u;
+    for (int q = 0; q < 64; ++q) {
+      s_cur[q] = run;
+      run += s_hist[q];
+    }
+  }
+  __syncthreads();
+  for (long long c = tid; c < d.nchunks; c += 1024) {
+    const uint32_t w = ctot[c].a + ctot[c].b + ctot[c].t;
+    order[atomicAdd(&s_cur[63u - (uint32_t)((unsigned long long)w * 63ull / wmax)], 1u)] = (uint32_t)c;
   }
 }
 
@@ -418,6 +455,11 @@ struct EmitParams {
   const long long* count_seq;
   long long seq;
   long long* error_flag;
+  // dynamic scheduling: every CTA draws unit numbers from *ticket (atomicInc with wrap = nunits + gridDim - 1: each CTA ends
+  // on exactly one failed draw, so the counter is back at 0 when the grid retires)
+  uint32_t* ticket;
+  uint32_t ticket_wrap;
+  const uint32_t* order;  // chunk numbers, heaviest first (mc_totals)
 };
 
 __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float vmul, float vadd) {
@@ -427,49 +469,111 @@ __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float 
 }
 
 constexpr int kEmitWarps = 8;
+constexpr int kUnitWords = 256;  // words of one x-plane per CTA unit (= threads per CTA)
+constexpr int kHaloMax = 72;     // words staged behind the unit (rows j+1 and the next word of a row: wz + 1 <= 72 up to nz = 2272)
+constexpr int kStageWords = kUnitWords + kHaloMax;
+constexpr int kXfMax = 1024;  // lattice indices with a tabulated output coordinate
 
-// lane l holds cnt_l items; returns the exclusive prefix and the warp total
-__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+// position of the n-th (0-based) set bit of m; popc(m) > n
+__device__ __forceinline__ int nth_set_bit(uint32_t m, uint32_t n) {
+  int pos = 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const uint32_t low = m & ((1u << s) - 1u);
+    const uint32_t c = __popc(low);
+    if (n >= c) {
+      n -= c;
+      m >>= s;
+      pos += s;
+    } else {
+      m = low;
+    }
+  }
+  return pos;
+}
+
+// What a unit needs of the words it touches, staged once per unit: plane 0 = the unit's x-plane i, plane 1 = i + 1.
+struct EmitStage {
+  uint32_t pos[2][kStageWords];  // sign masks
+  uint32_t A[2][kStageWords];    // id of the word's first in-plane vertex (chunk base + chunk-local prefix)
+  uint32_t my[2][kStageWords];   // crossing masks of the owned y- / z-edges
+  uint32_t mz[2][kStageWords];
+  uint32_t B[kStageWords];       // id of the word's first x-edge vertex, mask of the owned x-edges (plane i only)
+  uint32_t mx[kStageWords];
+  uint32_t T[kUnitWords];        // slot of the word's first triangle, mask of its active cells, its row j
+  uint32_t act[kUnitWords];
+  uint32_t row[kUnitWords];
+  uint32_t offV[kUnitWords];     // exclusive prefix over the unit's words of crossing samples / active cells
+  uint32_t offC[kUnitWords];
+  uint32_t warp_tot[kEmitWarps];
+  uint32_t unit, chunk;  // the ticket drawn for the next loop iteration and the chunk it maps to
+};
+
+// largest l in [0, kUnitWords) with off[l] <= idx
+__device__ __forceinline__ int locate_word(const uint32_t* __restrict__ off, uint32_t idx) {
+  int lo = 0;
+#pragma unroll
+  for (int step = kUnitWords / 2; step > 0; step >>= 1)
+    if (off[lo + step] <= idx) lo += step;
+  return lo;
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
   uint32_t inc = v;
 #pragma unroll
   for (int sft = 1; sft < 32; sft <<= 1) {
     const uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
     if (lane >= sft) inc += y;
   }
-  total = __shfl_sync(0xffffffffu, inc, 31);
   return inc - v;
 }
 
-// item idx of the batch -> (lane that holds its word, position of its bit in that word's mask)
-__device__ __forceinline__ void locate_item(uint32_t idx, const uint32_t* __restrict__ s_off /*[33]*/, int& src) {
-  int lo = 0;  // largest l with s_off[l] <= idx
-#pragma unroll
-  for (int step = 16; step > 0; step >>= 1)
-    if (s_off[lo + step] <= idx) lo += step;
-  src = lo;
-}
-
-// kStaged (the host picks it when a batch of 32 words never straddles an x-plane, i.e. ny*wz % 32 == 0): the vertices and
-// triangles of a 32-item group occupy CONTIGUOUS output slots, so they are assembled in shared memory and written out
-// by the whole warp with coalesced 128-byte stores instead of scattered 4-byte stores per lane -- what NVLink peer
-// stores (gather mode) and HBM sector writes both want.
+// One CTA works through UNITS of 256 consecutive words of one x-plane, drawn from a ticket counter:
+//   stage   everything the unit's items will ask for goes to shared memory in ONE round of independent loads (the records
+//           of the unit's words and of the wz + 1 words behind them, in planes i and i + 1), then a CTA-wide scan of the
+//           per-word item counts;
+//   V / T   the unit's crossing samples / active cells are numbered 0..total and handed out in groups of 32 to the eight
+//           warps round-robin, one item per lane: full lanes, no load imbalance inside a unit, and neither phase reads
+//           global memory again except for the densities at the two ends of a crossing edge.
+// The earlier design (a warp per 32 words, items compacted inside the warp, neighbour records fetched from L2 per cell)
+// spent 118 us at 256^3: every group iteration was a chain of dependent L2 round trips, and the batches with 20-40 groups
+// ran serially in one warp (a third of the kernel was tail).
+//
+// kStaged (peer-memory destination): the vertices and triangles of a group occupy CONTIGUOUS output slots, so they are
+// assembled in shared memory and written out by the whole warp with coalesced 128-byte stores.
 template <bool kStaged>
 __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
-  __shared__ float s_vst[kStaged ? kEmitWarps : 1][96 * 3];       // 64 in-plane + 32 x-edge vertices of a group
-  __shared__ uint32_t s_fst[kStaged ? kEmitWarps : 1][160 * 3];   // triangles of a group (slab-local vertex ids)
-  __shared__ signed char s_tri[256][16];
+  __shared__ EmitStage S;
+  // kStaged: per warp 64 in-plane + 32 x-edge vertices and <= 160 triangles (slab-local vertex ids) of a group, in dynamic
+  // shared memory (the static part alone is 40 KB)
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float (*s_vst)[96 * 3] = reinterpret_cast<float (*)[96 * 3]>(s_dyn);
+  uint32_t (*s_fst)[160 * 3] = reinterpret_cast<uint32_t (*)[160 * 3]>(s_dyn + kEmitWarps * 96 * 3 * sizeof(float));
+  __shared__ unsigned short s_tri3[256][5];  // triangle t of a case: its three edges, 4 bits each, winding already applied
   __shared__ unsigned char s_ntri[256];
-  __shared__ unsigned short s_emask[256];
-  __shared__ uint32_t s_off[kEmitWarps][33];
   __shared__ uint32_t s_eid[12][kEmitWarps * 32];  // per-thread column of the 12 edge vertex ids
-  for (int t = threadIdx.x; t < 256 * 16; t += blockDim.x) (&s_tri[0][0])[t] = (&SMB_MC_TRI[0][0])[t];
-  for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-    s_ntri[t] = SMB_MC_NTRI[t];
-    s_emask[t] = SMB_MC_EDGEMASK[t];
+  __shared__ float s_xf[kXfMax];                   // output coordinate of lattice index n (y and z axes)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool flip = p.flags & SMB_MC_FLIP;
+  {
+    const int cs = tid;  // 256 threads = 256 cases
+    const int nt = SMB_MC_NTRI[cs];
+    s_ntri[cs] = (unsigned char)nt;
+    for (int t = 0; t < 5; ++t) {
+      uint32_t e0 = 0, e1 = 0, e2 = 0;
+      if (t < nt) {
+        e0 = (uint32_t)SMB_MC_TRI[cs][3 * t + 0];
+        e1 = (uint32_t)SMB_MC_TRI[cs][3 * t + 1];
+        e2 = (uint32_t)SMB_MC_TRI[cs][3 * t + 2];
+      }
+      s_tri3[cs][t] = (unsigned short)(flip ? (e1 | (e0 << 4) | (e2 << 8)) : (e0 | (e1 << 4) | (e2 << 8)));
+    }
   }
-  __syncthreads();
-
   const McDims d = p.d;
+  const bool use_xf = max(d.ny, d.nz) <= kXfMax;
+  if (use_xf)
+    for (int n = tid; n < max(d.ny, d.nz); n += kEmitWarps * 32) s_xf[n] = mc_xform((float)n, p.flags, p.vdiv, p.vmul, p.vadd);
+
   long long v_off = 0, f_off = 0;
   if (p.all_counts) {
     if (p.count_seq) {
@@ -495,300 +599,342 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
     }
   }
   const long long id_off = p.id_offset + v_off;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const long long gwarp = (long long)blockIdx.x * kEmitWarps + warp;
-  const long long nwarps = (long long)gridDim.x * kEmitWarps;
-  const long long nbatch = (d.nwords + 31) / 32;
+  const int wz = d.wz;
+  constexpr int kUnitsPerChunk = kChunkWords / kUnitWords;
+  const long long nunits = d.nchunks * kUnitsPerChunk;
   const long long sy = d.nz, sx = (long long)d.ny * d.nz;
-  uint32_t* off = s_off[warp];
 
-  for (long long batch = gwarp; batch < nbatch; batch += nwarps) {
-    // ---- phase 0: lane <-> word --------------------------------------------------
-    const long long wd = batch * 32 + lane;
-    uint32_t info = 0;
-    if (wd < d.nwords) info = __ldg(&p.rec[wd].info);
-    if (__ballot_sync(0xffffffffu, info & 1u) == 0u) continue;  // warp-uniform: nothing in these 32 words
-    uint32_t mx = 0, my = 0, mz = 0, act = 0, v0 = 0, v1 = 0, t0 = 0;
-    int wi = 0, wj = 0, ww = 0;
-    WordMasks km;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) km.m[r] = km.s[r] = 0u;
-    if (info & 1u) {
-      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd]));
-      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd]) + 1);
-      mx = hi.x;
-      my = hi.y;
-      mz = hi.z;
-      act = hi.w;
-      wi = (int)(wd / d.pw);
-      const int jw = (int)(wd - (long long)wi * d.pw);
-      wj = jw / d.wz;
-      ww = jw - wj * d.wz;
-      const uint4 cb = __ldg(reinterpret_cast<const uint4*>(&p.cbase[(long long)wi * d.cpp + jw / kChunkWords]));
-      v0 = cb.x + lo.x;
-      v1 = cb.y + lo.y;
-      t0 = cb.z + lo.z;
-      if (act) km = load_masks(p.pos, d, wi, wj, ww);
-    }
+  // Units are drawn heavy chunks first (p.order, written by mc_totals); the draw for the NEXT unit is issued at the head of
+  // the current one, so the atomic's and the order load's latencies are covered by the unit's own work.
+  uint32_t nu = 0, nc = 0;
+  if (tid == 0) {
+    nu = atomicInc(p.ticket, p.ticket_wrap);
+    nc = nu < nunits ? __ldg(p.order + nu / kUnitsPerChunk) : 0u;
+    S.unit = nu;
+    S.chunk = nc;
+  }
+  for (;;) {
+    __syncthreads();  // S.unit / S.chunk are set, the previous unit's shared data is no longer read, the tables are written
+    const uint32_t u = S.unit;
+    if (u >= nunits) break;
+    const uint32_t chunk = S.chunk;
+    const int i = (int)(chunk / d.cpp);
+    const int w0 = (int)(chunk - (uint32_t)i * d.cpp) * kChunkWords + (int)(u % kUnitsPerChunk) * kUnitWords;
+    const int nown = min(kUnitWords, d.pw - w0);
+    const int nst = min(kStageWords, d.pw - w0);
+    const bool hx = i + 1 < d.nx;
+    const bool store_inplane = hx || p.emit_last_plane;
+    // nothing to do: behind the end of the plane / last plane of a slab that is not the last (numbered, not stored)
+    const bool skip = nown <= 0 || (!hx && !store_inplane);
+    if (tid == 0) nu = atomicInc(p.ticket, p.ticket_wrap);
 
-    // ---- phase V: one lane per crossing sample -> its owned vertices -------------
-    {
-      const uint32_t own = mx | my | mz;
-      uint32_t total;
-      const uint32_t ex = warp_excl_scan(__popc(own), lane, total);
-      __syncwarp();
-      off[lane] = ex;
-      if (lane == 0) off[32] = 0xffffffffu;
-      __syncwarp();
-      for (uint32_t base = 0; base < total; base += 32) {  // warp-uniform
-        const uint32_t idx = base + lane;
-        const bool valid = idx < total;
-        int src = 0;
-        if (valid) locate_item(idx, off, src);
-        const uint32_t smx = __shfl_sync(0xffffffffu, mx, src), smy = __shfl_sync(0xffffffffu, my, src);
-        const uint32_t smz = __shfl_sync(0xffffffffu, mz, src);
-        const uint32_t sv0 = __shfl_sync(0xffffffffu, v0, src), sv1 = __shfl_sync(0xffffffffu, v1, src);
-        const int si = __shfl_sync(0xffffffffu, wi, src), sj = __shfl_sync(0xffffffffu, wj, src);
-        const int sw = __shfl_sync(0xffffffffu, ww, src);
-        const uint32_t sex = __shfl_sync(0xffffffffu, ex, src);
-        uint32_t sl_in = 0, sl_x = 0, c_in = 0, c_x = 0;
-        int bit = 0;
-        bool by = false, bz = false, bx = false;
-        if (valid) {
-          const uint32_t sown = smx | smy | smz;
-          bit = __fns(sown, 0, (int)(idx - sex) + 1);
-          const uint32_t below = (1u << bit) - 1u;
-          by = (smy >> bit) & 1u, bz = (smz >> bit) & 1u, bx = (smx >> bit) & 1u;
-          sl_in = sv0 + __popc(smy & below) + __popc(smz & below);
-          sl_x = sv1 + __popc(smx & below);
-          c_in = (by ? 1u : 0u) + (bz ? 1u : 0u);
-          c_x = bx ? 1u : 0u;
+    // ---- stage -----------------------------------------------------------------------------------------------------
+    if (!skip) {
+      for (int t = tid; t < nst; t += kEmitWarps * 32) {
+        const int jw = w0 + t;
+        const long long wd = (long long)i * d.pw + jw;
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd]));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd]) + 1);
+        const uint4 cb = __ldg(reinterpret_cast<const uint4*>(&p.cbase[(long long)i * d.cpp + jw / kChunkWords]));
+        const uint32_t ps = __ldg(p.pos + wd);
+        uint32_t a1 = 0, my1 = 0, mz1 = 0, ps1 = 0;
+        if (hx) {
+          const uint4 hi1 = __ldg(reinterpret_cast<const uint4*>(&p.rec[wd + d.pw]) + 1);
+          a1 = __ldg(&p.rec[wd + d.pw].a) + __ldg(&p.cbase[(long long)(i + 1) * d.cpp + jw / kChunkWords].a);
+          my1 = hi1.y;
+          mz1 = hi1.z;
+          ps1 = __ldg(p.pos + wd + d.pw);
         }
-        // kStaged: the slots of a group are consecutive from lane 0's (lane 0 always holds an item)
-        const uint32_t b_in = __shfl_sync(0xffffffffu, sl_in, 0), b_x = __shfl_sync(0xffffffffu, sl_x, 0);
-        if (valid) {
-          const int k = sw * 32 + bit;
-          const long long pt = (long long)si * sx + (long long)sj * sy + k;
-          const float a = mc_val(p.grid, pt, p.sub, p.sign);
-          const float fi = (float)(p.x_origin + si), fj = (float)sj, fk = (float)k;
-          const bool store_inplane = (si < d.nx - 1) || p.emit_last_plane;
-          float* st = s_vst[kStaged ? warp : 0];
-          if (by) {
-            const float bb = mc_val(p.grid, pt + sy, p.sub, p.sign);
-            const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = kStaged ? st + 3 * (sl_in - b_in) : p.verts + 3 * (v_off + sl_in);
-            if (kStaged || (store_inplane && v_off + sl_in < p.vcap)) {
-              o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
-              o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
-              o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
-            }
-          }
-          if (bz) {
-            const float bb = mc_val(p.grid, pt + 1, p.sub, p.sign);
-            const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            const uint32_t sl = sl_in + (by ? 1u : 0u);
-            float* o = kStaged ? st + 3 * (sl - b_in) : p.verts + 3 * (v_off + sl);
-            if (kStaged || (store_inplane && v_off + sl < p.vcap)) {
-              o[0] = mc_xform(fi, p.flags, p.vdiv, p.vmul, p.vadd);
-              o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
-              o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
-            }
-          }
-          if (bx) {
-            const float bb = mc_val(p.grid, pt + sx, p.sub, p.sign);
-            const float t = __fdiv_rn(a, __fsub_rn(a, bb));
-            float* o = kStaged ? st + 3 * (64 + sl_x - b_x) : p.verts + 3 * (v_off + sl_x);
-            if (kStaged || v_off + sl_x < p.vcap) {
-              o[0] = mc_xform(__fadd_rn(fi, t), p.flags, p.vdiv, p.vmul, p.vadd);
-              o[1] = mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
-              o[2] = mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
-            }
-          }
-        }
-        if (kStaged) {
-          const int nlast = (int)min(32u, total - base) - 1;  // lane of the group's last item
-          const uint32_t n_in = __shfl_sync(0xffffffffu, sl_in + c_in, nlast) - b_in;
-          const uint32_t n_x = __shfl_sync(0xffffffffu, sl_x + c_x, nlast) - b_x;
-          const int pl = __shfl_sync(0xffffffffu, si, 0);  // a group lies in one x-plane
-          const bool st_in = (pl < d.nx - 1) || p.emit_last_plane;
-          __syncwarp();
-          const float* st = s_vst[warp];
-          if (st_in) {
-            const long long o0 = v_off + b_in;
-            for (uint32_t t = lane; t < 3 * n_in; t += 32)
-              if (o0 + t / 3 < p.vcap) p.verts[3 * o0 + t] = st[t];
-          }
-          {
-            const long long o0 = v_off + b_x;
-            for (uint32_t t = lane; t < 3 * n_x; t += 32)
-              if (o0 + t / 3 < p.vcap) p.verts[3 * o0 + t] = st[3 * 64 + t];
-          }
-          __syncwarp();
+        S.pos[0][t] = ps;
+        S.pos[1][t] = ps1;
+        S.A[0][t] = cb.x + lo.x;
+        S.A[1][t] = a1;
+        S.my[0][t] = hi.y;
+        S.my[1][t] = my1;
+        S.mz[0][t] = hi.z;
+        S.mz[1][t] = mz1;
+        S.B[t] = cb.y + lo.y;
+        S.mx[t] = hi.x;
+        if (t < kUnitWords) {
+          S.T[t] = cb.z + lo.z;
+          S.act[t] = hi.w;
+          S.row[t] = (uint32_t)(jw / wz);
         }
       }
     }
-
-    // ---- phase T: one lane per active cell -> its triangles ----------------------
+    if (tid == 0) nc = nu < nunits ? __ldg(p.order + nu / kUnitsPerChunk) : 0u;
+    __syncthreads();  // also: every thread has read S.unit / S.chunk
+    if (skip) {
+      if (tid == 0) {
+        S.unit = nu;
+        S.chunk = nc;
+      }
+      continue;
+    }
+    // ---- CTA-wide exclusive scan of (crossing samples, active cells) per word, packed 16 | 16 -------------------------
+    uint32_t totV, totC;
     {
-      uint32_t total;
-      const uint32_t ex = warp_excl_scan(__popc(act), lane, total);
-      if (total == 0u) continue;  // warp-uniform
-      __syncwarp();
-      off[lane] = ex;
-      if (lane == 0) off[32] = 0xffffffffu;
-      __syncwarp();
-      int carry_src = -1;       // word (lane) whose cells straddle the previous 32-item group ...
-      uint32_t carry_sum = 0u;  // ... and the triangles it has emitted so far
-      for (uint32_t base = 0; base < total; base += 32) {  // warp-uniform
-        const uint32_t idx = base + lane;
-        const bool valid = idx < total;
-        int src = 0;
-        if (valid) locate_item(idx, off, src);
-        WordMasks sk;
+      uint32_t cnt = 0;
+      if (tid < nown) cnt = (uint32_t)__popc(S.mx[tid] | S.my[0][tid] | S.mz[0][tid]) | ((uint32_t)__popc(S.act[tid]) << 16);
+      const uint32_t ex = warp_excl_scan(cnt, lane);
+      if (lane == 31) S.warp_tot[warp] = ex + cnt;
+      __syncthreads();
+      uint32_t base = 0, total = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          sk.m[r] = __shfl_sync(0xffffffffu, km.m[r], src);
-          sk.s[r] = __shfl_sync(0xffffffffu, km.s[r], src);
-        }
-        const uint32_t sact = __shfl_sync(0xffffffffu, act, src);
-        const uint32_t st0 = __shfl_sync(0xffffffffu, t0, src);
-        const int si = __shfl_sync(0xffffffffu, wi, src), sj = __shfl_sync(0xffffffffu, wj, src);
-        const int sw = __shfl_sync(0xffffffffu, ww, src);
-        const uint32_t sex = __shfl_sync(0xffffffffu, ex, src);
-        int bit = 0;
-        uint32_t cs = 0, ntri = 0;
-        if (valid) {
-          bit = __fns(sact, 0, (int)(idx - sex) + 1);
-          cs = cell_case(sk, bit);
-          ntri = s_ntri[cs];
-        }
-        // triangles of the lower cells of the same word: segmented inclusive scan over the
-        // lanes (items are sorted by word, then bit) + the carry of a straddling word
-        const int key = valid ? src : -2;
-        uint32_t inc = ntri;
-#pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xffffffffu, inc, sft);
-          const int ky = __shfl_up_sync(0xffffffffu, key, sft);
-          if (lane >= sft && ky == key) inc += y;
-        }
-        if (key == carry_src) inc += carry_sum;
-        carry_src = __shfl_sync(0xffffffffu, key, 31);
-        carry_sum = __shfl_sync(0xffffffffu, inc, 31);
-        // slot of this cell's first triangle relative to the slab's first (32-bit: a slab holds < 2^32 triangles);
-        // consecutive over the lanes of a group, so lane 0's is the start of the group's run
-        const uint32_t rel_slot = st0 + (inc - ntri);
-        const uint32_t rel_base = __shfl_sync(0xffffffffu, rel_slot, 0);
-        if (ntri != 0u) {
-          // ids of the vertices on this cell's crossing edges, grouped by the sample that
-          // owns them: owner (di,dj,dk) holds x-edge 2dj+dk (di=0), y-edge 4+2di+dk (dj=0),
-          // z-edge 8+2di+dj (dk=0)
-          const uint32_t emask = s_emask[cs];
-          const int jw = sj * d.wz + sw;
-          // The four (di,dj) rows of the cell: the owners dk = 0 and dk = 1 of a row live in the same word
-          // (bit, bit+1) unless bit == 31.  The record loads of two rows (one x-plane) are issued together and
-          // unconditionally (an active cell has all four rows): two trips to L2 per cell instead of one per
-          // owner (eight); all four rows at once would spill at the 64 registers that give 4 CTAs per SM.
-#pragma unroll
-          for (int di = 0; di < 2; ++di) {
-            uint2 rlo[2], rcb[2];  // (a, b) prefixes of the word / bases of its chunk
-            uint4 rhi[2];          // (mx, my, mz, act)
-#pragma unroll
-            for (int dj = 0; dj < 2; ++dj) {
-              const int jw2 = jw + dj * d.wz;
-              const long long w2 = (long long)(si + di) * d.pw + jw2;
-              rlo[dj] = __ldg(reinterpret_cast<const uint2*>(&p.rec[w2]));
-              rhi[dj] = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
-              rcb[dj] = __ldg(reinterpret_cast<const uint2*>(&p.cbase[(long long)(si + di) * d.cpp + jw2 / kChunkWords]));
-            }
-#pragma unroll
-            for (int dj = 0; dj < 2; ++dj) {
-#pragma unroll
-              for (int dk = 0; dk < 2; ++dk) {
-                uint32_t ebits = 0u;  // x-edge needs di == 0, y-edge dj == 0, z-edge dk == 0
-                if (di == 0) ebits |= 1u << (2 * dj + dk);
-                if (dj == 0) ebits |= 1u << (4 + 2 * di + dk);
-                if (dk == 0) ebits |= 1u << (8 + 2 * di + dj);
-                if (!(emask & ebits)) continue;
-                uint2 lo = rlo[dj], cb = rcb[dj];
-                uint4 hi = rhi[dj];
-                int bb = bit + dk;
-                if (bb == 32) {  // the owner is sample 0 of the next word of the row (rare)
-                  const int jw2 = jw + dj * d.wz + 1;
-                  const long long w2 = (long long)(si + di) * d.pw + jw2;
-                  lo = __ldg(reinterpret_cast<const uint2*>(&p.rec[w2]));
-                  hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
-                  cb = __ldg(reinterpret_cast<const uint2*>(&p.cbase[(long long)(si + di) * d.cpp + jw2 / kChunkWords]));
-                  bb = 0;
-                }
-                const uint32_t below = (1u << bb) - 1u;
-                const uint32_t idyz = cb.x + lo.x + __popc(hi.y & below) + __popc(hi.z & below);
-                if (di == 0) s_eid[2 * dj + dk][threadIdx.x] = cb.y + lo.y + __popc(hi.x & below);
-                if (dj == 0) s_eid[4 + 2 * di + dk][threadIdx.x] = idyz;
-                if (dk == 0) s_eid[8 + 2 * di + dj][threadIdx.x] = idyz + ((hi.y >> bb) & 1u);
-              }
-            }
-          }
-          const bool flip = p.flags & SMB_MC_FLIP;
-          if (kStaged) {
-            // slab-local ids of the triangles into the group's contiguous run in shared memory
-            uint32_t* o = s_fst[warp] + 3 * (rel_slot - rel_base);
-            for (uint32_t t = 0; t < ntri; ++t) {
-              const uint32_t i0 = s_eid[s_tri[cs][3 * t + 0]][threadIdx.x];
-              const uint32_t i1 = s_eid[s_tri[cs][3 * t + 1]][threadIdx.x];
-              const uint32_t i2 = s_eid[s_tri[cs][3 * t + 2]][threadIdx.x];
-              o[3 * t + 0] = flip ? i1 : i0;
-              o[3 * t + 1] = flip ? i0 : i1;
-              o[3 * t + 2] = i2;
-            }
-          } else {
-            const long long slot0 = f_off + rel_slot;
-            if (p.flags & SMB_MC_FACES_I32) {
-              // int32 indices (what Blender's loop arrays and a PCIe / NVLink wire want); ids < 2^31 is checked on the host
-              int* o = static_cast<int*>(p.faces) + 3 * slot0;
-              const int ido = (int)id_off;
-              for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
-                const int i0 = (int)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + ido;
-                const int i1 = (int)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + ido;
-                const int i2 = (int)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + ido;
-                o[3 * t + 0] = flip ? i1 : i0;
-                o[3 * t + 1] = flip ? i0 : i1;
-                o[3 * t + 2] = i2;
-              }
-            } else {
-              long long* o = static_cast<long long*>(p.faces) + 3 * slot0;
-              for (uint32_t t = 0; t < ntri && slot0 + t < p.fcap; ++t) {
-                const long long i0 = (long long)s_eid[s_tri[cs][3 * t + 0]][threadIdx.x] + id_off;
-                const long long i1 = (long long)s_eid[s_tri[cs][3 * t + 1]][threadIdx.x] + id_off;
-                const long long i2 = (long long)s_eid[s_tri[cs][3 * t + 2]][threadIdx.x] + id_off;
-                o[3 * t + 0] = flip ? i1 : i0;
-                o[3 * t + 1] = flip ? i0 : i1;
-                o[3 * t + 2] = i2;
-              }
-            }
+      for (int q = 0; q < kEmitWarps; ++q) {
+        const uint32_t v = S.warp_tot[q];
+        if (q < warp) base += v;
+        total += v;
+      }
+      totV = total & 0xffffu;
+      totC = total >> 16;
+      const uint32_t e = base + ex;
+      S.offV[tid] = tid < nown ? (e & 0xffffu) : totV;  // words behind the unit: never <= a valid item index
+      S.offC[tid] = tid < nown ? (e >> 16) : totC;
+      __syncthreads();
+    }
+    const float xi = mc_xform((float)(p.x_origin + i), p.flags, p.vdiv, p.vmul, p.vadd);
+
+    // ---- phase V: one lane per crossing sample -> its owned vertices -----------------------------------------------------
+    for (uint32_t base = (uint32_t)warp * 32u; base < totV; base += kEmitWarps * 32u) {  // warp-uniform
+      const uint32_t idx = base + lane;
+      const bool valid = idx < totV;
+      uint32_t sl_in = 0, sl_x = 0, c_in = 0, c_x = 0;
+      bool by = false, bz = false, bx = false;
+      int j = 0, k = 0;
+      long long pt = 0;
+      if (valid) {
+        const int src = locate_word(S.offV, idx);
+        const uint32_t smx = S.mx[src], smy = S.my[0][src], smz = S.mz[0][src];
+        const int bit = nth_set_bit(smx | smy | smz, idx - S.offV[src]);
+        const uint32_t below = (1u << bit) - 1u;
+        by = (smy >> bit) & 1u, bz = (smz >> bit) & 1u, bx = (smx >> bit) & 1u;
+        sl_in = S.A[0][src] + __popc(smy & below) + __popc(smz & below);
+        sl_x = S.B[src] + __popc(smx & below);
+        c_in = (by ? 1u : 0u) + (bz ? 1u : 0u);
+        c_x = bx ? 1u : 0u;
+        j = (int)S.row[src];
+        k = (w0 + src - j * wz) * 32 + bit;
+        pt = (long long)i * sx + (long long)j * sy + k;
+      }
+      // kStaged: the slots of a group are consecutive from lane 0's (lane 0 always holds an item)
+      const uint32_t b_in = __shfl_sync(0xffffffffu, sl_in, 0), b_x = __shfl_sync(0xffffffffu, sl_x, 0);
+      if (valid) {
+        // all densities of the item in one round trip
+        const float a = mc_val(p.grid, pt, p.sub, p.sign);
+        float vy = 0.f, vz = 0.f, vx = 0.f;
+        if (by) vy = mc_val(p.grid, pt + sy, p.sub, p.sign);
+        if (bz) vz = mc_val(p.grid, pt + 1, p.sub, p.sign);
+        if (bx) vx = mc_val(p.grid, pt + sx, p.sub, p.sign);
+        const float fj = (float)j, fk = (float)k;
+        const float xj = use_xf ? s_xf[j] : mc_xform(fj, p.flags, p.vdiv, p.vmul, p.vadd);
+        const float xk = use_xf ? s_xf[k] : mc_xform(fk, p.flags, p.vdiv, p.vmul, p.vadd);
+        float* st = s_vst[kStaged ? warp : 0];
+        if (by) {
+          const float t = __fdiv_rn(a, __fsub_rn(a, vy));
+          float* o = kStaged ? st + 3 * (sl_in - b_in) : p.verts + 3 * (v_off + sl_in);
+          if (kStaged || (store_inplane && v_off + sl_in < p.vcap)) {
+            o[0] = xi;
+            o[1] = mc_xform(__fadd_rn(fj, t), p.flags, p.vdiv, p.vmul, p.vadd);
+            o[2] = xk;
           }
         }
+        if (bz) {
+          const float t = __fdiv_rn(a, __fsub_rn(a, vz));
+          const uint32_t sl = sl_in + (by ? 1u : 0u);
+          float* o = kStaged ? st + 3 * (sl - b_in) : p.verts + 3 * (v_off + sl);
+          if (kStaged || (store_inplane && v_off + sl < p.vcap)) {
+            o[0] = xi;
+            o[1] = xj;
+            o[2] = mc_xform(__fadd_rn(fk, t), p.flags, p.vdiv, p.vmul, p.vadd);
+          }
+        }
+        if (bx) {
+          const float t = __fdiv_rn(a, __fsub_rn(a, vx));
+          float* o = kStaged ? st + 3 * (64 + sl_x - b_x) : p.verts + 3 * (v_off + sl_x);
+          if (kStaged || v_off + sl_x < p.vcap) {
+            o[0] = mc_xform(__fadd_rn((float)(p.x_origin + i), t), p.flags, p.vdiv, p.vmul, p.vadd);
+            o[1] = xj;
+            o[2] = xk;
+          }
+        }
+      }
+      if (kStaged) {
+        const int nlast = (int)min(32u, totV - base) - 1;  // lane of the group's last item
+        const uint32_t n_in = __shfl_sync(0xffffffffu, sl_in + c_in, nlast) - b_in;
+        const uint32_t n_x = __shfl_sync(0xffffffffu, sl_x + c_x, nlast) - b_x;
+        __syncwarp();
+        const float* st = s_vst[warp];
+        if (store_inplane) {
+          const long long o0 = v_off + b_in;
+          for (uint32_t t = lane; t < 3 * n_in; t += 32)
+            if (o0 + t / 3 < p.vcap) p.verts[3 * o0 + t] = st[t];
+        }
+        {
+          const long long o0 = v_off + b_x;
+          for (uint32_t t = lane; t < 3 * n_x; t += 32)
+            if (o0 + t / 3 < p.vcap) p.verts[3 * o0 + t] = st[3 * 64 + t];
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- phase T: one lane per active cell -> its triangles -------------------------------------------------------------
+    // sign mask / record fields of word t2 (relative to the unit) of plane i + di: staged, or (nz > 2272) from global memory
+    auto pos_at = [&](int di, int t2) -> uint32_t {
+      return t2 < kStageWords ? S.pos[di][t2] : __ldg(p.pos + (long long)(i + di) * d.pw + w0 + t2);
+    };
+    // the cell's 8 corner signs: row r = (di, dj) contributes the bits (k, k + 1) of its word, taken across the word border
+    auto cell_case_at = [&](int src, int bit) -> uint32_t {
+      uint32_t cs = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int t2 = src + (r & 1) * wz;
+        const uint32_t two = __funnelshift_r(pos_at(r >> 1, t2), pos_at(r >> 1, t2 + 1), bit) & 3u;
+        cs |= two << (2 * r);
+      }
+      return cs;
+    };
+    struct RowInfo {
+      uint32_t A, my, mz, B, mx;
+    };
+    auto row_info = [&](int di, int t2) -> RowInfo {
+      RowInfo r;
+      if (t2 < kStageWords) {
+        r.A = S.A[di][t2];
+        r.my = S.my[di][t2];
+        r.mz = S.mz[di][t2];
+        r.B = di == 0 ? S.B[t2] : 0u;
+        r.mx = di == 0 ? S.mx[t2] : 0u;
+      } else {
+        const int jw2 = w0 + t2;
+        const long long w2 = (long long)(i + di) * d.pw + jw2;
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(&p.rec[w2]));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(&p.rec[w2]) + 1);
+        const uint2 cb = __ldg(reinterpret_cast<const uint2*>(&p.cbase[(long long)(i + di) * d.cpp + jw2 / kChunkWords]));
+        r.A = cb.x + lo.x;
+        r.B = cb.y + lo.y;
+        r.mx = hi.x;
+        r.my = hi.y;
+        r.mz = hi.z;
+      }
+      return r;
+    };
+    for (uint32_t base = (uint32_t)warp * 32u; base < totC; base += kEmitWarps * 32u) {  // warp-uniform
+      const uint32_t idx = base + lane;
+      const bool valid = idx < totC;
+      int src = 0, bit = 0;
+      uint32_t cs = 0, ntri = 0;
+      if (valid) {
+        src = locate_word(S.offC, idx);
+        bit = nth_set_bit(S.act[src], idx - S.offC[src]);
+        cs = cell_case_at(src, bit);
+        ntri = s_ntri[cs];
+      }
+      // Triangles are numbered in word order, then cell order: the group's run starts at the first triangle of lane 0's
+      // cell = the word's first slot + the triangles of the word's lower cells (one cell per lane, summed over the warp),
+      // and continues over the lanes.
+      const int src0 = __shfl_sync(0xffffffffu, src, 0), bit0 = __shfl_sync(0xffffffffu, bit, 0);
+      uint32_t pre = 0;
+      if (bit0 != 0) {  // warp-uniform
+        if (lane < bit0 && ((S.act[src0] >> lane) & 1u)) pre = s_ntri[cell_case_at(src0, lane)];
+        pre = __reduce_add_sync(0xffffffffu, pre);
+      }
+      const uint32_t rel_base = S.T[src0] + pre;
+      const uint32_t rel_slot = rel_base + warp_excl_scan(ntri, lane);
+      if (ntri != 0u) {
+        // ids of the vertices on the cell's 12 edges, by the sample that owns them: owner (di,dj,dk) holds x-edge 2dj+dk
+        // (di=0), y-edge 4+2di+dk (dj=0), z-edge 8+2di+dj (dk=0).  The owners dk = 0, 1 of a row (di,dj) are bits k, k+1 of
+        // one word: the second one's ids follow from the first one's by the crossing bits at k.  All 12 are computed
+        // (branch-free); the case's triangles only read the ones that exist.
+#pragma unroll
+        for (int di = 0; di < 2; ++di) {
+#pragma unroll
+          for (int dj = 0; dj < 2; ++dj) {
+            const int t2 = src + dj * wz;
+            const RowInfo r = row_info(di, t2);
+            const uint32_t below = (1u << bit) - 1u;
+            const uint32_t myb = (r.my >> bit) & 1u, mzb = (r.mz >> bit) & 1u;
+            const uint32_t idyz0 = r.A + __popc(r.my & below) + __popc(r.mz & below);
+            uint32_t idyz1 = idyz0 + myb + mzb;
+            uint32_t idx0 = 0, idx1 = 0;
+            if (di == 0) {
+              idx0 = r.B + __popc(r.mx & below);
+              idx1 = idx0 + ((r.mx >> bit) & 1u);
+            }
+            if (bit == 31) {  // the owner dk = 1 is sample 0 of the next word of the row: nothing of that word lies below it
+              const RowInfo r2 = row_info(di, t2 + 1);
+              idyz1 = r2.A;
+              idx1 = r2.B;
+            }
+            if (di == 0) {
+              s_eid[2 * dj + 0][tid] = idx0;
+              s_eid[2 * dj + 1][tid] = idx1;
+            }
+            if (dj == 0) {
+              s_eid[4 + 2 * di + 0][tid] = idyz0;
+              s_eid[4 + 2 * di + 1][tid] = idyz1;
+            }
+            s_eid[8 + 2 * di + dj][tid] = idyz0 + myb;
+          }
+        }
+        const unsigned short* tri = s_tri3[cs];
         if (kStaged) {
-          // the whole warp writes the group's run: 128 contiguous bytes (int32) / 256 (int64) per store instruction
-          const int nlast = (int)min(32u, total - base) - 1;
-          const uint32_t n3 = 3u * (__shfl_sync(0xffffffffu, rel_slot + ntri, nlast) - rel_base);
-          __syncwarp();
-          const uint32_t* st = s_fst[warp];
-          const long long o0 = f_off + rel_base;
+          // slab-local ids of the triangles into the group's contiguous run in shared memory
+          uint32_t* o = s_fst[warp] + 3 * (rel_slot - rel_base);
+          for (uint32_t t = 0; t < ntri; ++t) {
+            const uint32_t e = tri[t];
+            o[3 * t + 0] = s_eid[e & 15u][tid];
+            o[3 * t + 1] = s_eid[(e >> 4) & 15u][tid];
+            o[3 * t + 2] = s_eid[e >> 8][tid];
+          }
+        } else {
+          const long long slot0 = f_off + rel_slot;
+          const uint32_t nt = (uint32_t)max(0LL, min((long long)ntri, p.fcap - slot0));
           if (p.flags & SMB_MC_FACES_I32) {
-            int* o = static_cast<int*>(p.faces) + 3 * o0;
+            // int32 indices (what Blender's loop arrays and a PCIe / NVLink wire want); ids < 2^31 is checked on the host
+            int* o = static_cast<int*>(p.faces) + 3 * slot0;
             const int ido = (int)id_off;
-            for (uint32_t t = lane; t < n3; t += 32)
-              if (o0 + t / 3 < p.fcap) o[t] = (int)st[t] + ido;
+            for (uint32_t t = 0; t < nt; ++t) {
+              const uint32_t e = tri[t];
+              o[3 * t + 0] = (int)s_eid[e & 15u][tid] + ido;
+              o[3 * t + 1] = (int)s_eid[(e >> 4) & 15u][tid] + ido;
+              o[3 * t + 2] = (int)s_eid[e >> 8][tid] + ido;
+            }
           } else {
-            long long* o = static_cast<long long*>(p.faces) + 3 * o0;
-            for (uint32_t t = lane; t < n3; t += 32)
-              if (o0 + t / 3 < p.fcap) o[t] = (long long)st[t] + id_off;
+            long long* o = static_cast<long long*>(p.faces) + 3 * slot0;
+            for (uint32_t t = 0; t < nt; ++t) {
+              const uint32_t e = tri[t];
+              o[3 * t + 0] = (long long)s_eid[e & 15u][tid] + id_off;
+              o[3 * t + 1] = (long long)s_eid[(e >> 4) & 15u][tid] + id_off;
+              o[3 * t + 2] = (long long)s_eid[e >> 8][tid] + id_off;
+            }
           }
-          __syncwarp();
         }
       }
+      if (kStaged) {
+        // the whole warp writes the group's run: 128 contiguous bytes (int32) / 256 (int64) per store instruction
+        const int nlast = (int)min(32u, totC - base) - 1;
+        const uint32_t n3 = 3u * (__shfl_sync(0xffffffffu, rel_slot + ntri, nlast) - rel_base);
+        __syncwarp();
+        const uint32_t* st = s_fst[warp];
+        const long long o0 = f_off + rel_base;
+        if (p.flags & SMB_MC_FACES_I32) {
+          int* o = static_cast<int*>(p.faces) + 3 * o0;
+          const int ido = (int)id_off;
+          for (uint32_t t = lane; t < n3; t += 32)
+            if (o0 + t / 3 < p.fcap) o[t] = (int)st[t] + ido;
+        } else {
+          long long* o = static_cast<long long*>(p.faces) + 3 * o0;
+          for (uint32_t t = lane; t < n3; t += 32)
+            if (o0 + t / 3 < p.fcap) o[t] = (long long)st[t] + id_off;
+        }
+        __syncwarp();
+      }
+    }
+    if (tid == 0) {
+      S.unit = nu;
+      S.chunk = nc;
     }
   }
   if (p.all_counts) __threadfence_system();  // peer-memory stores are performed before the grid retires
@@ -842,7 +988,7 @@ extern "C" size_t smb_mc_workspace_bytes(int nx, int ny, int nz) {
 
 static int launch_count(const McDims& d, const McWorkspace& w, int emit_last_plane, smb_mc_counts* counts_dev, cudaStream_t st) {
   mc_count<<<(unsigned)d.nchunks, 256, 0, st>>>(w.pos, d, w.rec, w.ctot);
-  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev);
+  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev, w.ticket, w.order);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 
@@ -916,13 +1062,21 @@ static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, flo
   p.count_seq = reinterpret_cast<const long long*>(count_seq);
   p.seq = seq;
   p.error_flag = reinterpret_cast<long long*>(error_flag);
-  const long long nbatch = (d.nwords + 31) / 32;
-  long long blocks = (nbatch + kEmitWarps - 1) / kEmitWarps;
-  const long long cap = (long long)sm_count() * 8;
+  const long long nunits = d.nchunks * (kChunkWords / kUnitWords);
+  long long blocks = nunits;
+  const long long cap = (long long)sm_count() * 4;  // the resident set: units are drawn from the ticket counter, not assigned
   if (blocks > cap) blocks = cap;
+  if (nunits + blocks > 0xffffffffLL) return SMB_ERR_BAD_ARG;
+  p.ticket = w.ticket;
+  p.order = w.order;
+  p.ticket_wrap = (uint32_t)(nunits + blocks - 1);  // every CTA ends on exactly one failed draw -> the counter is 0 again afterwards
   // staged, coalesced output only on request (SMB_MC_COALESCE: destination is peer memory): on local HBM the extra
-  // shared-memory pass costs more than the scattered 4-byte stores it replaces (measured 0.18 vs 0.15 ms at 256^3)
-  if ((flags & SMB_MC_COALESCE) && d.pw % 32 == 0) mc_emit<true><<<(unsigned)blocks, kEmitWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  // shared-memory pass costs more than the scattered 4-byte stores it replaces
+  constexpr size_t kStagedDyn = kEmitWarps * (96 * 3 * sizeof(float) + 160 * 3 * sizeof(uint32_t));
+  static const cudaError_t staged_attr =
+      cudaFuncSetAttribute(mc_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedDyn);
+  if (staged_attr != cudaSuccess) return SMB_ERR_CUDA;
+  if (flags & SMB_MC_COALESCE) mc_emit<true><<<(unsigned)blocks, kEmitWarps * 32, kStagedDyn, (cudaStream_t)stream>>>(p);
   else mc_emit<false><<<(unsigned)blocks, kEmitWarps * 32, 0, (cudaStream_t)stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
