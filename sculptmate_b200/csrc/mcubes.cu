@@ -41,6 +41,9 @@ namespace smb {
 
 constexpr int kChunkWords = 1024;  // words per count CTA (256 threads x 4): 512 CTAs at 256^3 (2048 = 256 CTAs left the 148 SMs 1.7 waves)
 constexpr int kWordsPerThread = 4;
+constexpr int kUnitWords = 256;   // mc_emit's unit: words of one x-plane staged per CTA (= its threads); 4 units per count chunk
+constexpr int kMaxSlices = 16;    // a heavy unit is worked on by up to 16 CTAs
+constexpr int kSliceWeight = 3072;  // vertices + triangles one work item should hold at most
 
 struct McDims {
   int nx, ny, nz, wz;   // wz = words per z-row
@@ -80,8 +83,9 @@ struct McWorkspace {
   WordRec* rec;      // nwords
   ChunkRec* ctot;    // nchunks totals
   ChunkRec* cbase;   // nchunks bases
-  uint32_t* ticket;  // mc_emit's unit counter (zeroed by mc_totals, wraps back to 0 at the end of every emit)
-  uint32_t* order;   // nchunks chunk numbers, heaviest first: the order mc_emit draws its units in
+  uint32_t* ticket;  // [0] mc_emit's work counter (zeroed by mc_totals, wraps back to 0 at the end of every emit), [1] number of work items
+  uint32_t* uw;      // weight (vertices + triangles) of every unit of 256 words (mc_count)
+  uint32_t* items;   // mc_emit's work list, heaviest first (mc_totals): (unit << 8) | (slice << 4) | (slices - 1)
   size_t bytes;
 };
 
@@ -102,7 +106,8 @@ __host__ inline McWorkspace carve(void* base, const McDims& d) {
   w.ctot = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
   w.cbase = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
   w.ticket = reinterpret_cast<uint32_t*>(take(256));
-  w.order = reinterpret_cast<uint32_t*>(take((size_t)d.nchunks * 4));
+  w.uw = reinterpret_cast<uint32_t*>(take((size_t)d.nchunks * (kChunkWords / kUnitWords) * 4));
+  w.items = reinterpret_cast<uint32_t*>(take((size_t)d.nchunks * (kChunkWords / kUnitWords) * kMaxSlices * 4));
   w.bytes = off;
   return w;
 }
@@ -240,7 +245,7 @@ __device__ __forceinline__ uint32_t cell_case(const WordMasks& k, int lane) {
 // The three counters are packed into one 64-bit lane (21/21/22 bits: a chunk holds at
 // most kChunkWords*64 in-plane vertices, kChunkWords*32 x-edge vertices, kChunkWords*160 triangles).
 __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos, McDims d, WordRec* __restrict__ rec,
-                                                ChunkRec* __restrict__ ctot) {
+                                                ChunkRec* __restrict__ ctot, uint32_t* __restrict__ uw) {
   __shared__ unsigned char s_ntri[256];
   __shared__ unsigned long long s_warp[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -315,6 +320,15 @@ __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos
       rec[(long long)i * d.pw + jw] = r;
     }
   }
+  if (tid < kChunkWords / kUnitWords) {
+    // weight of mc_emit's units (256 words = the words of two warps here): vertices + triangles
+    constexpr int kWarpsPerUnit = kUnitWords / (32 * kWordsPerThread);
+    unsigned long long v = 0;
+#pragma unroll
+    for (int q = 0; q < kWarpsPerUnit; ++q) v += s_warp[tid * kWarpsPerUnit + q];
+    uw[(long long)blockIdx.x * (kChunkWords / kUnitWords) + tid] =
+        (uint32_t)(v & 0x1fffffu) + (uint32_t)((v >> 21) & 0x1fffffu) + (uint32_t)(v >> 42);
+  }
   if (tid == 0) {
     ChunkRec cr;
     cr.a = (uint32_t)(total & 0x1fffffu);
@@ -331,7 +345,8 @@ __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos
 // Triangles: chunk order.  Sequential over tiles of 1024 with a running carry.
 __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ ctot, ChunkRec* __restrict__ cbase,
                                                   McDims d, int emit_last_plane, smb_mc_counts* __restrict__ counts,
-                                                  uint32_t* __restrict__ ticket, uint32_t* __restrict__ order) {
+                                                  const uint32_t* __restrict__ uw, uint32_t* __restrict__ ticket,
+                                                  uint32_t* __restrict__ items) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -398,24 +413,32 @@ __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ c
     counts->ntris = totals[1];
     counts->nverts_numbered = totals[0];
     counts->reserved = 0;
-    *ticket = 0u;
   }
-  // ---- the order mc_emit draws its work in: chunks by weight (vertices + triangles), heaviest first, in 64 linear
-  // classes -- longest-processing-time-first keeps the kernel's tail short when the surface is concentrated in a part of
-  // the volume.  The order inside a class depends on the atomics; it only affects scheduling, never the output.
-  __shared__ uint32_t s_hist[64], s_cur[64], s_max;
+  // ---- mc_emit's work list.  A unit = 256 consecutive words of a plane (4 per chunk); its weight (vertices + triangles)
+  // comes from mc_count.  Empty units produce no work, heavy ones are cut into up to 16
+  // slices (each staged by its own CTA, the groups dealt round-robin), and the items are listed heaviest first in 64
+  // linear classes: longest-processing-time-first keeps the tail of mc_emit short when the surface is concentrated in
+  // a part of the volume.  The order inside a class depends on the atomics; it only affects scheduling, never the output.
+  __shared__ uint32_t s_hist[64], s_cur[64];
   if (tid < 64) s_hist[tid] = 0u;
-  if (tid == 0) s_max = 0u;
   __syncthreads();
-  uint32_t mx = 0u;
-  for (long long c = tid; c < d.nchunks; c += 1024) mx = max(mx, ctot[c].a + ctot[c].b + ctot[c].t);
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (lane == 0) atomicMax(&s_max, mx);
-  __syncthreads();
-  const unsigned long long wmax = max(s_max, 1u);
-  for (long long c = tid; c < d.nchunks; c += 1024) {
-    const uint32_t w = ctot[c].a + ctot[c].b + ctot[c].t;
-    atomicAdd(&s_hist[63u - (uint32_t)((unsigned long long)w * 63ull / wmax)], 1u);
+  constexpr int kUnitsPerChunk = kChunkWords / kUnitWords;
+  const long long nunits = d.nchunks * kUnitsPerChunk;
+  auto slices_of = [](uint32_t w) -> uint32_t { return w == 0u ? 0u : min((uint32_t)kMaxSlices, (w + kSliceWeight - 1) / kSliceWeight); };
+  auto class_of = [](uint32_t w, uint32_t n) -> uint32_t { return 63u - min(63u, (w / n) * 63u / kSliceWeight); };
+  constexpr int kPer = 8;  // unit weights per thread and round: independent loads, one latency per 8192 units
+  for (long long u0 = 0; u0 < nunits; u0 += 1024 * kPer) {
+    uint32_t w[kPer];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const long long u = u0 + e * 1024 + tid;
+      w[e] = u < nunits ? uw[u] : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const uint32_t n = slices_of(w[e]);
+      if (n) atomicAdd(&s_hist[class_of(w[e], n)], n);
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -424,11 +447,26 @@ __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ c
       s_cur[q] = run;
       run += s_hist[q];
     }
+    ticket[0] = 0u;
+    ticket[1] = run;
   }
   __syncthreads();
-  for (long long c = tid; c < d.nchunks; c += 1024) {
-    const uint32_t w = ctot[c].a + ctot[c].b + ctot[c].t;
-    order[atomicAdd(&s_cur[63u - (uint32_t)((unsigned long long)w * 63ull / wmax)], 1u)] = (uint32_t)c;
+  for (long long u0 = 0; u0 < nunits; u0 += 1024 * kPer) {
+    uint32_t w[kPer];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const long long u = u0 + e * 1024 + tid;
+      w[e] = u < nunits ? uw[u] : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const uint32_t n = slices_of(w[e]);
+      if (n) {
+        const uint32_t u = (uint32_t)(u0 + e * 1024 + tid);
+        const uint32_t at = atomicAdd(&s_cur[class_of(w[e], n)], n);
+        for (uint32_t k = 0; k < n; ++k) items[at + k] = (u << 8) | (k << 4) | (n - 1u);
+      }
+    }
   }
 }
 
@@ -455,11 +493,10 @@ struct EmitParams {
   const long long* count_seq;
   long long seq;
   long long* error_flag;
-  // dynamic scheduling: every CTA draws unit numbers from *ticket (atomicInc with wrap = nunits + gridDim - 1: each CTA ends
-  // on exactly one failed draw, so the counter is back at 0 when the grid retires)
-  uint32_t* ticket;
-  uint32_t ticket_wrap;
-  const uint32_t* order;  // chunk numbers, heaviest first (mc_totals)
+  // dynamic scheduling: every CTA draws positions of the work list from ticket[0] (atomicInc with wrap = items + gridDim - 1:
+  // each CTA ends on exactly one failed draw, so the counter is back at 0 when the grid retires)
+  uint32_t* ticket;       // [0] counter, [1] number of work items
+  const uint32_t* items;  // the work list (mc_totals)
 };
 
 __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float vmul, float vadd) {
@@ -469,7 +506,6 @@ __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float 
 }
 
 constexpr int kEmitWarps = 8;
-constexpr int kUnitWords = 256;  // words of one x-plane per CTA unit (= threads per CTA)
 constexpr int kHaloMax = 72;     // words staged behind the unit (rows j+1 and the next word of a row: wz + 1 <= 72 up to nz = 2272)
 constexpr int kStageWords = kUnitWords + kHaloMax;
 constexpr int kXfMax = 1024;  // lattice indices with a tabulated output coordinate
@@ -506,7 +542,8 @@ struct EmitStage {
   uint32_t offV[kUnitWords];     // exclusive prefix over the unit's words of crossing samples / active cells
   uint32_t offC[kUnitWords];
   uint32_t warp_tot[kEmitWarps];
-  uint32_t unit, chunk;  // the ticket drawn for the next loop iteration and the chunk it maps to
+  uint32_t draw, item;  // the ticket drawn for the next loop iteration and the work item it maps to
+  uint32_t gctr;        // groups of the current item handed out so far
 };
 
 // largest l in [0, kUnitWords) with off[l] <= idx
@@ -601,32 +638,37 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
   const long long id_off = p.id_offset + v_off;
   const int wz = d.wz;
   constexpr int kUnitsPerChunk = kChunkWords / kUnitWords;
-  const long long nunits = d.nchunks * kUnitsPerChunk;
   const long long sy = d.nz, sx = (long long)d.ny * d.nz;
 
-  // Units are drawn heavy chunks first (p.order, written by mc_totals); the draw for the NEXT unit is issued at the head of
-  // the current one, so the atomic's and the order load's latencies are covered by the unit's own work.
+  // Work items (a unit, or one of the slices of a heavy unit) come from mc_totals' list, heaviest first; the draw for the
+  // NEXT item is issued at the head of the current one, so the atomic's and the list load's latencies are covered by work.
+  const uint32_t nitems = __ldg(p.ticket + 1);
+  const uint32_t wrap = nitems + gridDim.x - 1u;
   uint32_t nu = 0, nc = 0;
   if (tid == 0) {
-    nu = atomicInc(p.ticket, p.ticket_wrap);
-    nc = nu < nunits ? __ldg(p.order + nu / kUnitsPerChunk) : 0u;
-    S.unit = nu;
-    S.chunk = nc;
+    nu = atomicInc(p.ticket, wrap);
+    nc = nu < nitems ? __ldg(p.items + nu) : 0u;
+    S.draw = nu;
+    S.item = nc;
   }
   for (;;) {
-    __syncthreads();  // S.unit / S.chunk are set, the previous unit's shared data is no longer read, the tables are written
-    const uint32_t u = S.unit;
-    if (u >= nunits) break;
-    const uint32_t chunk = S.chunk;
+    __syncthreads();  // S.draw / S.item are set, the previous item's shared data is no longer read, the tables are written
+    if (S.draw >= nitems) break;
+    const uint32_t item = S.item;
+    const uint32_t u = item >> 8, slice = (item >> 4) & 15u, nslices = (item & 15u) + 1u;
+    const uint32_t chunk = u / kUnitsPerChunk;
     const int i = (int)(chunk / d.cpp);
     const int w0 = (int)(chunk - (uint32_t)i * d.cpp) * kChunkWords + (int)(u % kUnitsPerChunk) * kUnitWords;
     const int nown = min(kUnitWords, d.pw - w0);
     const int nst = min(kStageWords, d.pw - w0);
     const bool hx = i + 1 < d.nx;
     const bool store_inplane = hx || p.emit_last_plane;
-    // nothing to do: behind the end of the plane / last plane of a slab that is not the last (numbered, not stored)
-    const bool skip = nown <= 0 || (!hx && !store_inplane);
-    if (tid == 0) nu = atomicInc(p.ticket, p.ticket_wrap);
+    // nothing to store: last plane of a slab that is not the last (its in-plane crossings are numbered, not stored)
+    const bool skip = !hx && !store_inplane;
+    if (tid == 0) {
+      nu = atomicInc(p.ticket, wrap);
+      S.gctr = 0u;
+    }
 
     // ---- stage -----------------------------------------------------------------------------------------------------
     if (!skip) {
@@ -662,12 +704,12 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
         }
       }
     }
-    if (tid == 0) nc = nu < nunits ? __ldg(p.order + nu / kUnitsPerChunk) : 0u;
-    __syncthreads();  // also: every thread has read S.unit / S.chunk
+    if (tid == 0) nc = nu < nitems ? __ldg(p.items + nu) : 0u;
+    __syncthreads();  // also: every thread has read S.draw / S.item
     if (skip) {
       if (tid == 0) {
-        S.unit = nu;
-        S.chunk = nc;
+        S.draw = nu;
+        S.item = nc;
       }
       continue;
     }
@@ -695,8 +737,19 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
     }
     const float xi = mc_xform((float)(p.x_origin + i), p.flags, p.vdiv, p.vmul, p.vadd);
 
-    // ---- phase V: one lane per crossing sample -> its owned vertices -----------------------------------------------------
-    for (uint32_t base = (uint32_t)warp * 32u; base < totV; base += kEmitWarps * 32u) {  // warp-uniform
+    // The item's groups of 32 crossing samples (V) and of 32 active cells (T) -- every nslices-th group of the unit, starting
+    // at `slice` -- are handed to the warps by a shared counter, T groups (the longer ones) first.
+    const uint32_t ngV = (totV + 31u) / 32u, ngC = (totC + 31u) / 32u;
+    const uint32_t nVs = ngV > slice ? (ngV - slice + nslices - 1u) / nslices : 0u;
+    const uint32_t nCs = ngC > slice ? (ngC - slice + nslices - 1u) / nslices : 0u;
+    for (;;) {
+    uint32_t gq = 0;
+    if (lane == 0) gq = atomicAdd(&S.gctr, 1u);
+    gq = __shfl_sync(0xffffffffu, gq, 0);
+    if (gq >= nVs + nCs) break;
+    // ---- V: one lane per crossing sample -> its owned vertices -----------------------------------------------------------
+    if (gq >= nCs) {
+      const uint32_t base = (slice + nslices * (gq - nCs)) * 32u;
       const uint32_t idx = base + lane;
       const bool valid = idx < totV;
       uint32_t sl_in = 0, sl_x = 0, c_in = 0, c_x = 0;
@@ -777,9 +830,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
         }
         __syncwarp();
       }
+      continue;
     }
 
-    // ---- phase T: one lane per active cell -> its triangles -------------------------------------------------------------
+    // ---- T: one lane per active cell -> its triangles -------------------------------------------------------------------
     // sign mask / record fields of word t2 (relative to the unit) of plane i + di: staged, or (nz > 2272) from global memory
     auto pos_at = [&](int di, int t2) -> uint32_t {
       return t2 < kStageWords ? S.pos[di][t2] : __ldg(p.pos + (long long)(i + di) * d.pw + w0 + t2);
@@ -820,7 +874,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
       }
       return r;
     };
-    for (uint32_t base = (uint32_t)warp * 32u; base < totC; base += kEmitWarps * 32u) {  // warp-uniform
+    {
+      const uint32_t base = (slice + nslices * gq) * 32u;
       const uint32_t idx = base + lane;
       const bool valid = idx < totC;
       int src = 0, bit = 0;
@@ -932,9 +987,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
         __syncwarp();
       }
     }
+    }  // groups
     if (tid == 0) {
-      S.unit = nu;
-      S.chunk = nc;
+      S.draw = nu;
+      S.item = nc;
     }
   }
   if (p.all_counts) __threadfence_system();  // peer-memory stores are performed before the grid retires
@@ -987,8 +1043,8 @@ extern "C" size_t smb_mc_workspace_bytes(int nx, int ny, int nz) {
 }
 
 static int launch_count(const McDims& d, const McWorkspace& w, int emit_last_plane, smb_mc_counts* counts_dev, cudaStream_t st) {
-  mc_count<<<(unsigned)d.nchunks, 256, 0, st>>>(w.pos, d, w.rec, w.ctot);
-  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev, w.ticket, w.order);
+  mc_count<<<(unsigned)d.nchunks, 256, 0, st>>>(w.pos, d, w.rec, w.ctot, w.uw);
+  mc_totals<<<1, 1024, 0, st>>>(w.ctot, w.cbase, d, emit_last_plane, counts_dev, w.uw, w.ticket, w.items);
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 
@@ -1063,13 +1119,12 @@ static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, flo
   p.seq = seq;
   p.error_flag = reinterpret_cast<long long*>(error_flag);
   const long long nunits = d.nchunks * (kChunkWords / kUnitWords);
-  long long blocks = nunits;
-  const long long cap = (long long)sm_count() * 4;  // the resident set: units are drawn from the ticket counter, not assigned
+  if (nunits >= (1LL << 24)) return SMB_ERR_BAD_ARG;  // a work item carries its unit in 24 bits
+  long long blocks = nunits * kMaxSlices;
+  const long long cap = (long long)sm_count() * 4;  // the resident set: work is drawn from mc_totals' list, not assigned
   if (blocks > cap) blocks = cap;
-  if (nunits + blocks > 0xffffffffLL) return SMB_ERR_BAD_ARG;
   p.ticket = w.ticket;
-  p.order = w.order;
-  p.ticket_wrap = (uint32_t)(nunits + blocks - 1);  // every CTA ends on exactly one failed draw -> the counter is 0 again afterwards
+  p.items = w.items;
   // staged, coalesced output only on request (SMB_MC_COALESCE: destination is peer memory): on local HBM the extra
   // shared-memory pass costs more than the scattered 4-byte stores it replaces
   constexpr size_t kStagedDyn = kEmitWarps * (96 * 3 * sizeof(float) + 160 * 3 * sizeof(uint32_t));
