@@ -85,7 +85,7 @@ struct McWorkspace {
   ChunkRec* cbase;   // nchunks bases
   uint32_t* ticket;  // [0] mc_emit's work counter (zeroed by mc_totals, wraps back to 0 at the end of every emit), [1] number of work items
   uint32_t* uw;      // weight (vertices + triangles) of every unit of 256 words (mc_count)
-  uint32_t* items;   // mc_emit's work list, heaviest first (mc_totals): (unit << 8) | (slice << 4) | (slices - 1)
+  uint2* items;      // mc_emit's work list, heaviest first (mc_totals): x = plane, y = (first word / 256) << 8 | slice << 4 | slices - 1
   size_t bytes;
 };
 
@@ -107,7 +107,7 @@ __host__ inline McWorkspace carve(void* base, const McDims& d) {
   w.cbase = reinterpret_cast<ChunkRec*>(take((size_t)d.nchunks * sizeof(ChunkRec)));
   w.ticket = reinterpret_cast<uint32_t*>(take(256));
   w.uw = reinterpret_cast<uint32_t*>(take((size_t)d.nchunks * (kChunkWords / kUnitWords) * 4));
-  w.items = reinterpret_cast<uint32_t*>(take((size_t)d.nchunks * (kChunkWords / kUnitWords) * kMaxSlices * 4));
+  w.items = reinterpret_cast<uint2*>(take((size_t)d.nchunks * (kChunkWords / kUnitWords) * kMaxSlices * sizeof(uint2)));
   w.bytes = off;
   return w;
 }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) mc_count(const uint32_t* __restrict__ pos
 __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ ctot, ChunkRec* __restrict__ cbase,
                                                   McDims d, int emit_last_plane, smb_mc_counts* __restrict__ counts,
                                                   const uint32_t* __restrict__ uw, uint32_t* __restrict__ ticket,
-                                                  uint32_t* __restrict__ items) {
+                                                  uint2* __restrict__ items) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -462,9 +462,12 @@ __global__ void __launch_bounds__(1024) mc_totals(const ChunkRec* __restrict__ c
     for (int e = 0; e < kPer; ++e) {
       const uint32_t n = slices_of(w[e]);
       if (n) {
-        const uint32_t u = (uint32_t)(u0 + e * 1024 + tid);
+        const long long u = u0 + e * 1024 + tid;
+        const long long c = u / kUnitsPerChunk;
+        const uint32_t plane = (uint32_t)(c / d.cpp);
+        const uint32_t unit_in_plane = (uint32_t)(c - (long long)plane * d.cpp) * kUnitsPerChunk + (uint32_t)(u - c * kUnitsPerChunk);
         const uint32_t at = atomicAdd(&s_cur[class_of(w[e], n)], n);
-        for (uint32_t k = 0; k < n; ++k) items[at + k] = (u << 8) | (k << 4) | (n - 1u);
+        for (uint32_t k = 0; k < n; ++k) items[at + k] = make_uint2(plane, (unit_in_plane << 8) | (k << 4) | (n - 1u));
       }
     }
   }
@@ -496,7 +499,7 @@ struct EmitParams {
   // dynamic scheduling: every CTA draws positions of the work list from ticket[0] (atomicInc with wrap = items + gridDim - 1:
   // each CTA ends on exactly one failed draw, so the counter is back at 0 when the grid retires)
   uint32_t* ticket;       // [0] counter, [1] number of work items
-  const uint32_t* items;  // the work list (mc_totals)
+  const uint2* items;     // the work list (mc_totals)
 };
 
 __device__ __forceinline__ float mc_xform(float v, int flags, float vdiv, float vmul, float vadd) {
@@ -542,7 +545,8 @@ struct EmitStage {
   uint32_t offV[kUnitWords];     // exclusive prefix over the unit's words of crossing samples / active cells
   uint32_t offC[kUnitWords];
   uint32_t warp_tot[kEmitWarps];
-  uint32_t draw, item;  // the ticket drawn for the next loop iteration and the work item it maps to
+  uint32_t draw;        // the ticket drawn for the next loop iteration and the work item it maps to
+  uint2 item;
   uint32_t gctr;        // groups of the current item handed out so far
 };
 
@@ -576,9 +580,12 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
 // spent 118 us at 256^3: every group iteration was a chain of dependent L2 round trips, and the batches with 20-40 groups
 // ran serially in one warp (a third of the kernel was tail).
 //
+// kFar: rows are longer than the staged halo (wz + 1 > 72, nz > 2272): the neighbour words that fall behind it are read from
+// global memory; the common instantiation has no such path.
+//
 // kStaged (peer-memory destination): the vertices and triangles of a group occupy CONTIGUOUS output slots, so they are
 // assembled in shared memory and written out by the whole warp with coalesced 128-byte stores.
-template <bool kStaged>
+template <bool kStaged, bool kFar>
 __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
   __shared__ EmitStage S;
   // kStaged: per warp 64 in-plane + 32 x-edge vertices and <= 160 triangles (slab-local vertex ids) of a group, in dynamic
@@ -637,28 +644,27 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
   }
   const long long id_off = p.id_offset + v_off;
   const int wz = d.wz;
-  constexpr int kUnitsPerChunk = kChunkWords / kUnitWords;
   const long long sy = d.nz, sx = (long long)d.ny * d.nz;
 
   // Work items (a unit, or one of the slices of a heavy unit) come from mc_totals' list, heaviest first; the draw for the
   // NEXT item is issued at the head of the current one, so the atomic's and the list load's latencies are covered by work.
   const uint32_t nitems = __ldg(p.ticket + 1);
   const uint32_t wrap = nitems + gridDim.x - 1u;
-  uint32_t nu = 0, nc = 0;
+  uint32_t nu = 0;
+  uint2 nc = make_uint2(0u, 0u);
   if (tid == 0) {
     nu = atomicInc(p.ticket, wrap);
-    nc = nu < nitems ? __ldg(p.items + nu) : 0u;
+    if (nu < nitems) nc = __ldg(p.items + nu);
     S.draw = nu;
     S.item = nc;
   }
   for (;;) {
     __syncthreads();  // S.draw / S.item are set, the previous item's shared data is no longer read, the tables are written
     if (S.draw >= nitems) break;
-    const uint32_t item = S.item;
-    const uint32_t u = item >> 8, slice = (item >> 4) & 15u, nslices = (item & 15u) + 1u;
-    const uint32_t chunk = u / kUnitsPerChunk;
-    const int i = (int)(chunk / d.cpp);
-    const int w0 = (int)(chunk - (uint32_t)i * d.cpp) * kChunkWords + (int)(u % kUnitsPerChunk) * kUnitWords;
+    const uint2 item = S.item;
+    const uint32_t slice = (item.y >> 4) & 15u, nslices = (item.y & 15u) + 1u;
+    const int i = (int)item.x;
+    const int w0 = (int)(item.y >> 8) * kUnitWords;
     const int nown = min(kUnitWords, d.pw - w0);
     const int nst = min(kStageWords, d.pw - w0);
     const bool hx = i + 1 < d.nx;
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
         }
       }
     }
-    if (tid == 0) nc = nu < nitems ? __ldg(p.items + nu) : 0u;
+    if (tid == 0 && nu < nitems) nc = __ldg(p.items + nu);
     __syncthreads();  // also: every thread has read S.draw / S.item
     if (skip) {
       if (tid == 0) {
@@ -836,7 +842,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
     // ---- T: one lane per active cell -> its triangles -------------------------------------------------------------------
     // sign mask / record fields of word t2 (relative to the unit) of plane i + di: staged, or (nz > 2272) from global memory
     auto pos_at = [&](int di, int t2) -> uint32_t {
-      return t2 < kStageWords ? S.pos[di][t2] : __ldg(p.pos + (long long)(i + di) * d.pw + w0 + t2);
+      return (!kFar || t2 < kStageWords) ? S.pos[di][t2] : __ldg(p.pos + (long long)(i + di) * d.pw + w0 + t2);
     };
     // the cell's 8 corner signs: row r = (di, dj) contributes the bits (k, k + 1) of its word, taken across the word border
     auto cell_case_at = [&](int src, int bit) -> uint32_t {
@@ -854,7 +860,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
     };
     auto row_info = [&](int di, int t2) -> RowInfo {
       RowInfo r;
-      if (t2 < kStageWords) {
+      if (!kFar || t2 < kStageWords) {
         r.A = S.A[di][t2];
         r.my = S.my[di][t2];
         r.mz = S.mz[di][t2];
@@ -950,7 +956,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
             // int32 indices (what Blender's loop arrays and a PCIe / NVLink wire want); ids < 2^31 is checked on the host
             int* o = static_cast<int*>(p.faces) + 3 * slot0;
             const int ido = (int)id_off;
-            for (uint32_t t = 0; t < nt; ++t) {
+#pragma unroll
+            for (uint32_t t = 0; t < 5u; ++t) {
+              if (t >= nt) break;
               const uint32_t e = tri[t];
               o[3 * t + 0] = (int)s_eid[e & 15u][tid] + ido;
               o[3 * t + 1] = (int)s_eid[(e >> 4) & 15u][tid] + ido;
@@ -958,7 +966,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) mc_emit(EmitParams p) {
             }
           } else {
             long long* o = static_cast<long long*>(p.faces) + 3 * slot0;
-            for (uint32_t t = 0; t < nt; ++t) {
+#pragma unroll
+            for (uint32_t t = 0; t < 5u; ++t) {
+              if (t >= nt) break;
               const uint32_t e = tri[t];
               o[3 * t + 0] = (long long)s_eid[e & 15u][tid] + id_off;
               o[3 * t + 1] = (long long)s_eid[(e >> 4) & 15u][tid] + id_off;
@@ -1119,7 +1129,7 @@ static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, flo
   p.seq = seq;
   p.error_flag = reinterpret_cast<long long*>(error_flag);
   const long long nunits = d.nchunks * (kChunkWords / kUnitWords);
-  if (nunits >= (1LL << 24)) return SMB_ERR_BAD_ARG;  // a work item carries its unit in 24 bits
+  if ((d.pw + kUnitWords - 1) / kUnitWords >= (1 << 24)) return SMB_ERR_BAD_ARG;  // a work item carries its unit-in-plane in 24 bits
   long long blocks = nunits * kMaxSlices;
   const long long cap = (long long)sm_count() * 4;  // the resident set: work is drawn from mc_totals' list, not assigned
   if (blocks > cap) blocks = cap;
@@ -1128,11 +1138,22 @@ static int launch_emit(const float* grid, int nx, int ny, int nz, float sub, flo
   // staged, coalesced output only on request (SMB_MC_COALESCE: destination is peer memory): on local HBM the extra
   // shared-memory pass costs more than the scattered 4-byte stores it replaces
   constexpr size_t kStagedDyn = kEmitWarps * (96 * 3 * sizeof(float) + 160 * 3 * sizeof(uint32_t));
-  static const cudaError_t staged_attr =
-      cudaFuncSetAttribute(mc_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedDyn);
+  static const cudaError_t staged_attr = [] {
+    cudaError_t e = cudaFuncSetAttribute(mc_emit<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedDyn);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc_emit<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedDyn);
+    return e;
+  }();
   if (staged_attr != cudaSuccess) return SMB_ERR_CUDA;
-  if (flags & SMB_MC_COALESCE) mc_emit<true><<<(unsigned)blocks, kEmitWarps * 32, kStagedDyn, (cudaStream_t)stream>>>(p);
-  else mc_emit<false><<<(unsigned)blocks, kEmitWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  const bool staged = flags & SMB_MC_COALESCE, far = d.wz + 1 > kHaloMax;
+  const unsigned g = (unsigned)blocks, b = kEmitWarps * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (staged) {
+    if (far) mc_emit<true, true><<<g, b, kStagedDyn, st>>>(p);
+    else mc_emit<true, false><<<g, b, kStagedDyn, st>>>(p);
+  } else {
+    if (far) mc_emit<false, true><<<g, b, 0, st>>>(p);
+    else mc_emit<false, false><<<g, b, 0, st>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? SMB_OK : SMB_ERR_CUDA;
 }
 

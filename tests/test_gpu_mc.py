@@ -144,10 +144,11 @@ def test_speculative_extract_equals_two_phase_incl_overflow():
         assert torch.equal(v, v2) and torch.equal(f, f2), radius
 
 
-@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 5, 33), (7, 4, 65), (40, 70, 31), (5, 300, 9)])
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 5, 33), (7, 4, 65), (40, 70, 31), (5, 300, 9), (3, 5, 2400), (2, 3, 4700)])
 def test_ragged_and_minimum_shapes_bit_exact(shape):
     """Non-cubic slabs, rows that are not a multiple of the 32-sample word, planes larger than one
-    2048-word chunk, and the 2x2x2 minimum -- all bit-exact against the oracle."""
+    1024-word chunk, the 2x2x2 minimum, and rows longer than the emit kernel's staged halo (nz > 2272: neighbour words
+    read from global memory; more than 256 words per row) -- all bit-exact against the oracle."""
     rng = np.random.RandomState(sum(shape))
     g = rng.randn(*shape).astype(np.float32)
     for a in range(3):  # a little smoothing so that surfaces are not pure noise
@@ -159,17 +160,20 @@ def test_ragged_and_minimum_shapes_bit_exact(shape):
     np.testing.assert_array_equal(f, f_ref)
 
 
-@pytest.mark.parametrize("kind,shape", [("gyroid", (33, 32, 64)), ("noise", (9, 32, 32)), ("torus", (64, 64, 64)), ("gyroid", (40, 96, 96))])
+@pytest.mark.parametrize("kind,shape", [("gyroid", (33, 32, 64)), ("noise", (9, 32, 32)), ("torus", (64, 64, 64)), ("gyroid", (40, 96, 96)),
+                                        ("gyroid", (37, 45, 50)), ("noise", (8, 5, 2400))])
 @pytest.mark.parametrize("faces_dtype", [torch.int64, torch.int32])
 def test_emit_variants_equal_the_default(kind, shape, faces_dtype):
     """The coalescing emit (MC_COALESCE: a warp's output run assembled in shared memory and written with 128-byte stores;
     what the multi-GPU gather uses for peer memory) and the int32 face width produce the same mesh as the default kernel,
-    on whole grids and on an interior slab with an id offset.  ny * ceil(nz/32) is a multiple of 32 here, the shape class
-    the staged kernel handles; other shapes fall back to the direct kernel inside the library."""
+    on whole grids and on an interior slab with an id offset, including ragged shapes and rows longer than the staged halo."""
     from sculptmate_b200 import _capi, runtime
 
     R = max(shape)
-    g = volume(kind, R, seed=3)[: shape[0], : shape[1], : shape[2]].copy()
+    if R <= 128:
+        g = volume(kind, R, seed=3)[: shape[0], : shape[1], : shape[2]].copy()
+    else:  # a long-row slab: do not build the R^3 volume
+        g = np.random.RandomState(3).randn(*shape).astype(np.float32)
     gd = torch.from_numpy(g).cuda()
     for emit_last, x_origin, off in ((True, 0, 0), (False, 5, 1000)):
         pend = runtime.mc_count(gd, sub=0.01, sign=1.0, emit_last_plane=emit_last)
