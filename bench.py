@@ -269,19 +269,27 @@ def sf3d_measure(dev, rank: int, world: int, steps: int, warmup: int, tet_n: int
         rec.append((a, b))
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in rec]
-    # the dominant kernel alone (K3: gather + both heads on tcgen05, fp16 planes), CUDA events on the launching stream
+    # the query + heads alone, CUDA events on the launching stream: the lattice tet-grid kernels (tables + tcgen05 MLP; what
+    # triplane_to_meshes runs on a lattice-ordered grid) and, for comparison, the arbitrary-position kernel K3 on the same vertices
     tcp = runtime.get_sf3d_points_pack(m.decoder, dev)
-    kq = []
+    lattice = h.lattice is not None and m.cfg.lattice_path
+    hpacks = [runtime.get_sf3d_head_decoder_pack(m.decoder, k, dev) for k in ("density", "vertex_offset")]
+    kq, kpts = [], []
     for i in range(steps + 2):
         flush.fill_(i & 0xFF)
         planes = runtime.prepare_planes_half(scenes[i % 2])
-        a, b = ev(), ev()
+        planes_cl = runtime.prepare_planes_cl(scenes[i % 2])
+        a, b, c = ev(), ev(), ev()
         a.record()
         runtime.query_points_tc(planes, tcp, pos, RADIUS, -1.0, align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"))
         b.record()
+        if lattice:
+            runtime.query_tetgrid_tc(planes_cl, hpacks, (1, 3), (True, False), (-1.0, 0.0), m._lattice_axis_u(dev), h.lattice[1])
+        c.record()
         torch.cuda.synchronize()
         if i >= 2:
-            kq.append(a.elapsed_time(b))
+            kpts.append(a.elapsed_time(b))
+            kq.append(b.elapsed_time(c) if lattice else a.elapsed_time(b))
     # e2e through the Python API the reference calls (sf3d/system.py:141-168): triplane in pinned host memory in,
     # mesh in pinned host memory out, copies inside the timed region
     stage_in = torch.empty_like(scenes[0])
@@ -320,9 +328,13 @@ def sf3d_measure(dev, rank: int, world: int, steps: int, warmup: int, tet_n: int
         "mesh": {"verts": int(mesh.v_pos.shape[0]), "tris": int(mesh.t_pos_idx.shape[0])},
         "e2e": {"value": nv * world / (e2e_ms / steps * 1e-3), "unit": "pts/s", "ms_per_step": e2e_ms / steps, "h2d_bytes_per_step": int(host_tp[0].numel() * 4),
                 "d2h_bytes_per_step": int(d2h), "api": "SF3D.triplane_to_meshes (Python drop-in); triplane from pinned host memory, mesh to pinned host memory"},
-        "roofline": {"kernel": "points_tc_kernel (gather + both heads on tcgen05, fp16 planes)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
+        "roofline": {"kernel": "tetgrid_tables_kernel + tetgrid_tc_kernel (layer 0 from three n^2 tables in fp32, hidden layer on tcgen05, both heads)"
+                               if lattice else "points_tc_kernel (gather + both heads on tcgen05, fp16 planes)",
+                     "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": f"{peak_kind} (burst)", "kernel_ms": kq_ms,
-                     "flop_per_point": sf3d_flop, "note": "gather-bound in practice (12 taps x 40 channels per point from L2-resident planes)"},
+                     "flop_per_point": sf3d_flop, "points_kernel_ms": float(np.mean(kpts)),
+                     "note": "algorithmic FLOPs of the reference's two heads (layer 0 counted although the lattice path replaces it by table sums); "
+                             "points_kernel_ms = the arbitrary-position kernel on the same vertices (gather-bound: 12 taps x 40 channels per point)"},
         "gpu_launches": 8 * steps * world,
     }
     if with_cpu and rank == 0:

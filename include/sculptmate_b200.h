@@ -370,6 +370,24 @@ int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges
                   void* stream);
 int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t n_vertices, float* out, void* stream);
 
+/* SF3D.query_triplane + decoder(include=[...]) (sf3d/system.py:153-154, 170-198; sf3d/models/network.py:148-208) at the
+ * vertices of a LATTICE-ordered tet grid: grid_vertices[(a*nB + b)*nC + c] = (coord_0[a], coord_1[b], coord_2[c]) up to a
+ * permutation of the spatial axes (the caller detects this once when it loads the grid, isosurface.py:71-81).  Every vertex
+ * then samples each plane at a position given by TWO lattice indices, so layer 0 of a head is the sum of three table rows,
+ *     W0 . [f_xy; f_xz; f_yz] + b0 = C[a][b] + T1[a][c] + T2[b][c],
+ * built per call in fp32 (n^2 bilinear interpolations per table instead of n^3 per plane); the hidden layers run on tcgen05
+ * (fp16 operands, fp32 accumulate) and the last Linear as fp32 dot products.  Up to 2 heads per call.
+ *   planes_cl       (3,Hp,Wp,40) fp32 channels-last (smb_scene_prepare)
+ *   decoder_blobs[h], layouts[h]   the head packed with smb_decoder_pack_host: Linear(120,64), (n_hidden-1) x Linear(64,64),
+ *                   last Linear padded to 4 rows (n_out[h] = 1..3 of them are read)
+ *   exp_act[h], out_bias[h]        1: out = exp(x + out_bias) (trunc_exp forward, config.yaml density head); 0: out = x
+ *   axis_u[k]       device array (extents[k]) of lattice index k's coordinate already mapped to (-1,1) with the reference's
+ *                   own scale_tensor ops; spatial_dim[k] in {0,1,2} says which of x,y,z it is (a permutation)
+ *   outs[h]         (extents[0]*extents[1]*extents[2], n_out[h]) fp32, vertex order of the grid */
+int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int align_corners, int nheads, const void* const* decoder_blobs,
+                         const smb_decoder_layout* const* layouts, const int* n_out, const int* exp_act, const float* out_bias,
+                         const float* const* axis_u, const int* extents, const int* spatial_dim, float* const* outs, void* stream);
+
 /* ------------------------------------------------------------ volume rendering
  * The two elementwise stages of TriplaneNeRFRenderer._forward (tsr/models/nerf_renderer.py:93-152) around the field
  * query (smb_query_points_tc / smb_query_points_f32 at the positions produced here):

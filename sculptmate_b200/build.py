@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsculptmate_b200.so")
-SOURCES = ["capi.cu", "field_f32.cu", "lattice_api.cu", "mcubes.cu", "sf3d.cu", "field_pts_tc.cu", "field_tc_ta.cu", "mesh_io.cu", "render.cu", "bake.cu"]
+SOURCES = ["capi.cu", "field_f32.cu", "lattice_api.cu", "mcubes.cu", "sf3d.cu", "field_pts_tc.cu", "field_tc_ta.cu", "tetgrid_tc.cu", "mesh_io.cu", "render.cu", "bake.cu"]
 # developer build (`python -m sculptmate_b200.build --dev` or SMB_DEV_VARIANTS=1): superseded / experimental lattice kernels and their
 # instrumentation, compiled with -DSMB_DEV_VARIANTS; the product library does not contain them
 DEV_SOURCES = ["field_tc.cu", "field_tc_pair.cu"]

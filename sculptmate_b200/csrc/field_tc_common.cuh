@@ -173,6 +173,7 @@ __device__ __forceinline__ void build_table(const TcParams& p, const TableGeom& 
 int launch_tc_pair(const TcParams& p, int sms, int poly_pairs, cudaStream_t st);
 // field_tc_ta.cu: the activations-in-TMEM variant
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st);
+void keep_async_scratch(int dev);  // lattice_api.cu: release threshold of the default memory pool
 int read_trace_ta(long long* host, int n);  // developer build: SMB_TC_TRACE=2 timeline of the last launch
 // mcubes.cu: sign masks of a density slab (the stand-alone pass the fused path replaces) / where they live
 int launch_mc_signs(const float* grid, int nx, int ny, int nz, float sub, float sign, void* workspace, size_t workspace_bytes,

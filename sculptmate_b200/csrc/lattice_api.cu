@@ -58,6 +58,20 @@ __global__ void __launch_bounds__(256) lattice_axis_tables(TcParams p, float* __
   }
 }
 
+// Keep freed stream-ordered scratch in the device's default pool instead of returning it to the driver at every
+// synchronisation (release threshold 0 is the default: each call would then pay a fresh allocation).
+void keep_async_scratch(int dev) {
+  static int pool_dev = -1;
+  if (pool_dev != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = 1ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_dev = dev;
+  }
+}
+
 #ifdef SMB_DEV_VARIANTS
 int launch_tc_smem(const TcParams& p, int sms, bool trace, cudaStream_t st);
 int read_trace_smem(long long* host, int n);
@@ -148,19 +162,7 @@ static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob
   // axis tables in stream-ordered scratch memory (the pool keeps the block between calls: no allocation cost after the first)
   const size_t tab_floats = ((size_t)nx + (size_t)R) * cfg->Hp * kHid;
   float* tabs = nullptr;
-  {
-    // keep freed scratch in the device's default pool instead of returning it to the driver at every synchronisation
-    // (release threshold 0 is the default: each call would then pay a fresh allocation)
-    static int pool_dev = -1;
-    if (pool_dev != dev) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = 1ull << 30;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      pool_dev = dev;
-    }
-  }
+  keep_async_scratch(dev);
   if (!getenv("SMB_NO_AXIS_TABLES") && cudaMallocAsync(reinterpret_cast<void**>(&tabs), tab_floats * sizeof(float), st) == cudaSuccess) {
     p.t1 = tabs;
     p.t2 = tabs + (size_t)nx * cfg->Hp * kHid;

@@ -1,0 +1,466 @@
+// SF3D on a LATTICE-ordered tetrahedral grid: query_triplane + the MaterialMLP heads `density` and `vertex_offset` at every
+// grid vertex (StableFast/sf3d/system.py:141-198, sf3d/models/network.py:148-208) without gathering a single plane texel per
+// vertex.
+//
+// When the tet grid's vertex array is an outer product of three coordinate lists (sf3d/models/isosurface.py
+// detects that once at load; a Kuhn / marching-cubes-style grid is), vertex (a, b, c) of the lattice samples the three planes
+// at positions that depend on TWO lattice indices each.  Interpolation and the first Linear are linear, so
+//     W0 . [f_xy ; f_xz ; f_yz] + b0  =  C[a][b] + T1[a][c] + T2[b][c]
+// with three tables of n^2 x 64 entries per head (3 x 161^2 instead of 161^3 bilinear gathers of 120 channels and 120 x 64
+// contractions), built per call by tetgrid_tables_kernel in fp32 -- closer to the reference's fp32 than the fp16 operands of
+// the points kernel (field_pts_tc.cu), which stays the path for arbitrary positions.
+//
+// tetgrid_tc_kernel then is the lattice kernel of field_tc_ta.cu with a different front end: a tile = 128 consecutive rows
+// (b, c) of one lattice plane a (rows flattened, so 161-long lines do not leave a 33-row tail tile); 4 producer warps sum the
+// three table rows of every sample into a shared-memory tile (coalesced 16-byte loads from the L2-resident tables, 16-byte
+// chunks XOR-swizzled so that the consumers' row-per-thread LDS.128 are conflict-free); 4 consumer warpgroups apply SiLU,
+// write the fp16 activations to TENSOR MEMORY as the A operand of the hidden layer's tcgen05.mma (weights and the bias
+// K-block resident in shared memory), and evaluate the head (1 or 3 outputs) as fp32 dot products in the last epilogue.
+// Both heads run in one launch (the tile index carries the head).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "field_tc_common.cuh"
+
+namespace smb {
+
+constexpr int kTgWG = 4;         // consumer warpgroups (4 x 96 + 8 = 392 TMEM columns); 4 producer warps, 640 threads
+constexpr int kTgMaxHeads = 2;
+constexpr int kTgSBytes = kTileM * kHid * 4;  // 32 KB: layer-0 pre-activations (already halved) of one tile, fp32
+
+struct TgHead {
+  const float* C;   // [nA][nB][64]  (b0/2 folded in)
+  const float* T1;  // [nA][nC][64]
+  const float* T2;  // [nB][nC][64]
+  const unsigned char* tc_weights;  // (n_hidden-1) x 8 KB fp16 UMMA images of W_l/2
+  const unsigned char* tc_biasblk;  // (n_hidden-1) x 8 KB bias K-blocks
+  const float* head_w;              // last Linear, (4,64) fp32 row-major (rows >= n_out unused), then its bias (4)
+  float* out;                       // (N, n_out)
+  int n_out;                        // 1 or 3
+  int exp_act;                      // 1: out = exp(x + out_bias) (trunc_exp forward); 0: out = x
+  float out_bias;
+};
+struct TgParams {
+  TgHead head[kTgMaxHeads];
+  int nheads, n_hidden;
+  int nA, nB, nC;  // lattice extents: slow, mid, fast index of the vertex order
+  int wait_ns;
+};
+
+struct TgTile {
+  int head, a, r0, nvalid;
+};
+__device__ __forceinline__ TgTile tg_tile(const TgParams& p, unsigned t, unsigned tpp, unsigned tiles_per_head) {
+  TgTile g;
+  g.head = (int)(t / tiles_per_head);
+  const unsigned rem = t - (unsigned)g.head * tiles_per_head;
+  g.a = (int)(rem / tpp);
+  g.r0 = (int)(rem - (unsigned)g.a * tpp) * kTileM;
+  g.nvalid = min(kTileM, p.nB * p.nC - g.r0);
+  return g;
+}
+
+__global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int nh = p.n_hidden;
+  const int wper = (nh - 1) * kWBytes;  // per head: hidden images, and as much again for the bias K-blocks
+  unsigned char* sW = smem;                              // [head][l-1]
+  unsigned char* sBB = sW + p.nheads * wper;             // [head][l-1]
+  unsigned char* sS = sBB + p.nheads * wper;             // [wg] 32 KB tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + kTgWG * kTgSBytes);
+  // bars[0] = weights; per warpgroup g: [1+3g] s_full, [2+3g] s_empty, [3+3g] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * kTgWG);
+  float* sHeadW = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [head][4*64 + 4]
+
+  const int tid_cta = threadIdx.x;
+  const int wid = tid_cta >> 5;
+  const int lane = tid_cta & 31;
+
+  if (tid_cta == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    for (int g = 0; g < kTgWG; ++g) {
+      mbar_init(smem_u32(&bars[1 + 3 * g]), 1);  // s_full: elected producer lane
+      mbar_init(smem_u32(&bars[2 + 3 * g]), 4);  // s_empty: one elected lane per consumer warp
+      mbar_init(smem_u32(&bars[3 + 3 * g]), 1);  // acc_full: tcgen05.commit
+    }
+    mbar_fence_init();
+  }
+  for (int i = tid_cta; i < p.nheads * (4 * kHid + 4); i += blockDim.x) {
+    const int h = i / (4 * kHid + 4);
+    sHeadW[i] = p.head[h].head_w[i - h * (4 * kHid + 4)];
+  }
+  if (wid == 0) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t bar_w = smem_u32(&bars[0]);
+  if (tid_cta == 0) {
+    mbar_expect_tx(bar_w, (uint32_t)(2 * p.nheads * wper));
+    for (int h = 0; h < p.nheads; ++h)
+      for (int off = 0; off < wper; off += kWBytes) {
+        bulk_g2s(smem_u32(sW + h * wper + off), p.head[h].tc_weights + off, (uint32_t)kWBytes, bar_w);
+        bulk_g2s(smem_u32(sBB + h * wper + off), p.head[h].tc_biasblk + off, (uint32_t)kWBytes, bar_w);
+      }
+  }
+
+  const int RP = p.nB * p.nC;                       // rows of one lattice plane
+  const unsigned tpp = (unsigned)((RP + kTileM - 1) / kTileM);
+  const unsigned tiles_per_head = (unsigned)p.nA * tpp;
+  const unsigned ntiles = tiles_per_head * (unsigned)p.nheads;
+
+  if (wid >= kTgWG * 4) {
+    // =================================================================== producer: one warp per warpgroup
+    const int g = wid - kTgWG * 4;
+    float4* dst = reinterpret_cast<float4*>(sS + g * kTgSBytes);
+    const uint32_t bar_full = smem_u32(&bars[1 + 3 * g]), bar_empty = smem_u32(&bars[2 + 3 * g]);
+    uint32_t par_empty = 1;  // a fresh barrier passes a wait on parity 1
+    const int half = lane >> 4, chunk = lane & 15;
+    for (unsigned n = 0;; ++n) {
+      const unsigned t = (n * gridDim.x + blockIdx.x) * kTgWG + g;
+      if (t >= ntiles) break;
+      const TgTile tg = tg_tile(p, t, tpp, tiles_per_head);
+      const TgHead& H = p.head[tg.head];
+      const float4* T2 = reinterpret_cast<const float4*>(H.T2);
+      const float4* T1 = reinterpret_cast<const float4*>(H.T1) + (long long)tg.a * p.nC * 16;
+      const float4* Cc = reinterpret_cast<const float4*>(H.C) + (long long)tg.a * p.nB * 16;
+      // this lane's rows: half, half + 2, ... ; (b, c) advance by two rows per step
+      int r = min(tg.r0 + half, RP - 1);
+      int b = r / p.nC, c = r - b * p.nC;
+      mbar_wait_sleep(bar_empty, par_empty, 20000u);
+      par_empty ^= 1u;
+      constexpr int kU = 4;
+#pragma unroll 1
+      for (int it = 0; it < kTileM / 2; it += kU) {
+        float4 v1[kU], v2[kU], vc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          v2[u] = __ldg(T2 + (long long)(b * p.nC + c) * 16 + chunk);
+          v1[u] = __ldg(T1 + c * 16 + chunk);
+          vc[u] = __ldg(Cc + b * 16 + chunk);
+          // two rows on; rows behind the plane's end repeat the last one (never read back)
+          c += 2;
+          if (c >= p.nC) {
+            c -= p.nC;
+            ++b;
+          }
+          if (b >= p.nB) {
+            b = p.nB - 1;
+            c = p.nC - 1;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int row = 2 * (it + u) + half;
+          float4 s;
+          s.x = v1[u].x + v2[u].x + vc[u].x;
+          s.y = v1[u].y + v2[u].y + vc[u].y;
+          s.z = v1[u].z + v2[u].z + vc[u].z;
+          s.w = v1[u].w + v2[u].w + vc[u].w;
+          dst[row * 16 + (chunk ^ (row & 7))] = s;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full);
+    }
+  } else {
+    // =================================================================== consumer
+    const int wg = wid >> 2;
+    const int q = wid & 3;
+    const int m = (q << 5) | lane;
+    const int tid_wg = tid_cta & 127;
+    const float4* sSv = reinterpret_cast<const float4*>(sS + wg * kTgSBytes);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(wg * 96);
+    const uint32_t a_tmem = d_tmem + 64;
+    const uint32_t ones_tmem = tmem_base + (uint32_t)(kTgWG * 96);
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t idesc_hidden = umma_idesc_f16_f32(128, 64);
+    const uint32_t bar_acc = smem_u32(&bars[3 + 3 * wg]);
+    const uint32_t bar_full = smem_u32(&bars[1 + 3 * wg]), bar_empty = smem_u32(&bars[2 + 3 * wg]);
+    uint32_t par_t = 0, par_acc = 0;
+
+    {  // constant activation block of the bias MMA: k = 64, 65 -> 1.0 (bias hi, lo rows), k = 66..79 -> 0
+      const uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(ones_tmem + lane_off, one);  // every warpgroup writes the same constants (idempotent)
+    }
+    mbar_wait(bar_w, 0);
+
+    // hand the finished activation columns to the tensor core: hidden layer L = 1..nh-1 of head h
+    auto issue_layer = [&](int h, int L) {
+      tmem_st_wait();
+      tc_fence_before();
+      named_bar_sync(1 + wg, 128);
+      if (tid_wg == 0) {
+        tc_fence_after();
+        const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sW + h * wper + (L - 1) * kWBytes));
+#pragma unroll
+        for (int kc = 0; kc < kHid / 16; ++kc)  // K = 16 per instruction = 8 packed columns of A, +32 B of B
+          umma_f16_ts(d_tmem, a_tmem + 8 * kc, b_desc + 2 * kc, idesc_hidden, kc > 0 ? 1u : 0u);
+        umma_f16_ts(d_tmem, ones_tmem, umma_desc_k_sw128(smem_u32(sBB + h * wper + (L - 1) * kWBytes)), idesc_hidden, 1u);
+        umma_commit(bar_acc);
+      }
+    };
+
+    for (unsigned n = 0;; ++n) {
+      const unsigned t = (n * gridDim.x + blockIdx.x) * kTgWG + wg;
+      if (t >= ntiles) break;
+      const TgTile tg = tg_tile(p, t, tpp, tiles_per_head);
+      const TgHead& H = p.head[tg.head];
+      {
+        // ---- layer 0: the producer's summed table rows -> SiLU -> activation columns ------------------
+        mbar_wait_sleep(bar_full, par_t, (uint32_t)p.wait_ns);
+        par_t ^= 1u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // 4 chunks of 16 columns
+          uint32_t pk[8];
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 v = sSv[m * 16 + ((4 * c + g4) ^ (m & 7))];
+            pk[2 * g4 + 0] = pack_half2(silu_from_half_arg(v.x), silu_from_half_arg(v.y));
+            pk[2 * g4 + 1] = pack_half2(silu_from_half_arg(v.z), silu_from_half_arg(v.w));
+          }
+          tmem_st8(a_tmem + lane_off + 8 * c, pk);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty);
+        issue_layer(tg.head, 1);
+      }
+      for (int l = 1; l < nh; ++l) {
+        mbar_wait_sleep(bar_acc, par_acc, (uint32_t)p.wait_ns);
+        par_acc ^= 1u;
+        tc_fence_after();
+        const bool last = l == nh - 1;
+        const float* hwf = sHeadW + tg.head * (4 * kHid + 4);
+        const float4* hw = reinterpret_cast<const float4*>(hwf);
+        const bool wide = H.n_out > 1;  // warp-uniform
+        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+        uint32_t r[2][16];
+        tmem_ld16(d_tmem + lane_off, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < 4) tmem_ld16(d_tmem + lane_off + (c + 1) * 16, r[(c + 1) & 1]);
+          const uint32_t* rc = r[c & 1];
+          float h[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = silu_from_half_arg(__uint_as_float(rc[i]));
+          if (!last) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h[2 * i], h[2 * i + 1]);
+            tmem_st8(a_tmem + lane_off + 8 * c, pk);
+          } else {
+            // the head (network.py:176-178: last Linear of the head) as fp32 dot products on the activations in registers
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = hw[4 * c + i];
+              d0 = fmaf(h[4 * i + 0], w.x, d0);
+              d0 = fmaf(h[4 * i + 1], w.y, d0);
+              d0 = fmaf(h[4 * i + 2], w.z, d0);
+              d0 = fmaf(h[4 * i + 3], w.w, d0);
+            }
+            if (wide) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 w1 = hw[16 + 4 * c + i], w2 = hw[32 + 4 * c + i];
+                d1 = fmaf(h[4 * i + 0], w1.x, d1);
+                d1 = fmaf(h[4 * i + 1], w1.y, d1);
+                d1 = fmaf(h[4 * i + 2], w1.z, d1);
+                d1 = fmaf(h[4 * i + 3], w1.w, d1);
+                d2 = fmaf(h[4 * i + 0], w2.x, d2);
+                d2 = fmaf(h[4 * i + 1], w2.y, d2);
+                d2 = fmaf(h[4 * i + 2], w2.z, d2);
+                d2 = fmaf(h[4 * i + 3], w2.w, d2);
+              }
+            }
+          }
+        }
+        if (!last) {
+          issue_layer(tg.head, l + 1);
+        } else if (m < tg.nvalid) {
+          const long long row = (long long)tg.a * RP + tg.r0 + m;
+          const float* hb = hwf + 4 * kHid;
+          float o0 = d0 + hb[0];
+          if (H.exp_act) o0 = expf(__fadd_rn(o0, H.out_bias));
+          if (!wide) {
+            H.out[row] = o0;
+          } else {
+            float* o = H.out + row * H.n_out;
+            o[0] = o0;
+            o[1] = d1 + hb[1];
+            if (H.n_out > 2) o[2] = d2 + hb[2];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- tables
+struct TgTabParams {
+  const float* planes_cl;  // (3, H, W, 40) fp32 channels-last
+  int H, W, align_corners;
+  const float* axis_u[3];  // normalised coordinate in (-1, 1) of the lattice's slow / mid / fast index
+  int n[3];                // extents of the three lattice indices
+  int sdim[3];             // spatial dimension (0 x, 1 y, 2 z) each lattice index runs along
+  int nheads;
+  const float* w0_half[kTgMaxHeads];  // (64, 120) fp32 = W_0 / 2
+  const float* b0_half[kTgMaxHeads];  // (64) fp32 = b_0 / 2
+  float* tab[kTgMaxHeads][3];         // C (slow, mid), T1 (slow, fast), T2 (mid, fast): (n_p, n_q, 64) fp32
+};
+
+// blockIdx.y = head * 3 + pair.  One warp per table entry: lanes 0..39 interpolate one channel each (the reference's
+// grid_sample bilinear taps with zero padding, system.py:186-195), then every lane contracts the 40 channels with two rows of
+// W_0/2 (shared memory, transposed so that consecutive lanes read consecutive words).
+__global__ void __launch_bounds__(256) tetgrid_tables_kernel(TgTabParams p) {
+  __shared__ float sWt[kCp][kHid];
+  __shared__ float sF[8][kCp];
+  const int head = blockIdx.y / 3, pair = blockIdx.y - head * 3;
+  const int lp = pair == 2 ? 1 : 0, lq = pair == 0 ? 1 : 2;  // the pair's two lattice indices
+  const int dp = p.sdim[lp], dq = p.sdim[lq];
+  const int plane = dp + dq - 1;  // {x,y} -> 0, {x,z} -> 1, {y,z} -> 2 (system.py:181-184)
+  // the plane's first coordinate (grid_sample's x = width) is the lower spatial dimension
+  const bool p_is_u = dp < dq;
+  for (int i = threadIdx.x; i < kCp * kHid; i += blockDim.x) {
+    const int c = i / kHid, n = i - c * kHid;
+    sWt[c][n] = p.w0_half[head][n * kFeat + plane * kCp + c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int np = p.n[lp], nq = p.n[lq];
+  const long long nent = (long long)np * nq;
+  const float* P = p.planes_cl + (long long)plane * p.H * p.W * kCp;
+  float* out = p.tab[head][pair];
+  const float b0 = pair == 0 ? p.b0_half[head][lane] : 0.0f, b1 = pair == 0 ? p.b0_half[head][lane + 32] : 0.0f;
+  for (long long e = (long long)blockIdx.x * 8 + warp; e < nent; e += (long long)gridDim.x * 8) {
+    const int ip = (int)(e / nq), iq = (int)(e - (long long)ip * nq);
+    const float up = p.axis_u[lp][ip], uq = p.axis_u[lq][iq];
+    const Tap2 tu = make_tap(p_is_u ? up : uq, p.W, p.align_corners);
+    const Tap2 tv = make_tap(p_is_u ? uq : up, p.H, p.align_corners);
+    for (int c = lane; c < kCp; c += 32) {
+      const float v00 = P[((long long)tv.i0 * p.W + tu.i0) * kCp + c], v01 = P[((long long)tv.i0 * p.W + tu.i1) * kCp + c];
+      const float v10 = P[((long long)tv.i1 * p.W + tu.i0) * kCp + c], v11 = P[((long long)tv.i1 * p.W + tu.i1) * kCp + c];
+      sF[warp][c] = tv.w0 * (tu.w0 * v00 + tu.w1 * v01) + tv.w1 * (tu.w0 * v10 + tu.w1 * v11);
+    }
+    __syncwarp();
+    float a0 = b0, a1 = b1;
+#pragma unroll 8
+    for (int c = 0; c < kCp; ++c) {
+      const float f = sF[warp][c];
+      a0 = fmaf(sWt[c][lane], f, a0);
+      a1 = fmaf(sWt[c][lane + 32], f, a1);
+    }
+    out[e * kHid + lane] = a0;
+    out[e * kHid + lane + 32] = a1;
+    __syncwarp();
+  }
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+// See include/sculptmate_b200.h.
+extern "C" int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int align_corners, int nheads,
+                                    const void* const* decoder_blobs, const smb_decoder_layout* const* layouts, const int* n_out,
+                                    const int* exp_act, const float* out_bias, const float* const* axis_u, const int* extents,
+                                    const int* spatial_dim, float* const* outs, void* stream) {
+  if (!planes_cl || !decoder_blobs || !layouts || !n_out || !exp_act || !out_bias || !axis_u || !extents || !spatial_dim || !outs)
+    return SMB_ERR_BAD_ARG;
+  if (nheads < 1 || nheads > kTgMaxHeads || Hp < 1 || Wp < 1) return SMB_ERR_BAD_ARG;
+  int seen = 0;
+  for (int a = 0; a < 3; ++a) {
+    if (extents[a] < 1 || spatial_dim[a] < 0 || spatial_dim[a] > 2 || !axis_u[a]) return SMB_ERR_BAD_ARG;
+    seen |= 1 << spatial_dim[a];
+  }
+  if (seen != 7) return SMB_ERR_BAD_ARG;
+  const int nh = (int)layouts[0]->n_hidden;
+  for (int h = 0; h < nheads; ++h) {
+    if (!decoder_blobs[h] || !layouts[h] || !outs[h] || (int)layouts[h]->n_hidden != nh) return SMB_ERR_BAD_ARG;
+    if (n_out[h] < 1 || n_out[h] > 3) return SMB_ERR_BAD_ARG;
+  }
+  if (nh < 2 || nh > kMaxHidden) return SMB_ERR_BAD_ARG;
+  const long long nA = extents[0], nB = extents[1], nC = extents[2];
+  if (nB * nC >= (1LL << 30) || nC < 2) return SMB_ERR_BAD_ARG;
+  const long long tiles = (long long)nheads * nA * ((nB * nC + kTileM - 1) / kTileM);
+  if (tiles >= (1LL << 31) / kTgWG) return SMB_ERR_BAD_ARG;  // 32-bit tile arithmetic in the kernel
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  // scratch for the tables: stream-ordered (the pool keeps the block between calls, see lattice_api.cu)
+  keep_async_scratch(dev);
+  const size_t per_head = (size_t)(nA * nB + nA * nC + nB * nC) * kHid;
+  float* tabs = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&tabs), per_head * nheads * sizeof(float), st) != cudaSuccess) return SMB_ERR_CUDA;
+
+  TgTabParams tp{};
+  tp.planes_cl = planes_cl;
+  tp.H = Hp;
+  tp.W = Wp;
+  tp.align_corners = align_corners;
+  TgParams p{};
+  p.nheads = nheads;
+  p.n_hidden = nh;
+  p.nA = (int)nA;
+  p.nB = (int)nB;
+  p.nC = (int)nC;
+  p.wait_ns = 200;
+  for (int a = 0; a < 3; ++a) {
+    tp.axis_u[a] = axis_u[a];
+    tp.n[a] = extents[a];
+    tp.sdim[a] = spatial_dim[a];
+  }
+  tp.nheads = nheads;
+  for (int h = 0; h < nheads; ++h) {
+    const unsigned char* blob = static_cast<const unsigned char*>(decoder_blobs[h]);
+    const smb_decoder_layout* L = layouts[h];
+    tp.w0_half[h] = reinterpret_cast<const float*>(blob + L->off_w0_half);
+    tp.b0_half[h] = reinterpret_cast<const float*>(blob + L->off_bias_half);
+    float* base = tabs + per_head * h;
+    tp.tab[h][0] = base;
+    tp.tab[h][1] = base + (size_t)nA * nB * kHid;
+    tp.tab[h][2] = base + (size_t)(nA * nB + nA * nC) * kHid;
+    TgHead& H = p.head[h];
+    H.C = tp.tab[h][0];
+    H.T1 = tp.tab[h][1];
+    H.T2 = tp.tab[h][2];
+    H.tc_weights = blob + L->off_tc_hidden;
+    H.tc_biasblk = blob + L->off_tc_biasblk;
+    // plain fp32 copy of the parameters: [W0 (64x120) b0 (64)] [(W_l (64x64) b_l (64)) x (nh-1)] [W_L (4x64) b_L (4)]
+    H.head_w = reinterpret_cast<const float*>(blob + L->off_f32) + (kHid * kFeat + kHid) + (size_t)(nh - 1) * (kHid * kHid + kHid);
+    H.out = outs[h];
+    H.n_out = n_out[h];
+    H.exp_act = exp_act[h];
+    H.out_bias = out_bias[h];
+  }
+  {
+    const long long maxent = nA * nB > nA * nC ? (nA * nB > nB * nC ? nA * nB : nB * nC) : (nA * nC > nB * nC ? nA * nC : nB * nC);
+    long long bx = (maxent + 7) / 8;
+    if (bx > (long long)sms * 8) bx = (long long)sms * 8;
+    tetgrid_tables_kernel<<<dim3((unsigned)bx, (unsigned)(3 * nheads)), 256, 0, st>>>(tp);
+  }
+  const size_t smem = (size_t)2 * nheads * (nh - 1) * kWBytes + (size_t)kTgWG * kTgSBytes + 8 * (1 + 3 * kTgWG) + 16 + 16 +
+                      (size_t)nheads * (4 * kHid + 4) * 4;
+  int rc = SMB_OK;
+  if (smem > 227 * 1024) {
+    rc = SMB_ERR_BAD_ARG;
+  } else {
+    static const cudaError_t attr = cudaFuncSetAttribute(tetgrid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr != cudaSuccess) {
+      rc = SMB_ERR_CUDA;
+    } else {
+      long long grid = (tiles + kTgWG - 1) / kTgWG;
+      if (grid > sms) grid = sms;
+      tetgrid_tc_kernel<<<(unsigned)grid, kTgWG * 128 + 128, smem, st>>>(p);
+      rc = smb_check(cudaGetLastError());
+    }
+  }
+  cudaFreeAsync(tabs, st);
+  return rc;
+}

@@ -870,6 +870,57 @@ def get_sf3d_head_pack(decoder: torch.nn.Module, name: str, device: torch.device
     return hit
 
 
+def get_sf3d_head_decoder_pack(decoder: torch.nn.Module, name: str, device: torch.device) -> DecoderPack:
+    """One MaterialMLP head (network.py:158-178: 120 -> 64 x n_hidden -> k <= 3) in the NeRFMLP blob format of
+    ``pack_decoder_host`` (last Linear zero-padded to 4 rows) -- what the lattice tet-grid kernel reads."""
+    lin = [m for m in decoder.heads[name] if isinstance(m, torch.nn.Linear)]
+    if len(lin) < 3 or lin[0].in_features != 120 or any(m.out_features != 64 for m in lin[:-1]) or lin[-1].out_features > 3:
+        raise NotImplementedError(f"head {name!r}: the lattice path expects 120 -> 64 x (n >= 2) -> (<= 3 outputs), SiLU")
+    params = [q for m in lin for q in (m.weight, m.bias)]
+    key = _param_key(params, device)
+    hit = _mlp_tc_cache.get(("sf3d_head_decoder", name), decoder)
+    if hit is None or hit.key != key:
+        f = lambda t: t.detach().to("cpu", torch.float32)  # noqa: E731
+        k = lin[-1].out_features
+        w_last, b_last = torch.zeros(4, 64), torch.zeros(4)
+        w_last[:k] = f(lin[-1].weight)
+        b_last[:k] = f(lin[-1].bias)
+        blob, lay = pack_decoder_host([*[f(m.weight) for m in lin[:-1]], w_last], [*[f(m.bias) for m in lin[:-1]], b_last])
+        hit = _mlp_tc_cache.put(("sf3d_head_decoder", name), decoder, DecoderPack(blob=blob.to(device), layout=lay, key=key))
+    return hit
+
+
+def query_tetgrid_tc(
+    planes: ScenePlanes, packs: Sequence[DecoderPack], n_out: Sequence[int], exp_act: Sequence[bool], out_bias: Sequence[float],
+    axis_u: Sequence[torch.Tensor], spatial_dim: Sequence[int], align_corners: bool = True,
+) -> List[torch.Tensor]:
+    """Heads of a MaterialMLP at every vertex of a lattice-ordered grid (``smb_query_tetgrid_tc``): ``axis_u[k]`` is the
+    (-1,1) coordinate of lattice index k (slow, mid, fast), ``spatial_dim[k]`` the spatial axis it runs along.
+    Returns one (N, n_out[h]) tensor per head."""
+    if planes.planes_cl is None:
+        raise ValueError("the lattice tet-grid path reads the fp32 channels-last planes (prepare_planes_cl)")
+    dev = planes.planes_cl.device
+    nh = len(packs)
+    ax = [a.detach().to(device=dev, dtype=torch.float32).contiguous() for a in axis_u]
+    ext = [int(a.numel()) for a in ax]
+    n = ext[0] * ext[1] * ext[2]
+    outs = [torch.empty((n, int(k)), dtype=torch.float32, device=dev) for k in n_out]
+    vp, ip, fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    blobs = (vp * nh)(*[p.blob.data_ptr() for p in packs])
+    lays = (ctypes.POINTER(DecoderLayout) * nh)(*[ctypes.pointer(p.layout) for p in packs])
+    with torch.cuda.device(dev):
+        check(
+            _capi.load().smb_query_tetgrid_tc(
+                planes.planes_cl.data_ptr(), planes.Hp, planes.Wp, int(bool(align_corners)), nh, blobs, lays,
+                (ip * nh)(*[int(k) for k in n_out]), (ip * nh)(*[int(bool(e)) for e in exp_act]), (fp * nh)(*[float(b) for b in out_bias]),
+                (vp * 3)(*[a.data_ptr() for a in ax]), (ip * 3)(*ext), (ip * 3)(*[int(d) for d in spatial_dim]),
+                (vp * nh)(*[o.data_ptr() for o in outs]), _stream_ptr(dev),
+            ),
+            "smb_query_tetgrid_tc",
+        )
+    return outs
+
+
 def query_points_tc(
     planes: ScenePlanes, pack: MlpTcPack, positions: torch.Tensor, radius: float, out0_bias: float,
     align_corners: bool, sigmoid_vec: bool, want: Sequence[str] = ("out0_act",),

@@ -19,6 +19,53 @@ from ... import runtime
 from .mesh import Mesh
 
 
+def detect_lattice(vertices: np.ndarray):
+    """Is ``vertices`` (N,3) a lattice in index order -- vertices[(a*nB + b)*nC + c] = (coordinates picked from three
+    lists by a, b, c), for some assignment of the spatial axes to the slow / mid / fast index?  Returns
+    ``(extents, spatial_dim, coords)`` (coords[k]: float32 array of index k's coordinate values) or None.  The check is
+    exact (bit-for-bit) and costs one pass over the array; a Kuhn / marching-cubes-style tet grid passes, a quartet
+    (BCC) tetrahedralisation does not and keeps the arbitrary-position kernel."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    n = v.shape[0]
+    if v.ndim != 2 or v.shape[1] != 3 or n < 8:
+        return None
+    d1 = np.flatnonzero(v[1] != v[0])
+    if d1.size != 1:
+        return None
+    fast = int(d1[0])
+    same = np.flatnonzero(v[:, fast] == v[0, fast])  # the fast coordinate returns to its first value every nC vertices
+    if same.size < 2:
+        return None
+    nC = int(same[1])
+    if nC < 2 or n % nC or nC >= n:
+        return None
+    d2 = np.flatnonzero(v[nC] != v[0])
+    if d2.size != 1 or int(d2[0]) == fast:
+        return None
+    mid = int(d2[0])
+    slow = 3 - fast - mid
+    rows = v[::nC]
+    same = np.flatnonzero(rows[:, mid] == rows[0, mid])
+    if same.size < 2:
+        return None
+    nB = int(same[1])
+    if nB < 2 or (n // nC) % nB:
+        return None
+    nA = n // (nC * nB)
+    if nA < 2:
+        return None
+    g = v.reshape(nA, nB, nC, 3)
+    ca, cb, cc = g[:, 0, 0, slow].copy(), g[0, :, 0, mid].copy(), g[0, 0, :, fast].copy()
+    ok = (
+        np.array_equal(g[..., slow], np.broadcast_to(ca[:, None, None], (nA, nB, nC)))
+        and np.array_equal(g[..., mid], np.broadcast_to(cb[None, :, None], (nA, nB, nC)))
+        and np.array_equal(g[..., fast], np.broadcast_to(cc[None, None, :], (nA, nB, nC)))
+    )
+    if not ok:
+        return None
+    return (nA, nB, nC), (slow, mid, fast), (ca, cb, cc)
+
+
 class IsosurfaceHelper(nn.Module):
     points_range: Tuple[float, float] = (0, 1)
 
@@ -41,6 +88,9 @@ class MarchingTetrahedraHelper(IsosurfaceHelper):
         self.register_buffer("indices", torch.from_numpy(tets["indices"]).long(), persistent=False)
         self._all_edges: Optional[torch.Tensor] = None
         self._topology = None  # (device, edges int32 (E,2), tets int32 (T,4), tet_edges int32 (T,6))
+        # (extents of the slow / mid / fast vertex index, the spatial axis of each, their coordinate lists) when the vertex
+        # array is an outer product of three coordinate lists, else None
+        self.lattice = detect_lattice(tets["vertices"])
 
     def normalize_grid_deformation(self, grid_vertex_offsets: torch.Tensor) -> torch.Tensor:
         """isosurface.py:106-113 (eager form, kept for callers outside the fused path)."""

@@ -39,6 +39,7 @@ class SF3D(BaseModule):
         radius: float = 0.87
         tets_path: str = ""
         precision: str = "tc"  # "tc": tcgen05 kernel (fp16 operands); "fp32": CUDA-core kernel at reference precision
+        lattice_path: bool = True  # take the table-based kernel when the tet grid's vertices form a lattice (precision "tc")
         decoder: dict = field(default_factory=lambda: dict(DEFAULT_DECODER_CFG))
 
     cfg: Config
@@ -49,6 +50,7 @@ class SF3D(BaseModule):
         self.register_buffer("bbox", torch.as_tensor([[-r, -r, -r], [r, r, r]], dtype=torch.float32))
         self.isosurface_helper = MarchingTetrahedraHelper(self.cfg.isosurface_resolution, self.cfg.tets_path)
         self._grid_positions = None
+        self._lattice_axes = None
 
     # ------------------------------------------------------------------ API
     def query_triplane(self, positions: torch.Tensor, triplanes: torch.Tensor) -> torch.Tensor:
@@ -101,6 +103,22 @@ class SF3D(BaseModule):
             self._grid_positions = scale_tensor(h.grid_vertices.to(device), h.points_range, self.bbox.to(device)).contiguous()
         return self._grid_positions
 
+    def _lattice_axis_u(self, device: torch.device):
+        """Per-index coordinate lists of a lattice-ordered grid, taken through the same two ``scale_tensor`` calls as every
+        vertex (grid -> bbox :147-151, then (-radius, radius) -> (-1, 1) :175-177): elementwise ops, so the values are
+        bit-identical to what the per-vertex path feeds grid_sample."""
+        if self._lattice_axes is None or self._lattice_axes[0] != device:
+            h = self.isosurface_helper
+            _, sdim, coords = h.lattice
+            bbox = self.bbox.to(device)
+            axes = []
+            for k in range(3):
+                c = torch.from_numpy(coords[k]).to(device)
+                pos = scale_tensor(c, h.points_range, (bbox[0, sdim[k]], bbox[1, sdim[k]]))
+                axes.append(scale_tensor(pos, (-self.cfg.radius, self.cfg.radius), (-1, 1)).contiguous())
+            self._lattice_axes = (device, axes)
+        return self._lattice_axes[1]
+
     def triplane_to_meshes(self, triplanes: torch.Tensor) -> List[Mesh]:
         meshes = []
         h = self.isosurface_helper
@@ -110,10 +128,23 @@ class SF3D(BaseModule):
             grid_vertices = self._positions(dev)  # scale_tensor(grid, points_range, bbox)   :147-151
             if self.decoder.cuda_heads_supported():
                 tc = self.cfg.precision == "tc"
-                planes = runtime.prepare_planes_half(triplane) if tc else runtime.prepare_planes_cl(triplane)
+                lattice = tc and h.lattice is not None and self.cfg.lattice_path
+                planes = None if lattice else (runtime.prepare_planes_half(triplane) if tc else runtime.prepare_planes_cl(triplane))
                 dens_spec = self.decoder.head_spec("density")
                 # query_triplane + decoder(include=[vertex_offset, density]) fused into one kernel  :153-154
-                if tc:
+                if tc and h.lattice is not None and self.cfg.lattice_path:
+                    # lattice-ordered grid: layer 0 from three n^2 tables instead of n^3 plane gathers (csrc/tetgrid_tc.cu)
+                    offs = self.decoder.head_spec("vertex_offset")
+                    density, deform = runtime.query_tetgrid_tc(
+                        runtime.prepare_planes_cl(triplane),
+                        [runtime.get_sf3d_head_decoder_pack(self.decoder, "density", dev),
+                         runtime.get_sf3d_head_decoder_pack(self.decoder, "vertex_offset", dev)],
+                        n_out=(1, 3), exp_act=(True, False), out_bias=(float(dens_spec.out_bias), 0.0),
+                        axis_u=self._lattice_axis_u(dev), spatial_dim=h.lattice[1], align_corners=True,
+                    )
+                    if float(offs.out_bias) != 0.0:
+                        deform = deform + float(offs.out_bias)
+                elif tc:
                     dec = runtime.query_points_tc(
                         planes, runtime.get_sf3d_points_pack(self.decoder, dev), grid_vertices, self.cfg.radius,
                         float(dens_spec.out_bias), align_corners=True, sigmoid_vec=False, want=("out0_act", "vec"),

@@ -190,3 +190,54 @@ def test_texel_query_heads_on_tensor_cores(tets_dir):
     assert np.abs(d.cpu().numpy() / r_d - 1).max() < 5e-3
     with pytest.raises(ValueError):
         m.query_and_decode(pos, tp, include=["density"], exclude=["features"])
+
+
+def test_lattice_tetgrid_query_vs_reference_and_fp32(golden, tets_dir):
+    """The table-based lattice kernel (csrc/tetgrid_tc.cu: layer 0 = C[a][b] + T1[a][c] + T2[b][c] in fp32, hidden layer on
+    tcgen05) against the unmodified reference's density / vertex_offset at the grid vertices (golden) and against the fp32
+    CUDA-core kernel; then on a grid whose vertex order runs x fastest (axes permuted), against the fp32 kernel."""
+    from sculptmate_b200 import runtime
+    from sculptmate_b200.sf3d.models.isosurface import detect_lattice
+    from sculptmate_b200.tsr.utils import scale_tensor
+
+    g = golden("sf3d_path.npz")
+    n = int(g["n"])
+    m = _model(g, tets_dir, n, float(g["threshold"]), precision="tc")
+    dev = torch.device("cuda")
+    assert m.isosurface_helper.lattice is not None and m.isosurface_helper.lattice[0] == (n + 1, n + 1, n + 1)
+    tp = torch.from_numpy(g["triplane"]).cuda()
+    planes = runtime.prepare_planes_cl(tp)
+    packs = [runtime.get_sf3d_head_decoder_pack(m.decoder, "density", dev), runtime.get_sf3d_head_decoder_pack(m.decoder, "vertex_offset", dev)]
+    dens, off = runtime.query_tetgrid_tc(planes, packs, (1, 3), (True, False), (-1.0, 0.0), m._lattice_axis_u(dev), m.isosurface_helper.lattice[1])
+    torch.cuda.synchronize()
+    # the reference's level at every grid vertex (density - threshold, system.py:155) and the deformed grid it produced
+    ref_density = g["grid_level"].reshape(-1) + np.float32(g["threshold"])
+    e_d = np.abs(dens.cpu().numpy().ravel() / ref_density - 1).max()
+    ref_off = np.arctanh(np.clip((g["grid_vertices"] - kuhn_tet_grid(n)[0]) * n, -0.999999, 0.999999))  # isosurface.py:106-113 inverted
+    e_o = np.abs(np.tanh(off.cpu().numpy()) - np.tanh(ref_off)).max()
+    print(f"lattice tet-grid kernel vs reference: density rel {e_d:.2e}, tanh(vertex_offset) abs {e_o:.2e}")
+    assert e_d < 1e-2 and e_o < 1e-2  # fp16 operands in the hidden layer only (the points kernel: 2e-2)
+    pos = m._positions(dev)
+    r = runtime.sf3d_query(planes, runtime.get_sf3d_heads(m.decoder, dev), -1.0, RADIUS, positions=pos, want=("density_act", "vertex_offset"))
+    e_d32 = np.abs(dens.cpu().numpy().ravel() / r["density_act"].cpu().numpy().ravel() - 1).max()
+    e_o32 = np.abs(off.cpu().numpy() - r["vertex_offset"].cpu().numpy()).max()
+    print(f"lattice tet-grid kernel vs fp32 kernel: density rel {e_d32:.2e}, vertex_offset abs {e_o32:.2e}")
+    assert e_d32 < 1e-2 and e_o32 < 1e-2
+
+    # a lattice stored with x running fastest and different extents per axis
+    ax = [np.linspace(0, 1, k, dtype=np.float32) for k in (7, 12, 9)]  # x, y, z coordinate lists
+    zz, yy, xx = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")  # index order: z slow, y mid, x fast
+    verts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=-1).astype(np.float32)
+    lat = detect_lattice(verts)
+    assert lat is not None and lat[0] == (9, 12, 7) and lat[1] == (2, 1, 0)
+    bbox = m.bbox.to(dev)
+    axis_u = []
+    for k in range(3):
+        c = torch.from_numpy(lat[2][k]).to(dev)
+        p_ = scale_tensor(c, (0, 1), (bbox[0, lat[1][k]], bbox[1, lat[1][k]]))
+        axis_u.append(scale_tensor(p_, (-RADIUS, RADIUS), (-1, 1)))
+    dens2, off2 = runtime.query_tetgrid_tc(planes, packs, (1, 3), (True, False), (-1.0, 0.0), axis_u, lat[1])
+    pos2 = scale_tensor(torch.from_numpy(verts).to(dev), (0, 1), bbox).contiguous()
+    r2 = runtime.sf3d_query(planes, runtime.get_sf3d_heads(m.decoder, dev), -1.0, RADIUS, positions=pos2, want=("density_act", "vertex_offset"))
+    assert np.abs(dens2.cpu().numpy().ravel() / r2["density_act"].cpu().numpy().ravel() - 1).max() < 1e-2
+    assert np.abs(off2.cpu().numpy() - r2["vertex_offset"].cpu().numpy()).max() < 1e-2
