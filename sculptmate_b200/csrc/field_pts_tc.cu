@@ -284,22 +284,28 @@ extern "C" int smb_mlp_tc_pack_host(const float* const* W, const float* const* B
   return SMB_OK;
 }
 
-// NCHW fp32 (3,Cp,H,W) -> channels-last fp16 (3,H,W,Cp)
-__global__ void planes_to_channels_last_half(const float* __restrict__ src, __half* __restrict__ dst, int H, int W) {
-  const int HW = H * W;
-  const long long total = 3LL * HW * smb::kCp;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(t % smb::kCp);
-    const long long r = t / smb::kCp;
-    const int hw = (int)(r % HW);
-    const int pl = (int)(r / HW);
-    dst[t] = __float2half_rn(src[((long long)pl * smb::kCp + c) * HW + hw]);
+// NCHW fp32 (3,Cp,H,W) -> channels-last fp16 (3,H,W,Cp); tiled through shared memory like planes_to_channels_last (field_f32.cu)
+constexpr int kClhTexels = 128;
+__global__ void __launch_bounds__(256) planes_to_channels_last_half(const float* __restrict__ src, __half* __restrict__ dst, int H, int W) {
+  __shared__ float s[smb::kCp][kClhTexels + 1];
+  const int p = blockIdx.y, HW = H * W, hw0 = blockIdx.x * kClhTexels;
+  const int nt = min(kClhTexels, HW - hw0);
+  for (int t = threadIdx.x; t < smb::kCp * kClhTexels; t += blockDim.x) {
+    const int c = t / kClhTexels, x = t - c * kClhTexels;
+    if (x < nt) s[c][x] = __ldg(src + ((long long)p * smb::kCp + c) * HW + hw0 + x);
+  }
+  __syncthreads();
+  __half2* o = reinterpret_cast<__half2*>(dst + ((long long)p * HW + hw0) * smb::kCp);  // Cp is even: pairs never straddle a texel
+  for (int t = threadIdx.x; t < nt * (smb::kCp / 2); t += blockDim.x) {
+    const int x = t / (smb::kCp / 2), c = 2 * (t - x * (smb::kCp / 2));
+    o[t] = __floats2half2_rn(s[c][x], s[c + 1][x]);
   }
 }
 
 extern "C" int smb_scene_prepare_half(const float* triplane, int Hp, int Wp, void* planes_cl_half, void* stream) {
   if (!triplane || !planes_cl_half || Hp <= 0 || Wp <= 0) return SMB_ERR_BAD_ARG;
-  planes_to_channels_last_half<<<1184, 256, 0, (cudaStream_t)stream>>>(triplane, static_cast<__half*>(planes_cl_half), Hp, Wp);
+  planes_to_channels_last_half<<<dim3((Hp * Wp + kClhTexels - 1) / kClhTexels, 3), 256, 0, (cudaStream_t)stream>>>(
+      triplane, static_cast<__half*>(planes_cl_half), Hp, Wp);
   return smb_check(cudaGetLastError());
 }
 

@@ -26,12 +26,18 @@ namespace smb {
 
 constexpr int kTgWG = 4;         // consumer warpgroups (4 x 96 + 8 = 392 TMEM columns); 4 producer warps, 640 threads
 constexpr int kTgMaxHeads = 2;
-constexpr int kTgSBytes = kTileM * kHid * 4;  // 32 KB: layer-0 pre-activations (already halved) of one tile, fp32
+// A tile = a 4 x 4 x 8 block (slow x mid x fast index) of the lattice = 128 samples that need only 32 + 32 + 16 DISTINCT table
+// rows (20 KB) -- 0.6 rows per sample instead of 2: the tables come from L2, and two rows per sample made the kernel
+// L2-latency-bound (780 us: the consumers spent half their instructions waiting for the producers).
+constexpr int kTgA = 4, kTgB = 4, kTgC = 8;
+constexpr int kTgRow = kHid * 4;                                          // 256 B: one table row
+constexpr int kTgStageBytes = (kTgA * kTgC + kTgB * kTgC + kTgA * kTgB) * kTgRow;  // T1 | T2 | C = 20 KB
+constexpr int kTgStages = 2;                                              // per warpgroup
 
 struct TgHead {
   const float* C;   // [nA][nB][64]  (b0/2 folded in)
-  const float* T1;  // [nA][nC][64]
-  const float* T2;  // [nB][nC][64]
+  const float* T1;  // [nA][nC][64]  16-byte chunks of a row stored at chunk ^ (c & 7)
+  const float* T2;  // [nB][nC][64]  same
   const unsigned char* tc_weights;  // (n_hidden-1) x 8 KB fp16 UMMA images of W_l/2
   const unsigned char* tc_biasblk;  // (n_hidden-1) x 8 KB bias K-blocks
   const float* head_w;              // last Linear, (4,64) fp32 row-major (rows >= n_out unused), then its bias (4)
@@ -48,15 +54,18 @@ struct TgParams {
 };
 
 struct TgTile {
-  int head, a, r0, nvalid;
+  int head, a0, b0, c0;
 };
-__device__ __forceinline__ TgTile tg_tile(const TgParams& p, unsigned t, unsigned tpp, unsigned tiles_per_head) {
+__device__ __forceinline__ TgTile tg_tile(unsigned t, unsigned ntb, unsigned ntc, unsigned tiles_per_head) {
   TgTile g;
   g.head = (int)(t / tiles_per_head);
-  const unsigned rem = t - (unsigned)g.head * tiles_per_head;
-  g.a = (int)(rem / tpp);
-  g.r0 = (int)(rem - (unsigned)g.a * tpp) * kTileM;
-  g.nvalid = min(kTileM, p.nB * p.nC - g.r0);
+  unsigned rem = t - (unsigned)g.head * tiles_per_head;
+  const unsigned ta = rem / (ntb * ntc);
+  rem -= ta * ntb * ntc;
+  const unsigned tb = rem / ntc;
+  g.a0 = (int)ta * kTgA;
+  g.b0 = (int)tb * kTgB;
+  g.c0 = (int)(rem - tb * ntc) * kTgC;
   return g;
 }
 
@@ -66,10 +75,10 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
   const int wper = (nh - 1) * kWBytes;  // per head: hidden images, and as much again for the bias K-blocks
   unsigned char* sW = smem;                              // [head][l-1]
   unsigned char* sBB = sW + p.nheads * wper;             // [head][l-1]
-  unsigned char* sS = sBB + p.nheads * wper;             // [wg] 32 KB tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + kTgWG * kTgSBytes);
-  // bars[0] = weights; per warpgroup g: [1+3g] s_full, [2+3g] s_empty, [3+3g] acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * kTgWG);
+  unsigned char* sS = sBB + p.nheads * wper;             // [wg][stage] 20 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + kTgWG * kTgStages * kTgStageBytes);
+  // bars[0] = weights; per warpgroup g: [1+5g+s] full[s], [3+5g+s] empty[s], [5+5g] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 5 * kTgWG);
   float* sHeadW = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // [head][4*64 + 4]
 
   const int tid_cta = threadIdx.x;
@@ -79,9 +88,11 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
   if (tid_cta == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     for (int g = 0; g < kTgWG; ++g) {
-      mbar_init(smem_u32(&bars[1 + 3 * g]), 1);  // s_full: elected producer lane
-      mbar_init(smem_u32(&bars[2 + 3 * g]), 4);  // s_empty: one elected lane per consumer warp
-      mbar_init(smem_u32(&bars[3 + 3 * g]), 1);  // acc_full: tcgen05.commit
+      for (int st = 0; st < kTgStages; ++st) {
+        mbar_init(smem_u32(&bars[1 + 5 * g + st]), 1);  // full: the producer's expect_tx arrival + the copies' bytes
+        mbar_init(smem_u32(&bars[3 + 5 * g + st]), 4);  // empty: one elected lane per consumer warp
+      }
+      mbar_init(smem_u32(&bars[5 + 5 * g]), 1);  // acc_full: tcgen05.commit
     }
     mbar_fence_init();
   }
@@ -104,80 +115,60 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
       }
   }
 
-  const int RP = p.nB * p.nC;                       // rows of one lattice plane
-  const unsigned tpp = (unsigned)((RP + kTileM - 1) / kTileM);
-  const unsigned tiles_per_head = (unsigned)p.nA * tpp;
+  const unsigned nta = (unsigned)((p.nA + kTgA - 1) / kTgA), ntb = (unsigned)((p.nB + kTgB - 1) / kTgB);
+  const unsigned ntc = (unsigned)((p.nC + kTgC - 1) / kTgC);
+  const unsigned tiles_per_head = nta * ntb * ntc;
   const unsigned ntiles = tiles_per_head * (unsigned)p.nheads;
 
   if (wid >= kTgWG * 4) {
     // =================================================================== producer: one warp per warpgroup
+    // Lanes 0..11 each issue one bulk copy per tile: the fast-index runs T1[a0+l][c0..], T2[b0+l][c0..] (contiguous rows,
+    // <= 2 KB) and C[a0+l][b0..] (<= 1 KB) straight into the stage; indices behind the lattice's end are clamped (their
+    // samples are never stored).  No registers, no per-thread load latency: the copies of two tiles are in flight.
     const int g = wid - kTgWG * 4;
-    float4* dst = reinterpret_cast<float4*>(sS + g * kTgSBytes);
-    const uint32_t bar_full = smem_u32(&bars[1 + 3 * g]), bar_empty = smem_u32(&bars[2 + 3 * g]);
-    uint32_t par_empty = 1;  // a fresh barrier passes a wait on parity 1
-    const int half = lane >> 4, chunk = lane & 15;
-    for (unsigned n = 0;; ++n) {
+    uint32_t par_empty = 3;  // bit s: parity to wait on; a fresh barrier passes a wait on parity 1
+    unsigned k = 0;
+    for (unsigned n = 0;; ++n, ++k) {
       const unsigned t = (n * gridDim.x + blockIdx.x) * kTgWG + g;
       if (t >= ntiles) break;
-      const TgTile tg = tg_tile(p, t, tpp, tiles_per_head);
+      const int st = (int)(k & 1u);
+      const TgTile tg = tg_tile(t, ntb, ntc, tiles_per_head);
       const TgHead& H = p.head[tg.head];
-      const float4* T2 = reinterpret_cast<const float4*>(H.T2);
-      const float4* T1 = reinterpret_cast<const float4*>(H.T1) + (long long)tg.a * p.nC * 16;
-      const float4* Cc = reinterpret_cast<const float4*>(H.C) + (long long)tg.a * p.nB * 16;
-      // this lane's rows: half, half + 2, ... ; (b, c) advance by two rows per step
-      int r = min(tg.r0 + half, RP - 1);
-      int b = r / p.nC, c = r - b * p.nC;
-      mbar_wait_sleep(bar_empty, par_empty, 20000u);
-      par_empty ^= 1u;
-      constexpr int kU = 4;
-#pragma unroll 1
-      for (int it = 0; it < kTileM / 2; it += kU) {
-        float4 v1[kU], v2[kU], vc[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          v2[u] = __ldg(T2 + (long long)(b * p.nC + c) * 16 + chunk);
-          v1[u] = __ldg(T1 + c * 16 + chunk);
-          vc[u] = __ldg(Cc + b * 16 + chunk);
-          // two rows on; rows behind the plane's end repeat the last one (never read back)
-          c += 2;
-          if (c >= p.nC) {
-            c -= p.nC;
-            ++b;
-          }
-          if (b >= p.nB) {
-            b = p.nB - 1;
-            c = p.nC - 1;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int row = 2 * (it + u) + half;
-          float4 s;
-          s.x = v1[u].x + v2[u].x + vc[u].x;
-          s.y = v1[u].y + v2[u].y + vc[u].y;
-          s.z = v1[u].z + v2[u].z + vc[u].z;
-          s.w = v1[u].w + v2[u].w + vc[u].w;
-          dst[row * 16 + (chunk ^ (row & 7))] = s;
-        }
-      }
+      const uint32_t bar_full = smem_u32(&bars[1 + 5 * g + st]);
+      mbar_wait_sleep(smem_u32(&bars[3 + 5 * g + st]), (par_empty >> st) & 1u, 20000u);
+      par_empty ^= 1u << st;
+      const int ncr = min(kTgC, p.nC - tg.c0), nbr = min(kTgB, p.nB - tg.b0);
+      const uint32_t bytes = (uint32_t)((kTgA + kTgB) * ncr + kTgA * nbr) * kTgRow;
+      unsigned char* stage = sS + (g * kTgStages + st) * kTgStageBytes;
+      if (lane == 0) mbar_expect_tx(bar_full, bytes);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full);
+      if (lane < kTgA) {
+        const int a = min(tg.a0 + lane, p.nA - 1);
+        bulk_g2s(smem_u32(stage + lane * kTgC * kTgRow), H.T1 + ((long long)a * p.nC + tg.c0) * kHid, (uint32_t)(ncr * kTgRow), bar_full);
+      } else if (lane < kTgA + kTgB) {
+        const int l = lane - kTgA, b = min(tg.b0 + l, p.nB - 1);
+        bulk_g2s(smem_u32(stage + (kTgA + l) * kTgC * kTgRow), H.T2 + ((long long)b * p.nC + tg.c0) * kHid, (uint32_t)(ncr * kTgRow), bar_full);
+      } else if (lane < 2 * kTgA + kTgB) {
+        const int l = lane - kTgA - kTgB, a = min(tg.a0 + l, p.nA - 1);
+        bulk_g2s(smem_u32(stage + ((kTgA + kTgB) * kTgC + l * kTgB) * kTgRow), H.C + ((long long)a * p.nB + tg.b0) * kHid,
+                 (uint32_t)(nbr * kTgRow), bar_full);
+      }
     }
   } else {
     // =================================================================== consumer
     const int wg = wid >> 2;
     const int q = wid & 3;
     const int m = (q << 5) | lane;
+    const int la = m >> 5, lb = (m >> 3) & 3, lc = m & 7;  // the sample's place in the tile's 4 x 4 x 8 block
     const int tid_wg = tid_cta & 127;
-    const float4* sSv = reinterpret_cast<const float4*>(sS + wg * kTgSBytes);
     const uint32_t d_tmem = tmem_base + (uint32_t)(wg * 96);
     const uint32_t a_tmem = d_tmem + 64;
     const uint32_t ones_tmem = tmem_base + (uint32_t)(kTgWG * 96);
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t idesc_hidden = umma_idesc_f16_f32(128, 64);
-    const uint32_t bar_acc = smem_u32(&bars[3 + 3 * wg]);
-    const uint32_t bar_full = smem_u32(&bars[1 + 3 * wg]), bar_empty = smem_u32(&bars[2 + 3 * wg]);
-    uint32_t par_t = 0, par_acc = 0;
+    const uint32_t bar_acc = smem_u32(&bars[5 + 5 * wg]);
+    uint32_t par_full = 0, par_acc = 0;
+    unsigned k = 0;
 
     {  // constant activation block of the bias MMA: k = 64, 65 -> 1.0 (bias hi, lo rows), k = 66..79 -> 0
       const uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -201,28 +192,34 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
       }
     };
 
-    for (unsigned n = 0;; ++n) {
+    for (unsigned n = 0;; ++n, ++k) {
       const unsigned t = (n * gridDim.x + blockIdx.x) * kTgWG + wg;
       if (t >= ntiles) break;
-      const TgTile tg = tg_tile(p, t, tpp, tiles_per_head);
+      const int st = (int)(k & 1u);
+      const TgTile tg = tg_tile(t, ntb, ntc, tiles_per_head);
       const TgHead& H = p.head[tg.head];
       {
-        // ---- layer 0: the producer's summed table rows -> SiLU -> activation columns ------------------
-        mbar_wait_sleep(bar_full, par_t, (uint32_t)p.wait_ns);
-        par_t ^= 1u;
+        // ---- layer 0: C[a][b] + T1[a][c] + T2[b][c] from the stage -> SiLU -> activation columns ------------------
+        const unsigned char* stage = sS + (wg * kTgStages + st) * kTgStageBytes;
+        const float4* t1 = reinterpret_cast<const float4*>(stage + (la * kTgC + lc) * kTgRow);
+        const float4* t2 = reinterpret_cast<const float4*>(stage + ((kTgA + lb) * kTgC + lc) * kTgRow);
+        const float4* cc = reinterpret_cast<const float4*>(stage + ((kTgA + kTgB) * kTgC + la * kTgB + lb) * kTgRow);
+        mbar_wait_sleep(smem_u32(&bars[1 + 5 * wg + st]), (par_full >> st) & 1u, (uint32_t)p.wait_ns);
+        par_full ^= 1u << st;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {  // 4 chunks of 16 columns
           uint32_t pk[8];
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
-            const float4 v = sSv[m * 16 + ((4 * c + g4) ^ (m & 7))];
-            pk[2 * g4 + 0] = pack_half2(silu_from_half_arg(v.x), silu_from_half_arg(v.y));
-            pk[2 * g4 + 1] = pack_half2(silu_from_half_arg(v.z), silu_from_half_arg(v.w));
+            const int ch = 4 * c + g4;
+            const float4 x = t1[ch ^ lc], y = t2[ch ^ lc], z = cc[ch];  // rows of the fast index are stored chunk-swizzled
+            pk[2 * g4 + 0] = pack_half2(silu_from_half_arg(x.x + y.x + z.x), silu_from_half_arg(x.y + y.y + z.y));
+            pk[2 * g4 + 1] = pack_half2(silu_from_half_arg(x.z + y.z + z.z), silu_from_half_arg(x.w + y.w + z.w));
           }
           tmem_st8(a_tmem + lane_off + 8 * c, pk);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty);
+        if (lane == 0) mbar_arrive(smem_u32(&bars[3 + 5 * wg + st]));
         issue_layer(tg.head, 1);
       }
       for (int l = 1; l < nh; ++l) {
@@ -277,8 +274,8 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
         }
         if (!last) {
           issue_layer(tg.head, l + 1);
-        } else if (m < tg.nvalid) {
-          const long long row = (long long)tg.a * RP + tg.r0 + m;
+        } else if (tg.a0 + la < p.nA && tg.b0 + lb < p.nB && tg.c0 + lc < p.nC) {
+          const long long row = ((long long)(tg.a0 + la) * p.nB + tg.b0 + lb) * p.nC + tg.c0 + lc;
           const float* hb = hwf + 4 * kHid;
           float o0 = d0 + hb[0];
           if (H.exp_act) o0 = expf(__fadd_rn(o0, H.out_bias));
@@ -354,8 +351,11 @@ __global__ void __launch_bounds__(256) tetgrid_tables_kernel(TgTabParams p) {
       a0 = fmaf(sWt[c][lane], f, a0);
       a1 = fmaf(sWt[c][lane + 32], f, a1);
     }
-    out[e * kHid + lane] = a0;
-    out[e * kHid + lane + 32] = a1;
+    // rows indexed by the fast lattice index (T1, T2) are stored with their 16-byte chunks at chunk ^ (c & 7): the kernel
+    // above bulk-copies 8 consecutive rows into shared memory and reads them one row per thread
+    const int sw = pair == 0 ? 0 : ((iq & 7) << 2);
+    out[e * kHid + (lane ^ sw)] = a0;
+    out[e * kHid + ((lane + 32) ^ sw)] = a1;
     __syncwarp();
   }
 }
@@ -386,7 +386,7 @@ extern "C" int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int 
   if (nh < 2 || nh > kMaxHidden) return SMB_ERR_BAD_ARG;
   const long long nA = extents[0], nB = extents[1], nC = extents[2];
   if (nB * nC >= (1LL << 30) || nC < 2) return SMB_ERR_BAD_ARG;
-  const long long tiles = (long long)nheads * nA * ((nB * nC + kTileM - 1) / kTileM);
+  const long long tiles = (long long)nheads * ((nA + kTgA - 1) / kTgA) * ((nB + kTgB - 1) / kTgB) * ((nC + kTgC - 1) / kTgC);
   if (tiles >= (1LL << 31) / kTgWG) return SMB_ERR_BAD_ARG;  // 32-bit tile arithmetic in the kernel
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
@@ -445,7 +445,7 @@ extern "C" int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int 
     if (bx > (long long)sms * 8) bx = (long long)sms * 8;
     tetgrid_tables_kernel<<<dim3((unsigned)bx, (unsigned)(3 * nheads)), 256, 0, st>>>(tp);
   }
-  const size_t smem = (size_t)2 * nheads * (nh - 1) * kWBytes + (size_t)kTgWG * kTgSBytes + 8 * (1 + 3 * kTgWG) + 16 + 16 +
+  const size_t smem = (size_t)2 * nheads * (nh - 1) * kWBytes + (size_t)kTgWG * kTgStages * kTgStageBytes + 8 * (1 + 5 * kTgWG) + 16 + 16 +
                       (size_t)nheads * (4 * kHid + 4) * 4;
   int rc = SMB_OK;
   if (smem > 227 * 1024) {
