@@ -368,6 +368,12 @@ int smb_mtet_count(const float* sdf, const int32_t* edges, int64_t n_edges, cons
 int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges,
                   const int32_t* tet_edges, int64_t n_tets, const void* workspace, float* verts, int64_t* faces,
                   void* stream);
+/* smb_mtet_emit with the caller's scale_tensor(v_pos, points_range, bbox) (sf3d/system.py:162-164) applied to every
+ * vertex in the same fp32 operation order: v = ((v - affine8[0]) / affine8[1]) * affine8[2+c] + affine8[5+c]
+ * (affine8: host array {in_lo, in_hi - in_lo, (bbox_hi - bbox_lo)[3], bbox_lo[3]}). */
+int smb_mtet_emit_affine(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges,
+                         const int32_t* tet_edges, int64_t n_tets, const void* workspace, float* verts, int64_t* faces,
+                         const float* affine8, void* stream);
 int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t n_vertices, float* out, void* stream);
 
 /* SF3D.query_triplane + decoder(include=[...]) (sf3d/system.py:153-154, 170-198; sf3d/models/network.py:148-208) at the

@@ -175,6 +175,7 @@ SIGNATURES = {
     "smb_mtet_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "smb_mtet_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "smb_mtet_emit": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "smb_mtet_emit_affine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "smb_mtet_deform": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p]),
 }
 

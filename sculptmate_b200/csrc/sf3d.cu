@@ -339,10 +339,14 @@ __global__ void __launch_bounds__(1024) mtet_totals(uint32_t* echunk, long long 
   }
 }
 
+struct MtetAffine {
+  int on;
+  float sub, div, mul[3], add[3];
+};
 // K4: vertices on crossing edges (isosurface.py:170-178, fp32 operation order kept)
 __global__ void __launch_bounds__(256) mtet_emit_verts(const float* __restrict__ pos, const float* __restrict__ sdf,
                                                        const int2* __restrict__ edges, long long ne, const uint32_t* __restrict__ evid,
-                                                       const uint32_t* __restrict__ echunk, float* __restrict__ verts) {
+                                                       const uint32_t* __restrict__ echunk, float* __restrict__ verts, MtetAffine af) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
     const uint32_t r = __ldg(evid + e);
     if (!(r >> 31)) continue;
@@ -356,7 +360,10 @@ __global__ void __launch_bounds__(256) mtet_emit_verts(const float* __restrict__
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float p0 = __ldg(pos + 3LL * ab.x + c), p1 = __ldg(pos + 3LL * ab.y + c);
-      verts[3 * vid + c] = __fadd_rn(__fmul_rn(p0, w0), __fmul_rn(p1, w1));  // (edges * w).sum(1)
+      float v = __fadd_rn(__fmul_rn(p0, w0), __fmul_rn(p1, w1));  // (edges * w).sum(1)
+      // scale_tensor(v_pos, points_range, bbox) of the caller (sf3d/system.py:162-164, utils.py:222-231), same fp32 ops
+      if (af.on) v = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v, af.sub), af.div), af.mul[c]), af.add[c]);
+      verts[3 * vid + c] = v;
     }
   }
 }
@@ -473,9 +480,8 @@ extern "C" int smb_mtet_count(const float* sdf, const int32_t* edges, int64_t n_
   return smb_check(cudaGetLastError());
 }
 
-extern "C" int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges,
-                             const int32_t* tet_edges, int64_t n_tets, const void* workspace, float* verts, int64_t* faces,
-                             void* stream) {
+static int mtet_emit_impl(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges, const int32_t* tet_edges,
+                          int64_t n_tets, const void* workspace, float* verts, int64_t* faces, const MtetAffine& af, void* stream) {
   if (!positions || !sdf || !edges || !tet_edges || !workspace || n_edges <= 0 || n_tets <= 0) return SMB_ERR_BAD_ARG;
   MtetWs w = mtet_carve(const_cast<void*>(workspace), n_edges, n_tets);
   cudaStream_t st = (cudaStream_t)stream;
@@ -484,11 +490,33 @@ extern "C" int smb_mtet_emit(const float* positions, const float* sdf, const int
   if (be > cap) be = cap;
   if (bt > cap) bt = cap;
   if (verts)
-    mtet_emit_verts<<<(unsigned)be, 256, 0, st>>>(positions, sdf, reinterpret_cast<const int2*>(edges), n_edges, w.evid, w.echunk, verts);
+    mtet_emit_verts<<<(unsigned)be, 256, 0, st>>>(positions, sdf, reinterpret_cast<const int2*>(edges), n_edges, w.evid, w.echunk, verts, af);
   if (faces)
     mtet_emit_faces<<<(unsigned)bt, 256, 0, st>>>(tet_edges, n_tets, w.tinfo, w.t1chunk, w.t2chunk, w.evid, w.echunk, w.totals,
                                                    reinterpret_cast<long long*>(faces));
   return smb_check(cudaGetLastError());
+}
+
+extern "C" int smb_mtet_emit(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges,
+                             const int32_t* tet_edges, int64_t n_tets, const void* workspace, float* verts, int64_t* faces,
+                             void* stream) {
+  MtetAffine af{};
+  return mtet_emit_impl(positions, sdf, edges, n_edges, tet_edges, n_tets, workspace, verts, faces, af, stream);
+}
+
+extern "C" int smb_mtet_emit_affine(const float* positions, const float* sdf, const int32_t* edges, int64_t n_edges,
+                                    const int32_t* tet_edges, int64_t n_tets, const void* workspace, float* verts, int64_t* faces,
+                                    const float* affine8, void* stream) {
+  if (!affine8) return SMB_ERR_BAD_ARG;
+  MtetAffine af{};
+  af.on = 1;
+  af.sub = affine8[0];
+  af.div = affine8[1];
+  for (int c = 0; c < 3; ++c) {
+    af.mul[c] = affine8[2 + c];
+    af.add[c] = affine8[5 + c];
+  }
+  return mtet_emit_impl(positions, sdf, edges, n_edges, tet_edges, n_tets, workspace, verts, faces, af, stream);
 }
 
 extern "C" int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t n_vertices, float* out, void* stream) {

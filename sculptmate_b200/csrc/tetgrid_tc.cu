@@ -310,52 +310,103 @@ struct TgTabParams {
   float* tab[kTgMaxHeads][3];         // C (slow, mid), T1 (slow, fast), T2 (mid, fast): (n_p, n_q, 64) fp32
 };
 
-// blockIdx.y = head * 3 + pair.  One warp per table entry: lanes 0..39 interpolate one channel each (the reference's
-// grid_sample bilinear taps with zero padding, system.py:186-195), then every lane contracts the 40 channels with two rows of
-// W_0/2 (shared memory, transposed so that consecutive lanes read consecutive words).
+// blockIdx.y = pair.  A warp works on 8 consecutive table entries at a time, for all heads at once: lanes 0..7 set up the
+// bilinear taps of one entry each (the reference's grid_sample with zero padding, system.py:186-195), the warp gathers
+// the 8 x 40 channel values (160-byte channels-last runs) into shared memory, then every lane contracts them with two
+// rows of W_0/2 per head (shared memory, transposed so that consecutive lanes read consecutive words; the eight
+// entries share every weight it loads) and stores its 2 x 8 outputs per head.
+constexpr int kTabE = 8;  // entries per warp iteration
+template <int kNH>
 __global__ void __launch_bounds__(256) tetgrid_tables_kernel(TgTabParams p) {
-  __shared__ float sWt[kCp][kHid];
-  __shared__ float sF[8][kCp];
-  const int head = blockIdx.y / 3, pair = blockIdx.y - head * 3;
+  __shared__ float sWt[kNH][kCp][kHid];
+  __shared__ __align__(16) float sF[8][kCp][kTabE];
+  __shared__ int sOff[8][kTabE][4];
+  __shared__ float sWgt[8][kTabE][4];
+  const int pair = blockIdx.y;
   const int lp = pair == 2 ? 1 : 0, lq = pair == 0 ? 1 : 2;  // the pair's two lattice indices
   const int dp = p.sdim[lp], dq = p.sdim[lq];
   const int plane = dp + dq - 1;  // {x,y} -> 0, {x,z} -> 1, {y,z} -> 2 (system.py:181-184)
   // the plane's first coordinate (grid_sample's x = width) is the lower spatial dimension
   const bool p_is_u = dp < dq;
-  for (int i = threadIdx.x; i < kCp * kHid; i += blockDim.x) {
-    const int c = i / kHid, n = i - c * kHid;
-    sWt[c][n] = p.w0_half[head][n * kFeat + plane * kCp + c];
+  for (int i = threadIdx.x; i < kNH * kCp * kHid; i += blockDim.x) {
+    const int h = i / (kCp * kHid), r = i - h * (kCp * kHid);
+    const int c = r / kHid, n = r - c * kHid;
+    sWt[h][c][n] = p.w0_half[h][n * kFeat + plane * kCp + c];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = p.n[lp], nq = p.n[lq];
   const long long nent = (long long)np * nq;
   const float* P = p.planes_cl + (long long)plane * p.H * p.W * kCp;
-  float* out = p.tab[head][pair];
-  const float b0 = pair == 0 ? p.b0_half[head][lane] : 0.0f, b1 = pair == 0 ? p.b0_half[head][lane + 32] : 0.0f;
-  for (long long e = (long long)blockIdx.x * 8 + warp; e < nent; e += (long long)gridDim.x * 8) {
-    const int ip = (int)(e / nq), iq = (int)(e - (long long)ip * nq);
-    const float up = p.axis_u[lp][ip], uq = p.axis_u[lq][iq];
-    const Tap2 tu = make_tap(p_is_u ? up : uq, p.W, p.align_corners);
-    const Tap2 tv = make_tap(p_is_u ? uq : up, p.H, p.align_corners);
-    for (int c = lane; c < kCp; c += 32) {
-      const float v00 = P[((long long)tv.i0 * p.W + tu.i0) * kCp + c], v01 = P[((long long)tv.i0 * p.W + tu.i1) * kCp + c];
-      const float v10 = P[((long long)tv.i1 * p.W + tu.i0) * kCp + c], v11 = P[((long long)tv.i1 * p.W + tu.i1) * kCp + c];
-      sF[warp][c] = tv.w0 * (tu.w0 * v00 + tu.w1 * v01) + tv.w1 * (tu.w0 * v10 + tu.w1 * v11);
+  float bias[kNH][2];
+#pragma unroll
+  for (int h = 0; h < kNH; ++h) {
+    bias[h][0] = pair == 0 ? p.b0_half[h][lane] : 0.0f;
+    bias[h][1] = pair == 0 ? p.b0_half[h][lane + 32] : 0.0f;
+  }
+  for (long long e0 = ((long long)blockIdx.x * 8 + warp) * kTabE; e0 < nent; e0 += (long long)gridDim.x * 8 * kTabE) {
+    if (lane < kTabE) {
+      const long long e = min(e0 + lane, nent - 1);
+      const int ip = (int)(e / nq), iq = (int)(e - (long long)ip * nq);
+      const float up = p.axis_u[lp][ip], uq = p.axis_u[lq][iq];
+      const Tap2 tu = make_tap(p_is_u ? up : uq, p.W, p.align_corners);
+      const Tap2 tv = make_tap(p_is_u ? uq : up, p.H, p.align_corners);
+      sOff[warp][lane][0] = (tv.i0 * p.W + tu.i0) * kCp;
+      sOff[warp][lane][1] = (tv.i0 * p.W + tu.i1) * kCp;
+      sOff[warp][lane][2] = (tv.i1 * p.W + tu.i0) * kCp;
+      sOff[warp][lane][3] = (tv.i1 * p.W + tu.i1) * kCp;
+      sWgt[warp][lane][0] = tv.w0;
+      sWgt[warp][lane][1] = tv.w1;
+      sWgt[warp][lane][2] = tu.w0;
+      sWgt[warp][lane][3] = tu.w1;
     }
     __syncwarp();
-    float a0 = b0, a1 = b1;
-#pragma unroll 8
-    for (int c = 0; c < kCp; ++c) {
-      const float f = sF[warp][c];
-      a0 = fmaf(sWt[c][lane], f, a0);
-      a1 = fmaf(sWt[c][lane + 32], f, a1);
+    for (int idx = lane; idx < kTabE * kCp; idx += 32) {
+      const int en = idx / kCp, c = idx - en * kCp;
+      const int* o = sOff[warp][en];
+      const float* w = sWgt[warp][en];
+      const float v00 = __ldg(P + o[0] + c), v01 = __ldg(P + o[1] + c), v10 = __ldg(P + o[2] + c), v11 = __ldg(P + o[3] + c);
+      sF[warp][c][en] = w[0] * (w[2] * v00 + w[3] * v01) + w[1] * (w[2] * v10 + w[3] * v11);
     }
-    // rows indexed by the fast lattice index (T1, T2) are stored with their 16-byte chunks at chunk ^ (c & 7): the kernel
-    // above bulk-copies 8 consecutive rows into shared memory and reads them one row per thread
-    const int sw = pair == 0 ? 0 : ((iq & 7) << 2);
-    out[e * kHid + (lane ^ sw)] = a0;
-    out[e * kHid + ((lane + 32) ^ sw)] = a1;
+    __syncwarp();
+    float acc[kNH][2][kTabE];
+#pragma unroll
+    for (int h = 0; h < kNH; ++h)
+#pragma unroll
+      for (int en = 0; en < kTabE; ++en) {
+        acc[h][0][en] = bias[h][0];
+        acc[h][1][en] = bias[h][1];
+      }
+#pragma unroll 4
+    for (int c = 0; c < kCp; ++c) {
+      const float4 fa = *reinterpret_cast<const float4*>(&sF[warp][c][0]), fb = *reinterpret_cast<const float4*>(&sF[warp][c][4]);
+      const float f[kTabE] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+      for (int h = 0; h < kNH; ++h) {
+        const float w0 = sWt[h][c][lane], w1 = sWt[h][c][lane + 32];
+#pragma unroll
+        for (int en = 0; en < kTabE; ++en) {
+          acc[h][0][en] = fmaf(w0, f[en], acc[h][0][en]);
+          acc[h][1][en] = fmaf(w1, f[en], acc[h][1][en]);
+        }
+      }
+    }
+#pragma unroll
+    for (int en = 0; en < kTabE; ++en) {
+      const long long e = e0 + en;
+      if (e < nent) {
+        // rows indexed by the fast lattice index (T1, T2) are stored with their 16-byte chunks at chunk ^ (c & 7): the kernel
+        // above bulk-copies 8 consecutive rows into shared memory and reads them one row per thread
+        const int iq = (int)(e % nq);
+        const int sw = pair == 0 ? 0 : ((iq & 7) << 2);
+#pragma unroll
+        for (int h = 0; h < kNH; ++h) {
+          float* out = p.tab[h][pair];
+          out[e * kHid + (lane ^ sw)] = acc[h][0][en];
+          out[e * kHid + ((lane + 32) ^ sw)] = acc[h][1][en];
+        }
+      }
+    }
     __syncwarp();
   }
 }
@@ -441,9 +492,10 @@ extern "C" int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int 
   }
   {
     const long long maxent = nA * nB > nA * nC ? (nA * nB > nB * nC ? nA * nB : nB * nC) : (nA * nC > nB * nC ? nA * nC : nB * nC);
-    long long bx = (maxent + 7) / 8;
-    if (bx > (long long)sms * 8) bx = (long long)sms * 8;
-    tetgrid_tables_kernel<<<dim3((unsigned)bx, (unsigned)(3 * nheads)), 256, 0, st>>>(tp);
+    long long bx = (maxent + 8 * kTabE - 1) / (8 * kTabE);
+    if (bx > (long long)sms * 4) bx = (long long)sms * 4;
+    if (nheads == 1) tetgrid_tables_kernel<1><<<dim3((unsigned)bx, 3), 256, 0, st>>>(tp);
+    else tetgrid_tables_kernel<2><<<dim3((unsigned)bx, 3), 256, 0, st>>>(tp);
   }
   const size_t smem = (size_t)2 * nheads * (nh - 1) * kWBytes + (size_t)kTgWG * kTgStages * kTgStageBytes + 8 * (1 + 5 * kTgWG) + 16 + 16 +
                       (size_t)nheads * (4 * kHid + 4) * 4;

@@ -735,9 +735,12 @@ _mtet_ws: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
 
 
 def marching_tets(
-    positions: torch.Tensor, sdf: torch.Tensor, edges: torch.Tensor, tets: torch.Tensor, tet_edges: torch.Tensor
+    positions: torch.Tensor, sdf: torch.Tensor, edges: torch.Tensor, tets: torch.Tensor, tet_edges: torch.Tensor,
+    affine: Optional[Sequence[float]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """MarchingTetrahedraHelper._forward on static int32 topology -> (verts (V,3) f32, faces (F,3) i64)."""
+    """MarchingTetrahedraHelper._forward on static int32 topology -> (verts (V,3) f32, faces (F,3) i64).
+    ``affine`` (8 floats: in_lo, in_hi - in_lo, (out_hi - out_lo)[3], out_lo[3]) applies the caller's ``scale_tensor`` to the
+    vertices inside the emit kernel (same fp32 operations, one pass instead of four elementwise kernels)."""
     _require_cuda(sdf, "level")
     dev = sdf.device
     ne, nt = int(edges.shape[0]), int(tets.shape[0])
@@ -759,11 +762,18 @@ def marching_tets(
         V, F = int(counts_pin[0]), int(counts_pin[1])
         verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
         faces = torch.empty((F, 3), dtype=torch.int64, device=dev)
-        if V or F:
+        if (V or F) and affine is None:
             check(
                 lib.smb_mtet_emit(positions.data_ptr(), sdf.data_ptr(), edges.data_ptr(), ne, tet_edges.data_ptr(), nt, ws.data_ptr(),
                                   verts.data_ptr(), faces.data_ptr(), _stream_ptr(dev)),
                 "smb_mtet_emit",
+            )
+        elif V or F:
+            af = (ctypes.c_float * 8)(*[float(x) for x in affine])
+            check(
+                lib.smb_mtet_emit_affine(positions.data_ptr(), sdf.data_ptr(), edges.data_ptr(), ne, tet_edges.data_ptr(), nt, ws.data_ptr(),
+                                         verts.data_ptr(), faces.data_ptr(), af, _stream_ptr(dev)),
+                "smb_mtet_emit_affine",
             )
     return verts, faces
 

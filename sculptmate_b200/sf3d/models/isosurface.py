@@ -131,7 +131,9 @@ class MarchingTetrahedraHelper(IsosurfaceHelper):
             )
         return self._topology[1:]
 
-    def forward(self, level: torch.Tensor, deformation: Optional[torch.Tensor] = None) -> Mesh:
+    def forward(self, level: torch.Tensor, deformation: Optional[torch.Tensor] = None, v_pos_affine=None) -> Mesh:
+        """``v_pos_affine`` (optional, 8 floats, see ``runtime.marching_tets``): the caller's scale_tensor of ``v_pos``
+        folded into the vertex kernel (sf3d/system.py:162-164)."""
         dev = level.device
         base = self._grid_vertices.to(dev)
         if deformation is not None:
@@ -141,7 +143,7 @@ class MarchingTetrahedraHelper(IsosurfaceHelper):
             grid_vertices = base
         edges, tets, tet_edges = self.topology(dev)
         sdf = level.detach().to(torch.float32).contiguous().view(-1)
-        v_pos, t_pos_idx = runtime.marching_tets(grid_vertices, sdf, edges, tets, tet_edges)
+        v_pos, t_pos_idx = runtime.marching_tets(grid_vertices, sdf, edges, tets, tet_edges, affine=v_pos_affine)
         return Mesh(
             v_pos=v_pos, t_pos_idx=t_pos_idx,
             grid_vertices=grid_vertices, tet_edges=self.all_edges, grid_level=level, grid_deformation=deformation,

@@ -51,6 +51,7 @@ class SF3D(BaseModule):
         self.isosurface_helper = MarchingTetrahedraHelper(self.cfg.isosurface_resolution, self.cfg.tets_path)
         self._grid_positions = None
         self._lattice_axes = None
+        self._affine = None
 
     # ------------------------------------------------------------------ API
     def query_triplane(self, positions: torch.Tensor, triplanes: torch.Tensor) -> torch.Tensor:
@@ -102,6 +103,17 @@ class SF3D(BaseModule):
             h = self.isosurface_helper
             self._grid_positions = scale_tensor(h.grid_vertices.to(device), h.points_range, self.bbox.to(device)).contiguous()
         return self._grid_positions
+
+    def _v_pos_affine(self, device: torch.device):
+        """scale_tensor(v, points_range, bbox) as the 8 floats of ``runtime.marching_tets``: the differences are taken in
+        fp32 exactly as utils.py:228-230 takes them (python-float subtraction for the input range, tensor for the bbox)."""
+        if self._affine is None:
+            h = self.isosurface_helper
+            bbox = self.bbox.detach().to("cpu", torch.float32)
+            span = bbox[1] - bbox[0]
+            lo, hi = h.points_range
+            self._affine = [float(lo), float(hi - lo), *[float(x) for x in span], *[float(x) for x in bbox[0]]]
+        return self._affine
 
     def _lattice_axis_u(self, device: torch.device):
         """Per-index coordinate lists of a lattice-ordered grid, taken through the same two ``scale_tensor`` calls as every
@@ -161,7 +173,7 @@ class SF3D(BaseModule):
                 decoded = self.decoder(values, include=["vertex_offset", "density"])
                 density, deform = decoded["density"], decoded["vertex_offset"].squeeze(0)
             sdf = density - self.cfg.isosurface_threshold  # :155
-            mesh = h(sdf.view(-1, 1), deform.view(-1, 3) if deform is not None else None)
-            mesh.v_pos = scale_tensor(mesh.v_pos, h.points_range, self.bbox.to(dev))  # :162-164
+            # scale_tensor(mesh.v_pos, points_range, bbox) (:162-164) runs inside the vertex kernel: the same fp32 operations
+            mesh = h(sdf.view(-1, 1), deform.view(-1, 3) if deform is not None else None, v_pos_affine=self._v_pos_affine(dev))
             meshes.append(mesh)
         return meshes
