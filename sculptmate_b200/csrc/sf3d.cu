@@ -230,59 +230,96 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
   return base + inc - v;
 }
 
-// K1: crossing flag per static edge + chunk-local prefix
+// K1: crossing flag per static edge + chunk-local prefix.  The index records are read COALESCED (lane-consecutive: edge
+// q * 256 + tid of the chunk) and the flags pass through shared memory to the thread that scans 8 consecutive edges --
+// reading 8 consecutive records per thread made every load instruction touch 32 different cache lines (129 us at 29 M
+// edges; the stream itself is 36 us of HBM time).
 __global__ void __launch_bounds__(256) mtet_edge_count(const float* __restrict__ sdf, const int2* __restrict__ edges, long long ne,
                                                        uint32_t* __restrict__ evid, uint32_t* __restrict__ echunk) {
   __shared__ uint32_t s_warp[8];
-  const long long e0 = (long long)blockIdx.x * kScan + threadIdx.x * 8;
-  uint32_t flag[8], sum = 0;
+  __shared__ __align__(8) unsigned char s_flag[kScan];
+  const long long c0 = (long long)blockIdx.x * kScan;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    flag[k] = 0;
-    if (e0 + k < ne) {
-      const int2 ab = __ldg(edges + e0 + k);
+  for (int q = 0; q < 8; ++q) {
+    const long long e = c0 + q * 256 + threadIdx.x;
+    unsigned char f = 0;
+    if (e < ne) {
+      const int2 ab = __ldg(edges + e);
       const bool oa = __ldg(sdf + ab.x) > 0.0f, ob = __ldg(sdf + ab.y) > 0.0f;  // occ_n = sdf_n > 0  :146
-      flag[k] = oa != ob ? 1u : 0u;                                             // mask_edges        :158
+      f = oa != ob ? 1 : 0;                                                     // mask_edges        :158
     }
-    sum += flag[k];
+    s_flag[q * 256 + threadIdx.x] = f;
   }
+  __syncthreads();
+  const uint2 fw = *reinterpret_cast<const uint2*>(&s_flag[threadIdx.x * 8]);  // this thread's 8 consecutive flags, one per byte
+  const uint32_t sum = __popc(fw.x) + __popc(fw.y);
   uint32_t total;
   uint32_t run = block_excl_scan(sum, s_warp, total);
+  const long long e0 = c0 + threadIdx.x * 8;
+  uint32_t out[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    if (e0 + k < ne) evid[e0 + k] = run | (flag[k] << 31);
-    run += flag[k];
+    const uint32_t f = ((k < 4 ? fw.x : fw.y) >> (8 * (k & 3))) & 1u;
+    out[k] = run | (f << 31);
+    run += f;
+  }
+  if (e0 + 8 <= ne) {  // evid is 16-byte aligned and chunks are multiples of 8
+    uint4* o = reinterpret_cast<uint4*>(evid + e0);
+    o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (e0 + k < ne) evid[e0 + k] = out[k];
   }
   if (threadIdx.x == 0) echunk[blockIdx.x] = total;
 }
 
-// K2: tet code, triangle count class, chunk-local prefixes of the two classes
+// K2: tet code, triangle count class, chunk-local prefixes of the two classes (coalesced like K1)
 __global__ void __launch_bounds__(256) mtet_tet_count(const float* __restrict__ sdf, const int4* __restrict__ tets, long long nt,
                                                       uint32_t* __restrict__ tinfo, uint32_t* __restrict__ t1chunk,
                                                       uint32_t* __restrict__ t2chunk) {
   __shared__ uint32_t s_warp[8];
-  const long long t0 = (long long)blockIdx.x * kScan + threadIdx.x * 8;
+  __shared__ __align__(8) unsigned char s_code[kScan];
+  const long long c0 = (long long)blockIdx.x * kScan;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const long long t = c0 + q * 256 + threadIdx.x;
+    unsigned char c = 0;
+    if (t < nt) {
+      const int4 v = __ldg(tets + t);
+      c = (unsigned char)((__ldg(sdf + v.x) > 0.0f ? 1u : 0u) | (__ldg(sdf + v.y) > 0.0f ? 2u : 0u) |
+                          (__ldg(sdf + v.z) > 0.0f ? 4u : 0u) | (__ldg(sdf + v.w) > 0.0f ? 8u : 0u));  // :182-183
+    }
+    s_code[q * 256 + threadIdx.x] = c;
+  }
+  __syncthreads();
+  const uint2 cw = *reinterpret_cast<const uint2*>(&s_code[threadIdx.x * 8]);
   uint32_t code[8], cls[8], sum = 0;  // cls: 1 -> low half, 2 -> high half (packed 16+16)
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    code[k] = 0;
-    cls[k] = 0;
-    if (t0 + k < nt) {
-      const int4 v = __ldg(tets + t0 + k);
-      const uint32_t c = (__ldg(sdf + v.x) > 0.0f ? 1u : 0u) | (__ldg(sdf + v.y) > 0.0f ? 2u : 0u) |
-                         (__ldg(sdf + v.z) > 0.0f ? 4u : 0u) | (__ldg(sdf + v.w) > 0.0f ? 8u : 0u);  // :182-183
-      code[k] = c;
-      const int n = c_ntri_table[c];
-      cls[k] = n == 1 ? 1u : (n == 2 ? 0x10000u : 0u);
-    }
+    code[k] = ((k < 4 ? cw.x : cw.y) >> (8 * (k & 3))) & 0xffu;
+    const int n = c_ntri_table[code[k]];  // code 0 (also the padding behind nt) has no triangle
+    cls[k] = n == 1 ? 1u : (n == 2 ? 0x10000u : 0u);
     sum += cls[k];
   }
   uint32_t total;
   uint32_t run = block_excl_scan(sum, s_warp, total);
+  const long long t0 = c0 + threadIdx.x * 8;
+  uint32_t out[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    if (t0 + k < nt) tinfo[t0 + k] = (run & 0xfffu) | (((run >> 16) & 0xfffu) << 12) | (code[k] << 24);
+    out[k] = (run & 0xfffu) | (((run >> 16) & 0xfffu) << 12) | (code[k] << 24);
     run += cls[k];
+  }
+  if (t0 + 8 <= nt) {
+    uint4* o = reinterpret_cast<uint4*>(tinfo + t0);
+    o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (t0 + k < nt) tinfo[t0 + k] = out[k];
   }
   if (threadIdx.x == 0) {
     t1chunk[blockIdx.x] = total & 0xffffu;
@@ -290,7 +327,8 @@ __global__ void __launch_bounds__(256) mtet_tet_count(const float* __restrict__ 
   }
 }
 
-// K3: one CTA: exclusive scans of the three chunk-total arrays (in place) + grand totals
+// K3: one CTA: exclusive scans of the three chunk-total arrays (in place) + grand totals; 8 consecutive entries per thread
+// and round (a round of 1024 entries cost five barriers: 37 us for the 38 K chunk totals of the n = 160 grid)
 __global__ void __launch_bounds__(1024) mtet_totals(uint32_t* echunk, long long nech, uint32_t* t1chunk, uint32_t* t2chunk,
                                                     long long ntch, long long* totals, smb_mtet_counts* counts) {
   __shared__ uint32_t warp_sums[32];
@@ -301,10 +339,15 @@ __global__ void __launch_bounds__(1024) mtet_totals(uint32_t* echunk, long long 
     const long long n = a == 0 ? nech : ntch;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (long long base = 0; base < n; base += 1024) {
-      const long long idx = base + tid;
-      const uint32_t v = idx < n ? arr[idx] : 0u;
-      uint32_t inc = v;
+    for (long long base = 0; base < n; base += 8192) {
+      const long long i0 = base + tid * 8;
+      uint32_t v[8], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = i0 + k < n ? arr[i0 + k] : 0u;
+        sum += v[k];
+      }
+      uint32_t inc = sum;
 #pragma unroll
       for (int s = 1; s < 32; s <<= 1) {
         uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
@@ -322,10 +365,14 @@ __global__ void __launch_bounds__(1024) mtet_totals(uint32_t* echunk, long long 
         warp_sums[lane] = winc - ws;
       }
       __syncthreads();
-      const uint32_t excl = carry_s + warp_sums[warp] + inc - v;
-      if (idx < n) arr[idx] = excl;
+      uint32_t run = carry_s + warp_sums[warp] + inc - sum;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (i0 + k < n) arr[i0 + k] = run;
+        run += v[k];
+      }
       __syncthreads();
-      if (tid == 1023) carry_s = excl + v;
+      if (tid == 1023) carry_s = run;
       __syncthreads();
     }
     if (tid == 0) totals[a] = carry_s;
