@@ -19,10 +19,11 @@
 //     epilogue's instructions).  The constant block is the same for every tile, so ONE copy serves all warpgroups
 //     (5 x 96 + 8 = 488 TMEM columns); round 1 gave each warpgroup its own (128 columns per slot -> only four tiles in
 //     flight), which is why it measured no gain then.  256^3: 2.85 -> 2.76 ms on the same GPU.
-//   * kPoly (default 3): kPoly of the 64 activations of a layer step take their tanh from an FMA-pipe polynomial (silu_poly
-//     below) -- the software-exponential trick of FlashAttention-4 applied to SiLU.  In round 1 (latency-bound kernel, a
-//     polynomial with 1e-3 error) it was slower; with the leaner steps of round 2 the SFU is busy 85 % of the time and
-//     moving 3 of 64 activations off it buys 4 % (more than 6 of 64 costs more FMA-pipe time than it frees SFU time).
+//   * kPoly (default 5): kPoly of the 32 activation PAIRS of a layer step take their tanh from an FMA-pipe polynomial
+//     (silu_poly2 below) -- the software-exponential trick of FlashAttention-4 applied to SiLU.  In round 1 (latency-bound
+//     kernel, a polynomial with 1e-3 error) it was slower; with the leaner steps of round 2 the SFU is busy 85 % of the time.
+//     All epilogue arithmetic runs on fp32 PAIRS (sm_100's FFMA2: one issue slot for two lanes), which halves the issue
+//     cost of the polynomial: scalar, 3 of 64 activations was the optimum (2.60 ms); packed, 5 pairs = 10 of 64 (2.50 ms).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -62,10 +63,29 @@ __device__ __forceinline__ float silu_poly(float h) {
   q = fmaf(q, x, 9.778961789e-01f);
   return fmaf(a, q, h);
 }
-// activation j (0..63) of a layer step: kPoly of the 64 go to the FMA pipe, spread evenly over the step
+// The same on a PAIR of activations with sm_100's packed fp32 instructions (FFMA2: one issue slot for two lanes, two
+// FMA-pipe cycles): 15 instructions for two activations instead of 24.
+__device__ __forceinline__ float2 silu_poly2(float2 h) {
+  const float2 a = make_float2(fabsf(h.x), fabsf(h.y));
+  float2 x = __ffma2_rn(a, make_float2(2.0f / 4.5f, 2.0f / 4.5f), make_float2(-1.0f, -1.0f));
+  x = make_float2(fminf(x.x, 1.0f), fminf(x.y, 1.0f));
+  float2 q = make_float2(3.815771247e-02f, 3.815771247e-02f);
+  q = __ffma2_rn(q, x, make_float2(1.059716077e-01f, 1.059716077e-01f));
+  q = __ffma2_rn(q, x, make_float2(-2.874662484e-01f, -2.874662484e-01f));
+  q = __ffma2_rn(q, x, make_float2(-1.656126921e-02f, -1.656126921e-02f));
+  q = __ffma2_rn(q, x, make_float2(3.707452418e-01f, 3.707452418e-01f));
+  q = __ffma2_rn(q, x, make_float2(-3.581689483e-01f, -3.581689483e-01f));
+  q = __ffma2_rn(q, x, make_float2(2.788679147e-01f, 2.788679147e-01f));
+  q = __ffma2_rn(q, x, make_float2(-2.090362925e-01f, -2.090362925e-01f));
+  q = __ffma2_rn(q, x, make_float2(9.955515848e-02f, 9.955515848e-02f));
+  q = __ffma2_rn(q, x, make_float2(9.778961789e-01f, 9.778961789e-01f));
+  return __ffma2_rn(a, q, h);
+}
+// activation pair jp (0..31) of a layer step: kPoly of the 32 pairs go to the FMA pipe, spread evenly over the step
 template <int kPoly>
-__device__ __forceinline__ float silu_mix(float h, int j) {
-  return (((j * kPoly) & 63) < kPoly) ? silu_poly(h) : silu_from_half_arg(h);
+__device__ __forceinline__ float2 silu_mix2(float2 h, int jp) {
+  constexpr int kP = kPoly % 100, kOff = kPoly / 100;  // developer sweeps encode a placement offset as kPoly = 100 * offset + pairs
+  return ((((jp + kOff) * kP) & 31) < kP) ? silu_poly2(h) : silu2_from_half_arg(h);
 }
 
 // developer instrumentation (kTrace, SMB_TC_TRACE=2): clock64 stamps of block 0, every consumer warp, first kTraceSteps layer steps
@@ -284,12 +304,12 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
             const float4 a = t0p[4 * c + g4], b = t1p[4 * c + g4], cv = cc[4 * c + g4];
-            const float h0 = cv.x + w0 * a.x + w1 * b.x;
-            const float h1 = cv.y + w0 * a.y + w1 * b.y;
-            const float h2 = cv.z + w0 * a.z + w1 * b.z;
-            const float h3 = cv.w + w0 * a.w + w1 * b.w;
-            pk[2 * g4 + 0] = pack_half2(silu_mix<kPoly>(h0, 16 * c + 4 * g4 + 0), silu_mix<kPoly>(h1, 16 * c + 4 * g4 + 1));
-            pk[2 * g4 + 1] = pack_half2(silu_mix<kPoly>(h2, 16 * c + 4 * g4 + 2), silu_mix<kPoly>(h3, 16 * c + 4 * g4 + 3));
+            // c + w0 T[h0] + w1 T[h1] on fp32 pairs (FFMA2): same operations and order as the scalar form
+            const float2 h01 = __ffma2_rn(make_float2(w1, w1), make_float2(b.x, b.y), __ffma2_rn(make_float2(w0, w0), make_float2(a.x, a.y), make_float2(cv.x, cv.y)));
+            const float2 h23 = __ffma2_rn(make_float2(w1, w1), make_float2(b.z, b.w), __ffma2_rn(make_float2(w0, w0), make_float2(a.z, a.w), make_float2(cv.z, cv.w)));
+            const float2 s01 = silu_mix2<kPoly>(h01, 8 * c + 2 * g4), s23 = silu_mix2<kPoly>(h23, 8 * c + 2 * g4 + 1);
+            pk[2 * g4 + 0] = pack_half2(s01.x, s01.y);
+            pk[2 * g4 + 1] = pack_half2(s23.x, s23.y);
           }
           tmem_st8(a_tmem + lane_off + 8 * c, pk);
         }
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
         xu_acquire();
         const float4* bl = reinterpret_cast<const float4*>(sBias + l * kHid);
         const float4* hw = reinterpret_cast<const float4*>(sHeadW);
-        float dacc = 0.0f;
+        float2 dacc = make_float2(0.0f, 0.0f);  // even / odd partial sums of the head's dot product
         uint32_t r[2][16];
         float4 bb[2][4];
         tmem_ld16(d_tmem + lane_off, r[0]);
@@ -350,21 +370,20 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
               h[4 * i + 3] = __uint_as_float(rc[4 * i + 3]) + bc[i].w;
             }
           }
+          float2 h2[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) h[i] = silu_mix<kPoly>(h[i], 16 * c + i);
+          for (int i = 0; i < 8; ++i) h2[i] = silu_mix2<kPoly>(make_float2(h[2 * i], h[2 * i + 1]), 8 * c + i);
           if (!last) {
             uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h[2 * i], h[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h2[i].x, h2[i].y);
             tmem_st8(a_tmem + lane_off + 8 * c, pk);
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 w = hw[4 * c + i];
-              dacc = fmaf(h[4 * i + 0], w.x, dacc);
-              dacc = fmaf(h[4 * i + 1], w.y, dacc);
-              dacc = fmaf(h[4 * i + 2], w.z, dacc);
-              dacc = fmaf(h[4 * i + 3], w.w, dacc);
+              dacc = __ffma2_rn(h2[2 * i], make_float2(w.x, w.y), dacc);
+              dacc = __ffma2_rn(h2[2 * i + 1], make_float2(w.z, w.w), dacc);
             }
           }
         }
@@ -374,7 +393,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
           issue_layer(l + 1);
           if (kTrace) tr_put(tr0, tr1, tr2, clock64());
         } else {
-          const float d = dacc + sBiasF[0];
+          const float d = dacc.x + dacc.y + sBiasF[0];
           const float act = expf(__fadd_rn(d, p.density_bias));
           if (m < tg.nvalid) {
             const long long o = tg.line * p.R + tg.k0 + m;
@@ -423,14 +442,16 @@ static int launch_tc_ta_n(const TcParams& p, int sms, cudaStream_t st) {
 
 // Default: FIVE consumer warpgroups (5 x 96 + 8 = 488 of the 512 TMEM columns; 768 threads, the producer warpgroup hands 40
 // of its 80 registers to the consumers with setmaxnreg so that they run at 88), hidden-layer bias through a fifth K=16
-// MMA, the density head fused into the last epilogue, and kDefaultPoly = 3 of the 64 activations of a layer step evaluated
-// on the FMA pipe (silu_poly, at least as accurate as tanh.approx) instead of the SFU.  Measured on one B200 at 256^3
-// (profiles/r02j_k1_steps.log): 2.72 ms with every tanh on the SFU, 2.64 / 2.60 / 2.63 / 2.62 / 2.63 / 2.67 ms with
-// 2 / 3 / 4 / 5 / 6 / 8 of 64 on the FMA pipe.  The product library instantiates exactly this kernel and its
+// MMA, the density head fused into the last epilogue, all epilogue arithmetic on fp32 pairs (FFMA2), and kDefaultPoly = 5
+// of the 32 activation pairs of a layer step evaluated on the FMA pipe (silu_poly2, at least as accurate as tanh.approx)
+// instead of the SFU.  Measured on one B200 at 256^3 (profiles/r02n_k1_packed.log), pairs on the FMA pipe: 0: 2.651,
+// 1: 2.625, 2: 2.575, 3: 2.533, 4: 2.554, 5: 2.500, 6: 2.542, 8: 2.597, 10: 2.698, 12: 2.829 ms; WHICH pairs matters as much
+// as how many (5 pairs shifted by 2 or 4 positions: 2.59 ms).  The product library instantiates exactly this kernel and its
 // four-warpgroup form (the fallback when five table buffers do not fit in shared memory).  A developer build
-// (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements DESIGN.md 4/K1 argues from: SMB_TC_TA_POLY=<n of 64>,
-// SMB_TC_TA_BIAS=0 (bias in the epilogue), SMB_TC_TA_STAGGER=<clk>, SMB_TC_TA_TOKENS=1|2|3, SMB_TC_TA_WG=4, SMB_TC_TRACE=2.
-constexpr int kDefaultPoly = 3;
+// (-DSMB_DEV_VARIANTS) also compiles the variants whose measurements DESIGN.md 4/K1 argues from: SMB_TC_TA_POLY=<pairs of 32>
+// (+ 100 x placement offset), SMB_TC_TA_BIAS=0 (bias in the epilogue), SMB_TC_TA_STAGGER=<clk>, SMB_TC_TA_TOKENS=1|2|3,
+// SMB_TC_TA_WG=4, SMB_TC_TRACE=2.
+constexpr int kDefaultPoly = 5;
 int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
 #ifdef SMB_DEV_VARIANTS
   static const int bias = getenv("SMB_TC_TA_BIAS") ? atoi(getenv("SMB_TC_TA_BIAS")) : 1;
@@ -440,9 +461,22 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
   if (bias && wgs == 5 && poly != kDefaultPoly) {
     switch (poly) {
       case 0: return launch_tc_ta_n<5, 4, true, 0>(p, sms, st);
+      case 1: return launch_tc_ta_n<5, 4, true, 1>(p, sms, st);
       case 2: return launch_tc_ta_n<5, 4, true, 2>(p, sms, st);
+      case 3: return launch_tc_ta_n<5, 4, true, 3>(p, sms, st);
+      case 10: return launch_tc_ta_n<5, 4, true, 10>(p, sms, st);
+      case 12: return launch_tc_ta_n<5, 4, true, 12>(p, sms, st);
+      case 7: return launch_tc_ta_n<5, 4, true, 7>(p, sms, st);
+      case 205: return launch_tc_ta_n<5, 4, true, 205>(p, sms, st);
+      case 405: return launch_tc_ta_n<5, 4, true, 405>(p, sms, st);
+      case 206: return launch_tc_ta_n<5, 4, true, 206>(p, sms, st);
+      case 306: return launch_tc_ta_n<5, 4, true, 306>(p, sms, st);
+      case 207: return launch_tc_ta_n<5, 4, true, 207>(p, sms, st);
+      case 307: return launch_tc_ta_n<5, 4, true, 307>(p, sms, st);
+      case 204: return launch_tc_ta_n<5, 4, true, 204>(p, sms, st);
+      case 304: return launch_tc_ta_n<5, 4, true, 304>(p, sms, st);
+      case 208: return launch_tc_ta_n<5, 4, true, 208>(p, sms, st);
       case 4: return launch_tc_ta_n<5, 4, true, 4>(p, sms, st);
-      case 5: return launch_tc_ta_n<5, 4, true, 5>(p, sms, st);
       case 6: return launch_tc_ta_n<5, 4, true, 6>(p, sms, st);
       default: return launch_tc_ta_n<5, 4, true, 8>(p, sms, st);
     }

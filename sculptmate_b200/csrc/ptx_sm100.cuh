@@ -181,6 +181,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 // silu(2h) = h + h*tanh(h): the caller folds the 1/2 into weights and bias
 __device__ __forceinline__ float silu_from_half_arg(float h) { return fmaf(h, tanh_approx(h), h); }
+// Two activations at once: sm_100's packed fp32 instruction (FFMA2, one issue slot for both lanes; the FMA pipe spends the
+// same two cycles on it as on two FFMAs -- tools/microbench/ffma2.cu -- so this helps kernels that are short of issue slots).
+__device__ __forceinline__ float2 silu2_from_half_arg(float2 h) {
+  const float2 t = make_float2(tanh_approx(h.x), tanh_approx(h.y));
+  return __ffma2_rn(h, t, h);
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);

@@ -213,8 +213,11 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
           for (int g4 = 0; g4 < 4; ++g4) {
             const int ch = 4 * c + g4;
             const float4 x = t1[ch ^ lc], y = t2[ch ^ lc], z = cc[ch];  // rows of the fast index are stored chunk-swizzled
-            pk[2 * g4 + 0] = pack_half2(silu_from_half_arg(x.x + y.x + z.x), silu_from_half_arg(x.y + y.y + z.y));
-            pk[2 * g4 + 1] = pack_half2(silu_from_half_arg(x.z + y.z + z.z), silu_from_half_arg(x.w + y.w + z.w));
+            // packed fp32 pairs (FADD2 / FFMA2): the kernel is short of issue slots, not of FMA-pipe time
+            const float2 lo = silu2_from_half_arg(__fadd2_rn(__fadd2_rn(make_float2(x.x, x.y), make_float2(y.x, y.y)), make_float2(z.x, z.y)));
+            const float2 hi = silu2_from_half_arg(__fadd2_rn(__fadd2_rn(make_float2(x.z, x.w), make_float2(y.z, y.w)), make_float2(z.z, z.w)));
+            pk[2 * g4 + 0] = pack_half2(lo.x, lo.y);
+            pk[2 * g4 + 1] = pack_half2(hi.x, hi.y);
           }
           tmem_st8(a_tmem + lane_off + 8 * c, pk);
         }
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
         const float* hwf = sHeadW + tg.head * (4 * kHid + 4);
         const float4* hw = reinterpret_cast<const float4*>(hwf);
         const bool wide = H.n_out > 1;  // warp-uniform
-        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+        float2 d0 = make_float2(0.f, 0.f), d1 = d0, d2 = d0;  // even / odd partial sums of the head's dot products
         uint32_t r[2][16];
         tmem_ld16(d_tmem + lane_off, r[0]);
 #pragma unroll
@@ -238,36 +241,30 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
           tmem_ld_wait();
           if (c + 1 < 4) tmem_ld16(d_tmem + lane_off + (c + 1) * 16, r[(c + 1) & 1]);
           const uint32_t* rc = r[c & 1];
-          float h[16];
+          float2 h[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) h[i] = silu_from_half_arg(__uint_as_float(rc[i]));
+          for (int i = 0; i < 8; ++i) h[i] = silu2_from_half_arg(make_float2(__uint_as_float(rc[2 * i]), __uint_as_float(rc[2 * i + 1])));
           if (!last) {
             uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h[2 * i], h[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) pk[i] = pack_half2(h[i].x, h[i].y);
             tmem_st8(a_tmem + lane_off + 8 * c, pk);
           } else {
             // the head (network.py:176-178: last Linear of the head) as fp32 dot products on the activations in registers
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 w = hw[4 * c + i];
-              d0 = fmaf(h[4 * i + 0], w.x, d0);
-              d0 = fmaf(h[4 * i + 1], w.y, d0);
-              d0 = fmaf(h[4 * i + 2], w.z, d0);
-              d0 = fmaf(h[4 * i + 3], w.w, d0);
+              d0 = __ffma2_rn(h[2 * i], make_float2(w.x, w.y), d0);
+              d0 = __ffma2_rn(h[2 * i + 1], make_float2(w.z, w.w), d0);
             }
             if (wide) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 w1 = hw[16 + 4 * c + i], w2 = hw[32 + 4 * c + i];
-                d1 = fmaf(h[4 * i + 0], w1.x, d1);
-                d1 = fmaf(h[4 * i + 1], w1.y, d1);
-                d1 = fmaf(h[4 * i + 2], w1.z, d1);
-                d1 = fmaf(h[4 * i + 3], w1.w, d1);
-                d2 = fmaf(h[4 * i + 0], w2.x, d2);
-                d2 = fmaf(h[4 * i + 1], w2.y, d2);
-                d2 = fmaf(h[4 * i + 2], w2.z, d2);
-                d2 = fmaf(h[4 * i + 3], w2.w, d2);
+                d1 = __ffma2_rn(h[2 * i], make_float2(w1.x, w1.y), d1);
+                d1 = __ffma2_rn(h[2 * i + 1], make_float2(w1.z, w1.w), d1);
+                d2 = __ffma2_rn(h[2 * i], make_float2(w2.x, w2.y), d2);
+                d2 = __ffma2_rn(h[2 * i + 1], make_float2(w2.z, w2.w), d2);
               }
             }
           }
@@ -277,15 +274,15 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
         } else if (tg.a0 + la < p.nA && tg.b0 + lb < p.nB && tg.c0 + lc < p.nC) {
           const long long row = ((long long)(tg.a0 + la) * p.nB + tg.b0 + lb) * p.nC + tg.c0 + lc;
           const float* hb = hwf + 4 * kHid;
-          float o0 = d0 + hb[0];
+          float o0 = d0.x + d0.y + hb[0];
           if (H.exp_act) o0 = expf(__fadd_rn(o0, H.out_bias));
           if (!wide) {
             H.out[row] = o0;
           } else {
             float* o = H.out + row * H.n_out;
             o[0] = o0;
-            o[1] = d1 + hb[1];
-            if (H.n_out > 2) o[2] = d2 + hb[2];
+            o[1] = d1.x + d1.y + hb[1];
+            if (H.n_out > 2) o[2] = d2.x + d2.y + hb[2];
           }
         }
       }
