@@ -82,10 +82,31 @@ __device__ __forceinline__ float2 silu_poly2(float2 h) {
   return __ffma2_rn(a, q, h);
 }
 // activation pair jp (0..31) of a layer step: kPoly of the 32 pairs go to the FMA pipe, spread evenly over the step
+// Which pairs: kPoly < 1000 = that many pairs, spread by the rule ((jp + offset) * pairs) & 31 < pairs with offset = kPoly / 100
+// (developer sweeps); kPoly >= 1000 = entry kPoly - 1000 of the candidate placements below (developer sweeps).
+__host__ __device__ constexpr unsigned poly_bits(unsigned a, unsigned b = 32, unsigned c = 32, unsigned d = 32, unsigned e = 32, unsigned f = 32,
+                                                 unsigned g = 32) {
+  return (a < 32 ? 1u << a : 0u) | (b < 32 ? 1u << b : 0u) | (c < 32 ? 1u << c : 0u) | (d < 32 ? 1u << d : 0u) | (e < 32 ? 1u << e : 0u) |
+         (f < 32 ? 1u << f : 0u) | (g < 32 ? 1u << g : 0u);
+}
+constexpr unsigned kPolyCand[] = {
+    poly_bits(0, 7, 13, 20, 26),      poly_bits(0, 6, 13, 19, 26),      poly_bits(0, 8, 16, 24, 4),      poly_bits(0, 8, 16, 24, 12, 28),
+    poly_bits(0, 7, 13, 20, 26, 31),  poly_bits(0, 1, 13, 20, 26),      poly_bits(0, 7, 14, 21, 28),     poly_bits(0, 5, 11, 16, 22, 27),
+    poly_bits(0, 3, 7, 13, 20, 26),   poly_bits(0, 7, 13, 20, 26, 10),  poly_bits(0, 7, 13, 20, 26, 16), poly_bits(0, 7, 13, 20, 26, 23),
+    poly_bits(0, 9, 13, 20, 26),      poly_bits(0, 7, 15, 20, 26),      poly_bits(0, 7, 13, 22, 26),     poly_bits(0, 7, 13, 20, 29),
+};
+template <int kPoly>
+__host__ __device__ constexpr unsigned poly_mask() {
+  if (kPoly >= 1000) return kPolyCand[kPoly - 1000];
+  unsigned m = 0;
+  for (int jp = 0; jp < 32; ++jp)
+    if ((((jp + kPoly / 100) * (kPoly % 100)) & 31) < (kPoly % 100)) m |= 1u << jp;
+  return m;
+}
 template <int kPoly>
 __device__ __forceinline__ float2 silu_mix2(float2 h, int jp) {
-  constexpr int kP = kPoly % 100, kOff = kPoly / 100;  // developer sweeps encode a placement offset as kPoly = 100 * offset + pairs
-  return ((((jp + kOff) * kP) & 31) < kP) ? silu_poly2(h) : silu2_from_half_arg(h);
+  constexpr unsigned kMask = poly_mask<kPoly>();
+  return ((kMask >> jp) & 1u) ? silu_poly2(h) : silu2_from_half_arg(h);
 }
 
 // developer instrumentation (kTrace, SMB_TC_TRACE=2): clock64 stamps of block 0, every consumer warp, first kTraceSteps layer steps
@@ -467,15 +488,22 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
       case 10: return launch_tc_ta_n<5, 4, true, 10>(p, sms, st);
       case 12: return launch_tc_ta_n<5, 4, true, 12>(p, sms, st);
       case 7: return launch_tc_ta_n<5, 4, true, 7>(p, sms, st);
-      case 205: return launch_tc_ta_n<5, 4, true, 205>(p, sms, st);
-      case 405: return launch_tc_ta_n<5, 4, true, 405>(p, sms, st);
-      case 206: return launch_tc_ta_n<5, 4, true, 206>(p, sms, st);
-      case 306: return launch_tc_ta_n<5, 4, true, 306>(p, sms, st);
-      case 207: return launch_tc_ta_n<5, 4, true, 207>(p, sms, st);
-      case 307: return launch_tc_ta_n<5, 4, true, 307>(p, sms, st);
-      case 204: return launch_tc_ta_n<5, 4, true, 204>(p, sms, st);
-      case 304: return launch_tc_ta_n<5, 4, true, 304>(p, sms, st);
-      case 208: return launch_tc_ta_n<5, 4, true, 208>(p, sms, st);
+      case 1000: return launch_tc_ta_n<5, 4, true, 1000>(p, sms, st);
+      case 1001: return launch_tc_ta_n<5, 4, true, 1001>(p, sms, st);
+      case 1002: return launch_tc_ta_n<5, 4, true, 1002>(p, sms, st);
+      case 1003: return launch_tc_ta_n<5, 4, true, 1003>(p, sms, st);
+      case 1004: return launch_tc_ta_n<5, 4, true, 1004>(p, sms, st);
+      case 1005: return launch_tc_ta_n<5, 4, true, 1005>(p, sms, st);
+      case 1006: return launch_tc_ta_n<5, 4, true, 1006>(p, sms, st);
+      case 1007: return launch_tc_ta_n<5, 4, true, 1007>(p, sms, st);
+      case 1008: return launch_tc_ta_n<5, 4, true, 1008>(p, sms, st);
+      case 1009: return launch_tc_ta_n<5, 4, true, 1009>(p, sms, st);
+      case 1010: return launch_tc_ta_n<5, 4, true, 1010>(p, sms, st);
+      case 1011: return launch_tc_ta_n<5, 4, true, 1011>(p, sms, st);
+      case 1012: return launch_tc_ta_n<5, 4, true, 1012>(p, sms, st);
+      case 1013: return launch_tc_ta_n<5, 4, true, 1013>(p, sms, st);
+      case 1014: return launch_tc_ta_n<5, 4, true, 1014>(p, sms, st);
+      case 1015: return launch_tc_ta_n<5, 4, true, 1015>(p, sms, st);
       case 4: return launch_tc_ta_n<5, 4, true, 4>(p, sms, st);
       case 6: return launch_tc_ta_n<5, 4, true, 6>(p, sms, st);
       default: return launch_tc_ta_n<5, 4, true, 8>(p, sms, st);
