@@ -400,20 +400,30 @@ def sharded_measure(model, dev, rank: int, world: int, R: int, steps: int, warmu
     thr = [float(x) for x in thr.tolist()]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # ---- T(1): rank 0 alone
-    t1_ms, ref = [], None
+    t1_ms, ref, t1_rejected = [], None, None
     if rank == 0:
-        for i in range(4 + steps):  # warm-up over both scenes twice: capacities learnt, both sets of output blocks allocated
-            flush.fill_(i & 0xFF)
-            a, b = ev(), ev()
-            a.record()
-            v1, f1 = model.extract_mesh_tensors(real[i % n_rot], R, thr[i % n_rot])
-            b.record()
-            torch.cuda.synchronize()
-            if i >= 4:
-                t1_ms.append(a.elapsed_time(b))
-            if i % n_rot == 0:
-                ref = (v1, f1)
-        del v1, f1
+        def t1_pass(n_warm):
+            nonlocal ref
+            out = []
+            for i in range(n_warm + steps):  # warm-up over both scenes twice: capacities learnt, both sets of output blocks allocated
+                flush.fill_(i & 0xFF)
+                a, b = ev(), ev()
+                a.record()
+                v1, f1 = model.extract_mesh_tensors(real[i % n_rot], R, thr[i % n_rot])
+                b.record()
+                torch.cuda.synchronize()
+                if i >= n_warm:
+                    out.append(a.elapsed_time(b))
+                if i % n_rot == 0:
+                    ref = (v1, f1)
+            return out
+
+        t1_ms = t1_pass(4)
+        if max(t1_ms) > 1.5 * float(np.median(t1_ms)):
+            # a step far above the median (an allocation or a host hiccup inside the timed region) would inflate T(1) and
+            # with it the speed-up: rejected and re-measured once, both passes reported
+            t1_rejected = pct(t1_ms)
+            t1_ms = t1_pass(2)
     dist.barrier()
     # ---- T(N)
     tn_ms, phases, exact, nV, nF = [], {}, None, 0, 0
@@ -448,7 +458,9 @@ def sharded_measure(model, dev, rank: int, world: int, R: int, steps: int, warmu
         return None
     tN = float(stats.item()) / steps
     t1 = float(np.mean(t1_ms))
+    t1_p50 = float(np.median(t1_ms))
     return {
+        "t1_unstable": bool(max(t1_ms) > 1.5 * t1_p50), "t1_rejected_pass": t1_rejected, "speedup_p50": t1_p50 / float(np.median(tn_ms)),
         "workload": f"TripoSR extract_mesh {R}^3, ONE lattice cut into x-slabs over {world} GPUs (BASELINE configs[2]); T(1) = the same scene through TSR.extract_mesh_tensors on rank 0",
         "resolution": R, "n_gpus": world, "steps": steps, "t1_ms": t1, "t1_ms_pct": pct(t1_ms), "tN_ms": tN, "tN_ms_pct": pct(tn_ms), "speedup": t1 / tN,
         "points_per_s": float(R) ** 3 / (tN * 1e-3), "scaling": "strong", "bit_exact_vs_1gpu": exact, "mesh": {"verts": nV, "tris": nF},
