@@ -82,6 +82,27 @@ __device__ __forceinline__ float2 silu_poly2(float2 h) {
   return __ffma2_rn(a, q, h);
 }
 // activation pair jp (0..31) of a layer step: kPoly of the 32 pairs go to the FMA pipe, spread evenly over the step
+// The same polynomial in Estrin form: 12 packed instructions + 3 squarings instead of 10 + clamp, but a dependency chain of 4
+// instead of 10 (developer variant, kPoly = 2000 + pairs).
+__device__ __forceinline__ float2 silu_poly2_estrin(float2 h) {
+  const float2 a = make_float2(fabsf(h.x), fabsf(h.y));
+  float2 x = __ffma2_rn(a, make_float2(2.0f / 4.5f, 2.0f / 4.5f), make_float2(-1.0f, -1.0f));
+  x = make_float2(fminf(x.x, 1.0f), fminf(x.y, 1.0f));
+  auto c2 = [](float v) { return make_float2(v, v); };
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 p01 = __ffma2_rn(c2(9.955515848e-02f), x, c2(9.778961789e-01f));
+  const float2 p23 = __ffma2_rn(c2(2.788679147e-01f), x, c2(-2.090362925e-01f));
+  const float2 p45 = __ffma2_rn(c2(3.707452418e-01f), x, c2(-3.581689483e-01f));
+  const float2 p67 = __ffma2_rn(c2(-2.874662484e-01f), x, c2(-1.656126921e-02f));
+  const float2 p89 = __ffma2_rn(c2(3.815771247e-02f), x, c2(1.059716077e-01f));
+  const float2 x4 = __fmul2_rn(x2, x2);
+  const float2 q03 = __ffma2_rn(p23, x2, p01);
+  const float2 q47 = __ffma2_rn(p67, x2, p45);
+  const float2 x8 = __fmul2_rn(x4, x4);
+  const float2 q07 = __ffma2_rn(q47, x4, q03);
+  const float2 q = __ffma2_rn(p89, x8, q07);
+  return __ffma2_rn(a, q, h);
+}
 // Which pairs: kPoly < 1000 = that many pairs, spread by the rule ((jp + offset) * pairs) & 31 < pairs with offset = kPoly / 100
 // (developer sweeps); kPoly >= 1000 = entry kPoly - 1000 of the candidate placements below (developer sweeps).
 __host__ __device__ constexpr unsigned poly_bits(unsigned a, unsigned b = 32, unsigned c = 32, unsigned d = 32, unsigned e = 32, unsigned f = 32,
@@ -95,9 +116,10 @@ constexpr unsigned kPolyCand[] = {
     poly_bits(0, 3, 7, 13, 20, 26),   poly_bits(0, 7, 13, 20, 26, 10),  poly_bits(0, 7, 13, 20, 26, 16), poly_bits(0, 7, 13, 20, 26, 23),
     poly_bits(0, 9, 13, 20, 26),      poly_bits(0, 7, 15, 20, 26),      poly_bits(0, 7, 13, 22, 26),     poly_bits(0, 7, 13, 20, 29),
 };
-template <int kPoly>
+template <int kPolyArg>
 __host__ __device__ constexpr unsigned poly_mask() {
-  if (kPoly >= 1000) return kPolyCand[kPoly - 1000];
+  constexpr int kPoly = kPolyArg >= 2000 ? kPolyArg - 2000 : kPolyArg;  // 2000 + n: the Estrin form, same placement rule
+  if (kPoly >= 1000) return kPolyCand[kPoly >= 1000 ? kPoly - 1000 : 0];
   unsigned m = 0;
   for (int jp = 0; jp < 32; ++jp)
     if ((((jp + kPoly / 100) * (kPoly % 100)) & 31) < (kPoly % 100)) m |= 1u << jp;
@@ -106,6 +128,7 @@ __host__ __device__ constexpr unsigned poly_mask() {
 template <int kPoly>
 __device__ __forceinline__ float2 silu_mix2(float2 h, int jp) {
   constexpr unsigned kMask = poly_mask<kPoly>();
+  if (kPoly >= 2000) return ((kMask >> jp) & 1u) ? silu_poly2_estrin(h) : silu2_from_half_arg(h);
   return ((kMask >> jp) & 1u) ? silu_poly2(h) : silu2_from_half_arg(h);
 }
 
@@ -488,6 +511,10 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
       case 10: return launch_tc_ta_n<5, 4, true, 10>(p, sms, st);
       case 12: return launch_tc_ta_n<5, 4, true, 12>(p, sms, st);
       case 7: return launch_tc_ta_n<5, 4, true, 7>(p, sms, st);
+      case 2005: return launch_tc_ta_n<5, 4, true, 2005>(p, sms, st);
+      case 2006: return launch_tc_ta_n<5, 4, true, 2006>(p, sms, st);
+      case 2007: return launch_tc_ta_n<5, 4, true, 2007>(p, sms, st);
+      case 2008: return launch_tc_ta_n<5, 4, true, 2008>(p, sms, st);
       case 1000: return launch_tc_ta_n<5, 4, true, 1000>(p, sms, st);
       case 1001: return launch_tc_ta_n<5, 4, true, 1001>(p, sms, st);
       case 1002: return launch_tc_ta_n<5, 4, true, 1002>(p, sms, st);
