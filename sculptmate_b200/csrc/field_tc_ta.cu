@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kTaWG * 128 + kTaProducers * 32, 1) lattice_tc
 
   // kRegShift (5 warpgroups): the CTA is launched at 80 registers per thread (768 threads); the producer
   // warpgroup gives registers back and the consumers take them (the increase is served from the registers the CTA itself gave back: 128 x (80 - 40) = 640 x (88 - 80))
-  constexpr bool kRegShift = kTaWG * 128 + kTaProducers * 32 > 640;
+  constexpr bool kRegShift = kTaWG * 128 + kTaProducers * 32 > 736;  // up to 736 threads every thread can have 88 registers
   if (wid >= kTaWG * 4) {
     if (kRegShift) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // =================================================================== producer
@@ -501,6 +501,10 @@ int launch_tc_ta(const TcParams& p, int sms, cudaStream_t st) {
   static const int bias = getenv("SMB_TC_TA_BIAS") ? atoi(getenv("SMB_TC_TA_BIAS")) : 1;
   static const int poly = getenv("SMB_TC_TA_POLY") ? atoi(getenv("SMB_TC_TA_POLY")) : kDefaultPoly;
   static const int wgs = getenv("SMB_TC_TA_WG") ? atoi(getenv("SMB_TC_TA_WG")) : 5;
+  static const int prod = getenv("SMB_TC_TA_PROD") ? atoi(getenv("SMB_TC_TA_PROD")) : 4;
+  if (prod == 2) return launch_tc_ta_n<5, 2, true, kDefaultPoly>(p, sms, st);
+  if (prod == 3) return launch_tc_ta_n<5, 3, true, kDefaultPoly>(p, sms, st);
+  if (prod == 1) return launch_tc_ta_n<5, 1, true, kDefaultPoly>(p, sms, st);
   if (p.dbg == 2) return wgs == 5 ? launch_tc_ta_n<5, 4, false, 0, true>(p, sms, st) : launch_tc_ta_n<4, 4, false, 0, true>(p, sms, st);
   if (bias && wgs == 5 && poly != kDefaultPoly) {
     switch (poly) {
