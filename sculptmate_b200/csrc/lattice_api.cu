@@ -18,11 +18,13 @@ struct TcEnv {
   int wait_ns = 2000;
   int trace = 0, stagger = 0, tokens = 0, poly = 0;
   char variant = 0;
+  bool axis_tables = true;  // SMB_NO_AXIS_TABLES: the producers interpolate per tile (the round-1 path, kept as the no-scratch fallback)
 };
 static const TcEnv& tc_env() {
   static const TcEnv env = [] {
     TcEnv e;
     if (const char* v = getenv("SMB_TC_WAITNS")) e.wait_ns = atoi(v);
+    if (getenv("SMB_NO_AXIS_TABLES")) e.axis_tables = false;
 #ifdef SMB_DEV_VARIANTS
     if (const char* v = getenv("SMB_TC_TRACE")) e.trace = atoi(v);
     if (const char* v = getenv("SMB_TC_TA_STAGGER")) e.stagger = atoi(v);
@@ -163,7 +165,7 @@ static int query_lattice_tc_impl(const float* planes_q, const void* decoder_blob
   const size_t tab_floats = ((size_t)nx + (size_t)R) * cfg->Hp * kHid;
   float* tabs = nullptr;
   keep_async_scratch(dev);
-  if (!getenv("SMB_NO_AXIS_TABLES") && cudaMallocAsync(reinterpret_cast<void**>(&tabs), tab_floats * sizeof(float), st) == cudaSuccess) {
+  if (tc_env().axis_tables && cudaMallocAsync(reinterpret_cast<void**>(&tabs), tab_floats * sizeof(float), st) == cudaSuccess) {
     p.t1 = tabs;
     p.t2 = tabs + (size_t)nx * cfg->Hp * kHid;
     const long long items = (long long)tab_floats / 4;
