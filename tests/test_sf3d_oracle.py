@@ -107,3 +107,44 @@ def test_static_topology_of_the_mirror_helper(tmp_path, golden):
     assert h.normalize_grid_deformation(torch.zeros(3, 3)).abs().max() == 0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         h(torch.zeros(h.grid_vertices.shape[0], 1), None)  # forward needs the CUDA library
+
+
+def test_lattice_table_decomposition_equals_the_first_linear(golden):
+    """The identity csrc/tetgrid_tc.cu is built on, checked on the CPU against the reference-pinned oracle: at the vertices
+    of a lattice-ordered grid (sf3d/models/isosurface.py detect_lattice) the first Linear of a head on the concatenated
+    plane features (sf3d/system.py:170-198, network.py:158-178) is the sum of three TWO-index tables,
+        W0 . [f_xy; f_xz; f_yz] + b0 = C[a][b] + T1[a][c] + T2[b][c],
+    each built from n^2 bilinear interpolations of ONE plane.  Axes deliberately permuted and unevenly sized."""
+    from sculptmate_b200.sf3d.models.isosurface import detect_lattice
+
+    g = golden("sf3d_path.npz")
+    sd = _sd(g)
+    W, b = so.heads_from_state_dict(sd, "density")
+    W0, b0 = W[0].astype(np.float64), b[0].astype(np.float64)
+    tp = g["triplane"].astype(np.float32)
+    Cp = tp.shape[1]
+    ax = [np.linspace(0.02, 0.97, k).astype(np.float32) for k in (5, 7, 6)]  # x, y, z coordinate lists in grid units
+    zz, xx, yy = np.meshgrid(ax[2], ax[0], ax[1], indexing="ij")  # vertex order: z slow, x mid, y fast
+    verts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], -1).astype(np.float32)
+    ext, sdim, coords = detect_lattice(verts)
+    assert ext == (6, 5, 7) and sdim == (2, 0, 1)
+    r = np.float32(0.87)
+    pos = (verts * (r - (-r)) + (-r)).astype(np.float32)  # scale_tensor(grid, (0,1), bbox)
+    feats = fo.sf3d_query_triplane(pos, tp, 0.87).astype(np.float64)
+    direct = feats @ W0.T + b0  # (N, 64)
+
+    def table(lp, lq):
+        """Entries (ip, iq) of the table of lattice indices (lp, lq): the ONE plane both spatial axes belong to."""
+        dp, dq = sdim[lp], sdim[lq]
+        plane = dp + dq - 1  # {x,y} -> 0, {x,z} -> 1, {y,z} -> 2
+        P = np.zeros((ext[lp] * ext[lq], 3), np.float32)
+        ip, iq = np.meshgrid(np.arange(ext[lp]), np.arange(ext[lq]), indexing="ij")
+        P[:, dp] = coords[lp][ip.ravel()]
+        P[:, dq] = coords[lq][iq.ravel()]
+        P = (P * (r - (-r)) + (-r)).astype(np.float32)  # the third coordinate is irrelevant for this plane
+        f = fo.sf3d_query_triplane(P, tp, 0.87).astype(np.float64)[:, plane * Cp : (plane + 1) * Cp]
+        return (f @ W0[:, plane * Cp : (plane + 1) * Cp].T).reshape(ext[lp], ext[lq], -1)
+
+    C, T1, T2 = table(0, 1) + b0, table(0, 2), table(1, 2)
+    total = (C[:, :, None, :] + T1[:, None, :, :] + T2[None, :, :, :]).reshape(-1, W0.shape[0])
+    assert np.abs(total - direct).max() < 1e-6
