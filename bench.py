@@ -335,7 +335,7 @@ def sf3d_measure(dev, rank: int, world: int, steps: int, warmup: int, tet_n: int
                      "flop_per_point": sf3d_flop, "points_kernel_ms": float(np.mean(kpts)),
                      "note": "algorithmic FLOPs of the reference's two heads (layer 0 counted although the lattice path replaces it by table sums); "
                              "points_kernel_ms = the arbitrary-position kernel on the same vertices (gather-bound: 12 taps x 40 channels per point)"},
-        "gpu_launches": 9 * steps * world,  # own kernels per call: channels-last, tables, tet-grid MLP, deform, edge / tet count, totals, emit verts / faces
+        "gpu_launches": 9 * steps * world,  # own kernels per call: channels-last, tables, tet-grid MLP (incl. density - threshold), deform, edge / tet count, totals, emit verts / faces
     }
     if with_cpu and rank == 0:
         # the reference's CPU path for this config, restated (oracle/sf3d_oracle.py: query_triplane align_corners=True ->

@@ -387,12 +387,15 @@ int smb_mtet_deform(const float* base, const float* deform, float scale, int64_t
  *   decoder_blobs[h], layouts[h]   the head packed with smb_decoder_pack_host: Linear(120,64), (n_hidden-1) x Linear(64,64),
  *                   last Linear padded to 4 rows (n_out[h] = 1..3 of them are read)
  *   exp_act[h], out_bias[h]        1: out = exp(x + out_bias) (trunc_exp forward, config.yaml density head); 0: out = x
+ *   out_sub (may be NULL)          out_sub[h] is subtracted from an exp-activated head AFTER the activation, in fp32: the caller's
+ *                   `density - isosurface_threshold` (sf3d/system.py:155) without a separate elementwise pass
  *   axis_u[k]       device array (extents[k]) of lattice index k's coordinate already mapped to (-1,1) with the reference's
  *                   own scale_tensor ops; spatial_dim[k] in {0,1,2} says which of x,y,z it is (a permutation)
  *   outs[h]         (extents[0]*extents[1]*extents[2], n_out[h]) fp32, vertex order of the grid */
 int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int align_corners, int nheads, const void* const* decoder_blobs,
                          const smb_decoder_layout* const* layouts, const int* n_out, const int* exp_act, const float* out_bias,
-                         const float* const* axis_u, const int* extents, const int* spatial_dim, float* const* outs, void* stream);
+                         const float* out_sub, const float* const* axis_u, const int* extents, const int* spatial_dim,
+                         float* const* outs, void* stream);
 
 /* ------------------------------------------------------------ volume rendering
  * The two elementwise stages of TriplaneNeRFRenderer._forward (tsr/models/nerf_renderer.py:93-152) around the field

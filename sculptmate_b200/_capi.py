@@ -102,7 +102,7 @@ SIGNATURES = {
     ),
     "smb_query_tetgrid_tc": (
         c_int,
-        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "smb_mc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "smb_mc_count": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),

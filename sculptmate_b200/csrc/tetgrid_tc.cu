@@ -45,6 +45,7 @@ struct TgHead {
   int n_out;                        // 1 or 3
   int exp_act;                      // 1: out = exp(x + out_bias) (trunc_exp forward); 0: out = x
   float out_bias;
+  float out_sub;  // subtracted after the activation (the caller's `density - threshold`, sf3d/system.py:155); 0 = off
 };
 struct TgParams {
   TgHead head[kTgMaxHeads];
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kTgWG * 128 + 128, 1) tetgrid_tc_kernel(TgPara
           const long long row = ((long long)(tg.a0 + la) * p.nB + tg.b0 + lb) * p.nC + tg.c0 + lc;
           const float* hb = hwf + 4 * kHid;
           float o0 = d0.x + d0.y + hb[0];
-          if (H.exp_act) o0 = expf(__fadd_rn(o0, H.out_bias));
+          if (H.exp_act) o0 = __fsub_rn(expf(__fadd_rn(o0, H.out_bias)), H.out_sub);
           if (!wide) {
             H.out[row] = o0;
           } else {
@@ -415,8 +416,8 @@ using namespace smb;
 // See include/sculptmate_b200.h.
 extern "C" int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int align_corners, int nheads,
                                     const void* const* decoder_blobs, const smb_decoder_layout* const* layouts, const int* n_out,
-                                    const int* exp_act, const float* out_bias, const float* const* axis_u, const int* extents,
-                                    const int* spatial_dim, float* const* outs, void* stream) {
+                                    const int* exp_act, const float* out_bias, const float* out_sub, const float* const* axis_u,
+                                    const int* extents, const int* spatial_dim, float* const* outs, void* stream) {
   if (!planes_cl || !decoder_blobs || !layouts || !n_out || !exp_act || !out_bias || !axis_u || !extents || !spatial_dim || !outs)
     return SMB_ERR_BAD_ARG;
   if (nheads < 1 || nheads > kTgMaxHeads || Hp < 1 || Wp < 1) return SMB_ERR_BAD_ARG;
@@ -486,6 +487,7 @@ extern "C" int smb_query_tetgrid_tc(const float* planes_cl, int Hp, int Wp, int 
     H.n_out = n_out[h];
     H.exp_act = exp_act[h];
     H.out_bias = out_bias[h];
+    H.out_sub = out_sub ? out_sub[h] : 0.0f;
   }
   {
     const long long maxent = nA * nB > nA * nC ? (nA * nB > nB * nC ? nA * nB : nB * nC) : (nA * nC > nB * nC ? nA * nC : nB * nC);

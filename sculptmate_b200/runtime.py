@@ -902,10 +902,11 @@ def get_sf3d_head_decoder_pack(decoder: torch.nn.Module, name: str, device: torc
 
 def query_tetgrid_tc(
     planes: ScenePlanes, packs: Sequence[DecoderPack], n_out: Sequence[int], exp_act: Sequence[bool], out_bias: Sequence[float],
-    axis_u: Sequence[torch.Tensor], spatial_dim: Sequence[int], align_corners: bool = True,
+    axis_u: Sequence[torch.Tensor], spatial_dim: Sequence[int], align_corners: bool = True, out_sub: Optional[Sequence[float]] = None,
 ) -> List[torch.Tensor]:
     """Heads of a MaterialMLP at every vertex of a lattice-ordered grid (``smb_query_tetgrid_tc``): ``axis_u[k]`` is the
     (-1,1) coordinate of lattice index k (slow, mid, fast), ``spatial_dim[k]`` the spatial axis it runs along.
+    ``out_sub[h]`` (optional) is subtracted from an exp-activated head after the activation (``density - threshold``).
     Returns one (N, n_out[h]) tensor per head."""
     if planes.planes_cl is None:
         raise ValueError("the lattice tet-grid path reads the fp32 channels-last planes (prepare_planes_cl)")
@@ -923,6 +924,7 @@ def query_tetgrid_tc(
             _capi.load().smb_query_tetgrid_tc(
                 planes.planes_cl.data_ptr(), planes.Hp, planes.Wp, int(bool(align_corners)), nh, blobs, lays,
                 (ip * nh)(*[int(k) for k in n_out]), (ip * nh)(*[int(bool(e)) for e in exp_act]), (fp * nh)(*[float(b) for b in out_bias]),
+                (fp * nh)(*[float(x) for x in out_sub]) if out_sub is not None else None,
                 (vp * 3)(*[a.data_ptr() for a in ax]), (ip * 3)(*ext), (ip * 3)(*[int(d) for d in spatial_dim]),
                 (vp * nh)(*[o.data_ptr() for o in outs]), _stream_ptr(dev),
             ),

@@ -138,6 +138,7 @@ class SF3D(BaseModule):
             triplane = triplanes[i]
             dev = triplane.device
             grid_vertices = self._positions(dev)  # scale_tensor(grid, points_range, bbox)   :147-151
+            level_done = False
             if self.decoder.cuda_heads_supported():
                 tc = self.cfg.precision == "tc"
                 lattice = tc and h.lattice is not None and self.cfg.lattice_path
@@ -153,7 +154,9 @@ class SF3D(BaseModule):
                          runtime.get_sf3d_head_decoder_pack(self.decoder, "vertex_offset", dev)],
                         n_out=(1, 3), exp_act=(True, False), out_bias=(float(dens_spec.out_bias), 0.0),
                         axis_u=self._lattice_axis_u(dev), spatial_dim=h.lattice[1], align_corners=True,
+                        out_sub=(float(self.cfg.isosurface_threshold), 0.0),  # density - threshold (:155) in the kernel's epilogue
                     )
+                    level_done = True
                     if float(offs.out_bias) != 0.0:
                         deform = deform + float(offs.out_bias)
                 elif tc:
@@ -172,7 +175,7 @@ class SF3D(BaseModule):
                 values = self.query_triplane(grid_vertices, triplane)
                 decoded = self.decoder(values, include=["vertex_offset", "density"])
                 density, deform = decoded["density"], decoded["vertex_offset"].squeeze(0)
-            sdf = density - self.cfg.isosurface_threshold  # :155
+            sdf = density if level_done else density - self.cfg.isosurface_threshold  # :155
             # scale_tensor(mesh.v_pos, points_range, bbox) (:162-164) runs inside the vertex kernel: the same fp32 operations
             mesh = h(sdf.view(-1, 1), deform.view(-1, 3) if deform is not None else None, v_pos_affine=self._v_pos_affine(dev))
             meshes.append(mesh)
