@@ -13,17 +13,22 @@
 //   K2 mc_count  : one thread per word, one CTA per chunk of 1024 words of a plane:
 //                  crossing masks by XOR of neighbouring sign masks, owned-vertex and
 //                  triangle counts (popc / case table), CTA-wide exclusive scan; writes
-//                  a 16-byte record per word + the chunk totals.
-//   K3 mc_totals : one CTA turns chunk totals into chunk bases in canonical order.
-//   K4 mc_emit   : a warp takes 32 consecutive words, compacts their crossing samples and
-//                  their active cells across the warp (popc + warp scan), and then works
-//                  one ITEM per lane: a crossing sample writes its <= 3 owned vertices
-//                  (each lattice edge is owned by exactly one sample -> no duplicates, no
-//                  atomics), an active cell writes its <= 5 triangles; vertex ids of
-//                  neighbouring words come from prefix[word] + popc(mask & lanes_below).
-//                  The surface is sparse (a few % of the cells), so lane-per-item keeps the
-//                  SIMT lanes full where lane-per-sample left > 80 % of them idle.  Density
-//                  is re-read only at the two end points of crossing edges.
+//                  a 32-byte record per word, the chunk totals and the weight of every
+//                  256-word unit.
+//   K3 mc_totals : one CTA turns chunk totals into chunk bases in canonical order and builds
+//                  mc_emit's work list (non-empty units, heavy ones cut into slices,
+//                  heaviest first).
+//   K4 mc_emit   : a CTA draws work items from a ticket counter; per item it stages what the
+//                  unit's 256 words and their neighbours will be asked for in shared memory
+//                  (one round of independent loads), scans the per-word item counts, and its
+//                  eight warps work through the unit's crossing samples and active cells in
+//                  groups of 32, ONE ITEM PER LANE: a crossing sample writes its <= 3 owned
+//                  vertices (each lattice edge is owned by exactly one sample -> no duplicates,
+//                  no atomics on the output), an active cell writes its <= 5 triangles, vertex
+//                  ids from the staged prefixes + popc(mask & lanes_below).  The surface is
+//                  sparse (a few % of the cells), so lane-per-item keeps the SIMT lanes full
+//                  where lane-per-sample left > 80 % of them idle.  Density is re-read only at
+//                  the two end points of crossing edges.
 //
 // Canonical order (identical to oracle/mc_oracle.c): vertices by x-plane i, inside a
 // plane first the in-plane crossings by (j,k) with the y-edge before the z-edge of a
